@@ -1,0 +1,245 @@
+/*
+ * papc_b200.h -- C ABI of the B200-native point-cloud primitive library.
+ *
+ * This is the drop-in boundary for ONE hot path of AgentMaker/PAPC: the PointNet++
+ * SetAbstraction forward and the PointPillars pillar encode.  The reference has no FFI
+ * layer -- its "ops" are plain Python callables -- so every entry point below cites the
+ * reference callable (file:line under /root/reference) whose computation it replaces.
+ * Short names used in the citations:
+ *   layers.py  = PAPC/models/layers/pointnet2_basic_layers.py
+ *   pc_ops.py  = PAPC/models/detect/pointpillars/libs/ops/point_cloud/point_cloud_ops.py
+ *   pillars.py = PAPC/models/detect/pointpillars/models/bones/pillars.py
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++/torch types.
+ *   - Every pointer is a DEVICE pointer on the current CUDA device unless the parameter
+ *     name ends in _host.  The caller allocates every input, output and workspace buffer;
+ *     the library never allocates, frees or retains memory.  Inputs are read-only.
+ *   - Tensors are dense row-major in the stated shape.
+ *   - `stream` is a cudaStream_t passed as void*.  Calls only enqueue work (asynchronous).
+ *   - Return value: PAPC_OK (0) or a negative papc_status.  Invalid arguments are rejected
+ *     before anything is launched.  papc_status_string() names a code.
+ *   - Re-entrant: no global mutable state; concurrent calls on distinct streams/workspaces
+ *     are safe.
+ */
+#ifndef PAPC_B200_H_
+#define PAPC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PAPC_ABI_VERSION 1
+
+typedef void *papc_stream_t; /* cudaStream_t */
+
+typedef enum papc_status {
+    PAPC_OK = 0,
+    PAPC_EINVAL = -1,       /* bad shape / null pointer / unsupported flag value          */
+    PAPC_EWORKSPACE = -2,   /* workspace too small (see the matching *_workspace_bytes)     */
+    PAPC_ECUDA = -3,        /* a CUDA runtime call failed; papc_last_cuda_error() has it    */
+    PAPC_EUNSUPPORTED = -4  /* valid request outside what this build implements             */
+} papc_status;
+
+const char *papc_status_string(int status);
+int papc_abi_version(void);
+/* cudaError_t of the most recent PAPC_ECUDA on this host thread (0 if none). */
+int papc_last_cuda_error(void);
+/* Number of CUDA kernels this library has launched from the calling host thread (monotonic;
+ * diagnostics for bench.py's gpu_launches -- memsets are not counted). */
+uint64_t papc_launch_count(void);
+
+/* ----------------------------------------------------------------------------------------
+ * A1  square_distance(src, dst)                                    layers.py:26-40
+ *     src [B,N,3], dst [B,M,3] -> out [B,N,M];  out = (-2*dot + |src|^2) + |dst|^2 with
+ *     dot = fma(z,z', fma(y,y', x*x')) and |.|^2 = (x*x + y*y) + z*z  (the pinned arithmetic
+ *     of oracle/papc_oracle.c).  C must be 3.
+ */
+int papc_square_distance_f32(const float *src, const float *dst, int B, int N, int M,
+                             float *out, papc_stream_t stream);
+
+/* A2  index_points(points, idx)                                    layers.py:43-62
+ *     points [B,N,C], idx [B,M] int64 (flatten trailing index dims into M) -> out [B,M,C].
+ *     Indices outside [0,N) are a caller error (the reference raises IndexError); they are
+ *     clamped so the kernel never reads out of bounds.
+ */
+int papc_gather_f32(const float *points, const int64_t *idx, int B, int N, int C, int M,
+                    float *out, papc_stream_t stream);
+
+/* A3  farthest_point_sample(xyz, npoint)                           layers.py:65-95
+ *     xyz [B,N,3] -> out_idx [B,npoint] int64.  start_idx [B] replaces the reference's
+ *     paddle.randint draw (:76); init_dist is the initial running distance (the reference
+ *     uses 1.0, :75 -- NOT 1e10; must be >= 0).  out_new_xyz (nullable) [B,npoint,3] receives
+ *     xyz[b, out_idx[b,i]] (the index_points call that always follows, :144 / :258).
+ *     workspace: papc_fps_workspace_bytes(B,N) bytes (0 for N <= 8192), may be NULL then.
+ */
+size_t papc_fps_workspace_bytes(int B, int N);
+int papc_fps_f32(const float *xyz, int B, int N, int npoint, const int64_t *start_idx,
+                 float init_dist, int64_t *out_idx, float *out_new_xyz, void *workspace,
+                 size_t workspace_bytes, papc_stream_t stream);
+
+/* A4  query_ball_point(radius, nsample, xyz, new_xyz)              layers.py:98-126
+ *     xyz [B,N,3], new_xyz [B,S,3] -> out_idx [B,S,nsample]: the nsample lowest indices j with
+ *     NOT(square_distance(new_xyz, xyz)[j] > radius2), ascending, padded with the first one.
+ *     radius2 must be float32(double(radius)**2) (:112).  An empty ball yields N in every slot
+ *     and increments *empty_count (nullable int32 device counter, caller zeroes it); the
+ *     reference fails with IndexError in that case.  idx_bits selects int64 (64, the
+ *     reference dtype) or int32 (32, used by the fused SetAbstraction path) output.
+ */
+int papc_ball_query_f32(const float *xyz, const float *new_xyz, int B, int N, int S,
+                        float radius2, int nsample, void *out_idx, int idx_bits,
+                        int32_t *empty_count, papc_stream_t stream);
+
+/* A5  the gather+centre+concat of sample_and_group                 layers.py:146-151, 263-267
+ *     out [B,S,K,3+D]: PAPC_XYZ_FIRST  -> [xyz[idx]-new_xyz, feats[idx]]  (SSG, :151)
+ *                      PAPC_FEATS_FIRST-> [feats[idx], xyz[idx]-new_xyz]  (MSG, :267)
+ *     feats may be NULL (D=0).  idx is int64 [B,S,K].
+ */
+enum { PAPC_XYZ_FIRST = 0, PAPC_FEATS_FIRST = 1 };
+int papc_group_gather_f32(const float *xyz, const float *new_xyz, const float *feats,
+                          const int64_t *idx, int B, int N, int S, int K, int D, int order,
+                          float *out, papc_stream_t stream);
+
+/* ----------------------------------------------------------------------------------------
+ * A7/A8  the grouped shared MLP: (Conv2D 1x1 + bias -> BatchNorm2D -> ReLU) x L -> max over
+ *        the K neighbours.                                          layers.py:214-219, 271-276
+ *
+ * Rows are the M = G*K grouped neighbours (G = B*S groups of K consecutive rows).  The input
+ * is either an explicit grouped tensor or -- the fused path, which never materialises
+ * [B,S,K,3+D] -- the (xyz, new_xyz, feats, idx) tuple it would be gathered from.
+ */
+#define PAPC_MAX_MLP_LAYERS 8
+enum { PAPC_BN_BATCH = 0,    /* training-mode statistics over all M rows (biased variance);   */
+                             /* what the reference's unregistered SA layers always do (A7)   */
+       PAPC_BN_RUNNING = 1,  /* normalise with running_mean / running_var                    */
+       PAPC_BN_NONE = 2 };   /* no normalisation (PFNLayer use_norm=False only, pillars.py:26-27) */
+enum { PAPC_OUT_BSC = 0,     /* out [B,S,Cout]  (channels-last)                               */
+       PAPC_OUT_BCS = 1 };   /* out [B,Cout,S]  (the reference's layout, layers.py:219)       */
+
+typedef struct papc_group_source {
+    const float *grouped; /* [G,K,cin] explicit rows, or NULL to gather:                     */
+    const float *xyz;     /* [B,N,3]                                                         */
+    const float *new_xyz; /* [B,S,3] subtracted from the xyz channels; NULL = no centring    */
+    const float *feats;   /* [B,N,D] or NULL (D = 0)                                         */
+    const int32_t *idx;   /* [B,S,K] int32, or NULL = identity (group_all: row k = point k)  */
+    int32_t B, N, S, K, D;
+    int32_t order;        /* PAPC_XYZ_FIRST / PAPC_FEATS_FIRST                               */
+} papc_group_source;
+
+typedef struct papc_mlp_layer {
+    const float *weight;       /* [cout,cin]  == Conv2D.weight [cout,cin,1,1]                */
+    const float *bias;         /* [cout] or NULL                                             */
+    const float *gamma;        /* [cout] BatchNorm weight                                    */
+    const float *beta;         /* [cout] BatchNorm bias                                      */
+    const float *running_mean; /* [cout], read when bn_mode == PAPC_BN_RUNNING               */
+    const float *running_var;  /* [cout]                                                     */
+    float *batch_mean;         /* [cout] out, nullable: batch mean (PAPC_BN_BATCH)           */
+    float *batch_var;          /* [cout] out, nullable: biased batch variance                */
+    int32_t cout;
+    int32_t reserved;
+} papc_mlp_layer;
+
+typedef struct papc_mlp {
+    int32_t num_layers; /* 1..PAPC_MAX_MLP_LAYERS */
+    int32_t cin;        /* 3+D for a gathered source */
+    int32_t bn_mode;
+    float eps;          /* 1e-5 for BatchNorm2D (layers.py:190) */
+    papc_mlp_layer layers[PAPC_MAX_MLP_LAYERS];
+} papc_mlp;
+
+size_t papc_sa_mlp_workspace_bytes(const papc_group_source *src, const papc_mlp *mlp);
+/* out: [B,S,cout_last] or [B,cout_last,S] per out_layout. */
+int papc_sa_mlp_f32(const papc_group_source *src, const papc_mlp *mlp, float *out,
+                    int out_layout, void *workspace, size_t workspace_bytes,
+                    papc_stream_t stream);
+
+/* Step-wise form of the same computation, for batch-sharded multi-GPU runs where the
+ * BatchNorm statistics of each layer are summed across ranks between the steps
+ * (SURVEY.md 8e).  papc_sa_mlp_f32 == for each layer { layer_forward; stats_reduce;
+ * bn_scale_shift } then pool_finish.
+ *
+ *   papc_mlp_layer_forward_f32: y = W * act(x) + bias for one layer.
+ *     layer 0: src != NULL (x, in_scale, in_shift ignored).
+ *     later  : x [M,cin] = previous layer's pre-BN output, act(v) = relu(in_scale*v+in_shift).
+ *     y [M,cout] (nullable when pooling) receives the pre-BN output; pool_max / pool_min
+ *     [M/K,cout] (nullable) receive the per-group extrema of y (valid because BN+ReLU is
+ *     monotone per channel, so max_k relu(bn(y_k)) = relu(bn(max_k y_k or min_k y_k))).
+ *     stats_partial: double [papc_mlp_stats_partial_rows(M), 2, cout] per-tile sums of y, y^2.
+ *   papc_mlp_stats_reduce_f64: fixed-order reduction -> sums double [2,cout].
+ *   papc_bn_scale_shift_f32: sums (already summed over ranks) + count -> scale, shift (and
+ *     optionally mean / biased var).
+ *   papc_sa_pool_finish_f32: out = relu(scale * (scale>=0 ? pool_max : pool_min) + shift).
+ */
+int64_t papc_mlp_stats_partial_rows(int64_t M);
+int papc_mlp_layer_forward_f32(const papc_group_source *src, const float *x,
+                               const float *in_scale, const float *in_shift, int64_t M,
+                               int32_t cin, int32_t cout, int32_t K, const float *weight,
+                               const float *bias, float *y, float *pool_max, float *pool_min,
+                               double *stats_partial, papc_stream_t stream);
+int papc_mlp_stats_reduce_f64(const double *stats_partial, int64_t partial_rows, int32_t cout,
+                              double *sums, papc_stream_t stream);
+int papc_bn_scale_shift_f32(const double *sums, double count, const float *gamma,
+                            const float *beta, float eps, int32_t cout, float *scale,
+                            float *shift, float *mean_out, float *var_out,
+                            papc_stream_t stream);
+int papc_bn_running_scale_shift_f32(const float *running_mean, const float *running_var,
+                                    const float *gamma, const float *beta, float eps,
+                                    int32_t cout, float *scale, float *shift,
+                                    papc_stream_t stream);
+int papc_sa_pool_finish_f32(const float *pool_max, const float *pool_min, const float *scale,
+                            const float *shift, int32_t B, int32_t S, int32_t cout,
+                            float *out, int out_layout, papc_stream_t stream);
+
+/* ----------------------------------------------------------------------------------------
+ * A9  points_to_voxel(points, voxel_size, coors_range, max_points, reverse_index, max_voxels)
+ *                                                                   pc_ops.py:106-166
+ *     points [N,F] (F >= 3) -> voxels [max_voxels,max_points,F] (zero padded; every element is
+ *     written), coors [max_voxels,3] int32 ((z,y,x) when reverse_index), num_points
+ *     [max_voxels] int32, *voxel_num int32 (device).  Rows >= *voxel_num are zero; the caller
+ *     slices [:voxel_num] as pc_ops.py:161-163 does.  Reproduces the sequential semantics
+ *     deterministically: first-come voxel numbering, per-voxel points in input order capped at
+ *     max_points, and the `break` at the first NEW cell once max_voxels exist (which drops
+ *     every later point).  voxel_size_host [3], coors_range_host [6] are HOST arrays.
+ */
+size_t papc_voxelize_workspace_bytes(int N, const float *voxel_size_host,
+                                     const float *coors_range_host, int max_voxels);
+int papc_voxelize_f32(const float *points, int N, int F, const float *voxel_size_host,
+                      const float *coors_range_host, int max_points, int reverse_index,
+                      int max_voxels, float *voxels, int32_t *coors, int32_t *num_points,
+                      int32_t *voxel_num, void *workspace, size_t workspace_bytes,
+                      papc_stream_t stream);
+
+/* A10 PillarFeatureNet.forward with a single (last) PFNLayer          pillars.py:79-108, 29-41
+ *     features [P,T,F] (F >= 3), num_voxels [P] int32, coors [P,4] int32 (b,z,y,x) -> out [P,cout].
+ *     Decorations [features, f_cluster(3), f_center(2)] (:82-95), padding rows zeroed (:99-102),
+ *     Linear(F+5 -> cout, weight [F+5,cout], bias nullable) -> BatchNorm1D over all P*T rows
+ *     (padding rows included, as the reference does) -> ReLU -> max over T.
+ *     bn_mode as above; eps 1e-3 in the reference (:24).  num_valid (nullable int32 device
+ *     scalar): only the first *num_valid pillars are processed (device-side voxel_num).
+ */
+size_t papc_pfn_workspace_bytes(int P, int cout);
+int papc_pfn_f32(const float *features, const int32_t *num_voxels, const int32_t *coors, int P,
+                 int T, int F, float vx, float vy, float x_offset, float y_offset,
+                 const float *weight, const float *bias, const float *gamma, const float *beta,
+                 const float *running_mean, const float *running_var, int bn_mode, float eps,
+                 int cout, const int32_t *num_valid, float *out, float *batch_mean,
+                 float *batch_var, void *workspace, size_t workspace_bytes,
+                 papc_stream_t stream);
+
+/* A11 PointPillarsScatter.forward                                     pillars.py:121-142
+ *     voxel_features [P,C], coords [P,4] int32 (b,z,y,x) -> canvas [batch,C,ny,nx]; every canvas
+ *     element is written exactly once (zero where no pillar).  Duplicate (b,y,x) keep the last
+ *     pillar, as NumPy fancy assignment does.  num_valid as above.
+ */
+size_t papc_pillar_scatter_workspace_bytes(int batch, int ny, int nx);
+int papc_pillar_scatter_f32(const float *voxel_features, const int32_t *coords, int P, int C,
+                            int batch, int ny, int nx, const int32_t *num_valid, float *canvas,
+                            void *workspace, size_t workspace_bytes, papc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PAPC_B200_H_ */

@@ -145,8 +145,10 @@ class Conv2D1x1:
     def __call__(self, x, acc=np.float64):
         # x [B,Cin,H,W] -> [B,Cout,H,W]; accumulate in float64 (or float32 for the timed port)
         w = self.weight.reshape(self.weight.shape[0], -1)
-        y = np.einsum("oc,bchw->bohw", w.astype(acc), x.astype(acc), optimize=True)
-        y = y + self.bias.astype(acc).reshape(1, -1, 1, 1)
+        B, Cin, H, W = x.shape
+        # a 1x1 convolution is a [cout,cin] x [cin,H*W] matrix product per batch item (BLAS)
+        y = np.matmul(w.astype(acc), np.ascontiguousarray(x).reshape(B, Cin, H * W).astype(acc))
+        y = y.reshape(B, -1, H, W) + self.bias.astype(acc).reshape(1, -1, 1, 1)
         return y.astype(F32)
 
 

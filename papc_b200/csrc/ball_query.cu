@@ -1,0 +1,285 @@
+// ball_query.cu -- square_distance, index_points, query_ball_point and the group gather
+// (reference: layers.py:26-62, 98-126, 146-151, 263-267) for sm_100a.
+//
+// query_ball_point never materialises the reference's [B,S,N] distance matrix nor sorts it:
+// "the nsample lowest in-radius indices, ascending" is an in-order scan with a warp ballot +
+// prefix popcount compaction.  One warp per query point; all warps of a CTA share one cloud
+// whose xyz block is staged into shared memory by a TMA bulk copy (cp.async.bulk, completion
+// on an mbarrier) -- chunked, so any N works with a fixed 28 KB of shared memory.
+#include "common.cuh"
+
+namespace papc {
+
+// ------------------------------------------------------------------ mbarrier / bulk copy PTX
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t phase) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(phase)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a lost transaction traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
+    for (uint32_t spin = 0; !mbar_try_wait(bar, phase); ++spin)
+        if (spin > (1u << 22)) __trap();
+}
+// 1-D TMA bulk copy global -> shared; size and both addresses must be multiples of 16 bytes.
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes,
+                                         uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// ------------------------------------------------------------------ square_distance
+__global__ void __launch_bounds__(256)
+square_distance_kernel(const float *__restrict__ src, const float *__restrict__ dst, int N, int M,
+                       float *__restrict__ out, size_t total) {
+    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; e < total; e += stride) {
+        const size_t j = e % M;
+        const size_t bi = e / M;  // b*N + i
+        const size_t b = bi / N;
+        const float *q = src + bi * 3;
+        const float *p = dst + (b * M + j) * 3;
+        const float qx = q[0], qy = q[1], qz = q[2];
+        const float px = p[0], py = p[1], pz = p[2];
+        out[e] = sqdist_expanded(qx, qy, qz, sq3(qx, qy, qz), px, py, pz, sq3(px, py, pz));
+    }
+}
+
+// ------------------------------------------------------------------ index_points
+template <typename VecT>
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const float *__restrict__ points, const int64_t *__restrict__ idx, int N,
+                   int Cv /* row length in VecT units */, int M, size_t total,
+                   float *__restrict__ out) {
+    const VecT *pin = reinterpret_cast<const VecT *>(points);
+    VecT *pout = reinterpret_cast<VecT *>(out);
+    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; e < total; e += stride) {
+        const size_t c = e % Cv;
+        const size_t bm = e / Cv;  // b*M + m
+        const size_t b = bm / M;
+        long long n = idx[bm];
+        n = n < 0 ? 0 : (n >= N ? N - 1 : n);
+        pout[e] = pin[(b * N + (size_t)n) * Cv + c];
+    }
+}
+
+// ------------------------------------------------------------------ query_ball_point
+constexpr int kBqWarps = 8;
+constexpr int kBqChunk = 2048;  // points per shared-memory stage: 24 KB xyz + 8 KB |p|^2
+
+template <typename IdxT>
+__global__ void __launch_bounds__(kBqWarps * 32)
+ball_query_kernel(const float *__restrict__ xyz, const float *__restrict__ new_xyz, int N, int S,
+                  float radius2, int K, IdxT *__restrict__ out_idx,
+                  int32_t *__restrict__ empty_count) {
+    __shared__ __align__(128) float s_p[kBqChunk * 3];  // AoS xyz of the current chunk
+    __shared__ float s_n[kBqChunk];                     // |p|^2
+    __shared__ __align__(8) uint64_t s_bar;
+
+    const int b = blockIdx.y;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int s = blockIdx.x * kBqWarps + warp;
+    const bool active = s < S;
+    const float *cloud = xyz + (size_t)b * N * 3;
+
+    float qx = 0.f, qy = 0.f, qz = 0.f, qn = 0.f;
+    if (active) {
+        const float *q = new_xyz + ((size_t)b * S + s) * 3;
+        qx = q[0];
+        qy = q[1];
+        qz = q[2];
+        qn = sq3(qx, qy, qz);
+    }
+    IdxT *out = out_idx + ((size_t)b * S + (active ? s : 0)) * K;
+
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    int cnt = 0;      // in-radius points found so far (may exceed K)
+    int first = -1;   // lowest in-radius index
+    uint32_t phase = 0;
+    for (int base = 0; base < N; base += kBqChunk) {
+        const int n = min(kBqChunk, N - base);
+        const float *gsrc = cloud + (size_t)base * 3;
+        const uint32_t bytes = (uint32_t)n * 12u;
+        // TMA bulk copy needs 16-byte aligned source and size; otherwise plain coalesced loads.
+        const bool tma_ok = ((reinterpret_cast<uintptr_t>(gsrc) & 15u) == 0) && ((bytes & 15u) == 0);
+        if (tma_ok) {
+            if (tid == 0) {
+                mbar_expect_tx(&s_bar, bytes);
+                bulk_g2s(s_p, gsrc, bytes, &s_bar);
+            }
+            mbar_wait(&s_bar, phase);
+            phase ^= 1;
+        } else {
+            for (int i = tid; i < n * 3; i += kBqWarps * 32) s_p[i] = gsrc[i];
+            __syncthreads();
+        }
+        for (int j = tid; j < n; j += kBqWarps * 32)
+            s_n[j] = sq3(s_p[j * 3 + 0], s_p[j * 3 + 1], s_p[j * 3 + 2]);
+        __syncthreads();
+
+        if (active && cnt < K) {
+            for (int j0 = 0; j0 < n; j0 += 32) {
+                const int j = j0 + lane;
+                bool in = false;
+                if (j < n) {
+                    const float d = sqdist_expanded(qx, qy, qz, qn, s_p[j * 3 + 0], s_p[j * 3 + 1],
+                                                    s_p[j * 3 + 2], s_n[j]);
+                    in = !(d > radius2);  // layers.py:112 masks "> r^2" OUT
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, in);
+                if (m) {
+                    if (first < 0) first = base + j0 + __ffs(m) - 1;
+                    const int pos = cnt + __popc(m & ((1u << lane) - 1u));
+                    if (in && pos < K) out[pos] = (IdxT)(base + j);
+                    cnt += __popc(m);
+                    if (cnt >= K) break;
+                }
+            }
+        }
+        __syncthreads();  // everyone done with s_p / s_n before the next stage overwrites it
+    }
+    if (active) {
+        const IdxT pad = (IdxT)(cnt > 0 ? first : N);  // empty ball: N, as the sort leaves it
+        for (int k = min(cnt, K) + lane; k < K; k += 32) out[k] = pad;
+        if (cnt == 0 && lane == 0 && empty_count != nullptr) atomicAdd(empty_count, 1);
+    }
+}
+
+// ------------------------------------------------------------------ group gather (A5)
+__global__ void __launch_bounds__(256)
+group_gather_kernel(const float *__restrict__ xyz, const float *__restrict__ new_xyz,
+                    const float *__restrict__ feats, const int64_t *__restrict__ idx, int N, int S,
+                    int K, int D, int order, float *__restrict__ out, size_t total) {
+    const int C = 3 + D;
+    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; e < total; e += stride) {
+        const int c = (int)(e % C);
+        const size_t row = e / C;      // (b*S + s)*K + k
+        const size_t g = row / K;      // b*S + s
+        const size_t b = g / S;
+        long long n = idx[row];
+        n = n < 0 ? 0 : (n >= N ? N - 1 : n);
+        const int cx = (order == PAPC_XYZ_FIRST) ? c : c - D;  // xyz channel if in [0,3)
+        float v;
+        if (cx >= 0 && cx < 3) {
+            v = __fsub_rn(xyz[(b * N + (size_t)n) * 3 + cx], new_xyz[g * 3 + cx]);
+        } else {
+            const int cf = (order == PAPC_XYZ_FIRST) ? c - 3 : c;
+            v = feats[(b * N + (size_t)n) * D + cf];
+        }
+        out[e] = v;
+    }
+}
+
+static int grid_for(size_t total, int threads) {
+    size_t blocks = (total + threads - 1) / threads;
+    const size_t cap = (size_t)kNumSMs * 16;
+    return (int)(blocks < cap ? (blocks ? blocks : 1) : cap);
+}
+
+}  // namespace papc
+
+using namespace papc;
+
+extern "C" int papc_square_distance_f32(const float *src, const float *dst, int B, int N, int M,
+                                        float *out, papc_stream_t stream) {
+    if (B < 0 || N < 0 || M < 0) return PAPC_EINVAL;
+    const size_t total = (size_t)B * N * M;
+    if (total == 0) return PAPC_OK;
+    if (!src || !dst || !out) return PAPC_EINVAL;
+    square_distance_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(src, dst, N, M, out,
+                                                                               total);
+    PAPC_LAUNCH_CHECK();
+    return PAPC_OK;
+}
+
+extern "C" int papc_gather_f32(const float *points, const int64_t *idx, int B, int N, int C, int M,
+                               float *out, papc_stream_t stream) {
+    if (B < 0 || N <= 0 || C < 0 || M < 0) return PAPC_EINVAL;
+    if ((size_t)B * M * C == 0) return PAPC_OK;
+    if (!points || !idx || !out) return PAPC_EINVAL;
+    cudaStream_t st = as_stream(stream);
+    const bool vec4 = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(points) & 15u) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
+    if (vec4) {
+        const size_t total = (size_t)B * M * (C / 4);
+        gather_rows_kernel<float4><<<grid_for(total, 256), 256, 0, st>>>(points, idx, N, C / 4, M,
+                                                                         total, out);
+    } else {
+        const size_t total = (size_t)B * M * C;
+        gather_rows_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(points, idx, N, C, M, total,
+                                                                        out);
+    }
+    PAPC_LAUNCH_CHECK();
+    return PAPC_OK;
+}
+
+extern "C" int papc_ball_query_f32(const float *xyz, const float *new_xyz, int B, int N, int S,
+                                   float radius2, int nsample, void *out_idx, int idx_bits,
+                                   int32_t *empty_count, papc_stream_t stream) {
+    if (B < 0 || N <= 0 || S < 0 || nsample <= 0) return PAPC_EINVAL;
+    if (idx_bits != 32 && idx_bits != 64) return PAPC_EINVAL;
+    if (nsample > N) return PAPC_EINVAL;  // the reference fails with a shape mismatch
+    if (B == 0 || S == 0) return PAPC_OK;
+    if (!xyz || !new_xyz || !out_idx) return PAPC_EINVAL;
+    if (B > 65535) return PAPC_EUNSUPPORTED;
+    dim3 grid(ceil_div(S, kBqWarps), B);
+    if (idx_bits == 64)
+        ball_query_kernel<int64_t><<<grid, kBqWarps * 32, 0, as_stream(stream)>>>(
+            xyz, new_xyz, N, S, radius2, nsample, reinterpret_cast<int64_t *>(out_idx), empty_count);
+    else
+        ball_query_kernel<int32_t><<<grid, kBqWarps * 32, 0, as_stream(stream)>>>(
+            xyz, new_xyz, N, S, radius2, nsample, reinterpret_cast<int32_t *>(out_idx), empty_count);
+    PAPC_LAUNCH_CHECK();
+    return PAPC_OK;
+}
+
+extern "C" int papc_group_gather_f32(const float *xyz, const float *new_xyz, const float *feats,
+                                     const int64_t *idx, int B, int N, int S, int K, int D,
+                                     int order, float *out, papc_stream_t stream) {
+    if (B < 0 || N <= 0 || S < 0 || K < 0 || D < 0) return PAPC_EINVAL;
+    if (order != PAPC_XYZ_FIRST && order != PAPC_FEATS_FIRST) return PAPC_EINVAL;
+    const size_t total = (size_t)B * S * K * (3 + D);
+    if (total == 0) return PAPC_OK;
+    if (!xyz || !new_xyz || !idx || !out || (D > 0 && !feats)) return PAPC_EINVAL;
+    group_gather_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
+        xyz, new_xyz, feats, idx, N, S, K, D, order, out, total);
+    PAPC_LAUNCH_CHECK();
+    return PAPC_OK;
+}

@@ -1,0 +1,728 @@
+// sa_mlp.cu -- the grouped shared MLP of SetAbstraction:
+//   (Conv2D 1x1 + bias -> BatchNorm2D -> ReLU) x L -> max over the K neighbours
+// (reference: layers.py:214-219 and 271-276), fp32 SIMT path for sm_100a.
+//
+// One kernel per layer computes y = W * act(x) + bias as a tiled GEMM over the M = B*S*K
+// grouped rows, with everything the reference runs as separate passes fused around it:
+//   prologue : layer 0 gathers its rows straight from (xyz, new_xyz, feats, idx) -- the
+//              [B,S,K,3+D] grouped tensor is never materialised; later layers apply the
+//              previous layer's BatchNorm (as a per-channel scale/shift) + ReLU while loading.
+//   epilogue : bias, the pre-BN store (hidden layers only), per-channel sum / sum-of-squares
+//              partials for the batch statistics (reduced in fp64, fixed order -> run-to-run
+//              deterministic), and for the last layer the per-group max AND min of y, so the
+//              max-pool is taken before BN+ReLU (exact: BN+ReLU is monotone per channel).
+// The train-mode BatchNorm is the only grid-wide dependency, hence one launch per layer plus
+// a tiny statistics kernel in between.
+#include "common.cuh"
+
+namespace papc {
+
+constexpr int BM = 128;      // rows per tile
+constexpr int BK = 16;       // reduction slice
+constexpr int kThreads = 256;
+constexpr int kPitchA = BM + 4;
+
+enum { POOL_NONE = 0, POOL_TILE = 1, POOL_ATOMIC = 2 };
+
+struct LayerArgs {
+    // gathered source (layer 0 of the fused path)
+    const float *xyz, *new_xyz, *feats;
+    const int32_t *idx;
+    int N, S, K, D, order;
+    // plain source: x [M,cin], optional act(v) = relu(in_scale*v + in_shift)
+    const float *x, *in_scale, *in_shift;
+    long long M;
+    int cin, cout;
+    const float *W, *bias;
+    float *y;
+    float *pool_max, *pool_min;
+    int pool_mode;
+    double *stats_partial;  // [tiles_m][2][cout]
+    int vec_a, vec_w, vec_y;  // 16-byte fast paths allowed
+};
+
+template <int BN>
+struct Smem {
+    static constexpr int kPitchW = BN + 4;
+    static constexpr int kA = 2 * BK * kPitchA;
+    static constexpr int kW = 2 * BK * kPitchW;
+    static constexpr int kMain = kA + kW;
+    static constexpr int kRed = 2 * 32 * BN;  // pool max + min scratch
+    static constexpr int kFloats = kMain > kRed ? kMain : kRed;
+};
+
+template <int BN, bool GATHER>
+__global__ void __launch_bounds__(kThreads, 2)
+mlp_layer_kernel(const LayerArgs a) {
+    constexpr int TN = BN / 16;  // columns per thread (8 or 4)
+    constexpr int kPitchW = Smem<BN>::kPitchW;
+    __shared__ __align__(16) float smem[Smem<BN>::kFloats];
+    __shared__ long long s_src[BM];  // gather: b*N + n   (source row of xyz / feats)
+    __shared__ int s_grp[BM];        // gather: b*S + s   (row of new_xyz)
+    float *As = smem;
+    float *Ws = smem + Smem<BN>::kA;
+
+    const int tid = threadIdx.x;
+    const int tx = tid & 15;
+    const int ty = tid >> 4;
+    const int nt = ceil_div(a.cout, BN);
+    const long long tile_m = blockIdx.x / nt;
+    const int tile_n = blockIdx.x % nt;
+    const long long m0 = tile_m * BM;
+    const int n0 = tile_n * BN;
+    const int cin = a.cin;
+    const int KT = ceil_div(cin, BK);
+
+    if (GATHER) {
+        for (int r = tid; r < BM; r += kThreads) {
+            const long long row = m0 + r;
+            long long src = 0;
+            int g = 0;
+            if (row < a.M) {
+                const long long gg = row / a.K;
+                const int k = (int)(row - gg * a.K);
+                const long long b = gg / a.S;
+                int n = a.idx ? a.idx[row] : k;
+                n = min(max(n, 0), a.N - 1);
+                src = b * a.N + n;
+                g = (int)gg;
+            }
+            s_src[r] = src;
+            s_grp[r] = g;
+        }
+        __syncthreads();
+    }
+
+    // ---- global -> register staging ------------------------------------------------------
+    // A tile: 128 rows x 16 k = 512 float4; thread handles (row = q/4, k4 = q%4) for q = tid, tid+256.
+    // W tile: BN cols x 16 k; thread handles (n = q/4, k4 = q%4) for q = tid (+256 if BN == 128).
+    float4 ra[2];
+    float4 rw[BN / 64];
+
+    auto load_a = [&](int kt) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int q = tid + h * kThreads;
+            const int r = q >> 2;
+            const int k = kt * BK + (q & 3) * 4;
+            const long long row = m0 + r;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (row < a.M) {
+                if (!GATHER) {
+                    const float *p = a.x + row * cin + k;
+                    if (a.vec_a && k + 3 < cin) {
+                        const float4 t = *reinterpret_cast<const float4 *>(p);
+                        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (k + j < cin) v[j] = p[j];
+                    }
+                    if (a.in_scale != nullptr) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (k + j < cin)
+                                v[j] = fmaxf(fmaf(v[j], a.in_scale[k + j], a.in_shift[k + j]), 0.f);
+                    }
+                } else {
+                    // internal k order: [feats 0..D) then xyz 0..3)  (W columns are permuted to match)
+                    const long long src = s_src[r];
+                    const int D = a.D;
+                    if (a.vec_a && k + 3 < D) {
+                        const float4 t = *reinterpret_cast<const float4 *>(a.feats + src * D + k);
+                        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int kk = k + j;
+                            if (kk < D) {
+                                v[j] = a.feats[src * D + kk];
+                            } else if (kk < D + 3) {
+                                const int c = kk - D;
+                                float pv = a.xyz[src * 3 + c];
+                                if (a.new_xyz != nullptr)
+                                    pv = __fsub_rn(pv, a.new_xyz[(long long)s_grp[r] * 3 + c]);
+                                v[j] = pv;
+                            }
+                        }
+                    }
+                }
+            }
+            ra[h] = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    };
+    auto wcol = [&](int k) -> int {  // internal k -> column of W (or -1)
+        if (!GATHER) return k < cin ? k : -1;
+        if (k < a.D) return a.order == PAPC_XYZ_FIRST ? k + 3 : k;
+        if (k < a.D + 3) return a.order == PAPC_XYZ_FIRST ? k - a.D : k;
+        return -1;
+    };
+    auto load_w = [&](int kt) {
+#pragma unroll
+        for (int h = 0; h < BN / 64; ++h) {
+            const int q = tid + h * kThreads;
+            const int n = n0 + (q >> 2);
+            const int k = kt * BK + (q & 3) * 4;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (n < a.cout) {
+                const float *p = a.W + (long long)n * cin;
+                if (!GATHER && a.vec_w && k + 3 < cin) {
+                    const float4 t = *reinterpret_cast<const float4 *>(p + k);
+                    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int c = wcol(k + j);
+                        if (c >= 0) v[j] = p[c];
+                    }
+                }
+            }
+            rw[h] = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    };
+    auto store_tiles = [&](int buf) {
+        float *Ab = As + buf * BK * kPitchA;
+        float *Wb = Ws + buf * BK * kPitchW;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int q = tid + h * kThreads;
+            const int r = q >> 2;
+            const int kk = (q & 3) * 4;
+            Ab[(kk + 0) * kPitchA + r] = ra[h].x;
+            Ab[(kk + 1) * kPitchA + r] = ra[h].y;
+            Ab[(kk + 2) * kPitchA + r] = ra[h].z;
+            Ab[(kk + 3) * kPitchA + r] = ra[h].w;
+        }
+#pragma unroll
+        for (int h = 0; h < BN / 64; ++h) {
+            const int q = tid + h * kThreads;
+            const int n = q >> 2;
+            const int kk = (q & 3) * 4;
+            Wb[(kk + 0) * kPitchW + n] = rw[h].x;
+            Wb[(kk + 1) * kPitchW + n] = rw[h].y;
+            Wb[(kk + 2) * kPitchW + n] = rw[h].z;
+            Wb[(kk + 3) * kPitchW + n] = rw[h].w;
+        }
+    };
+
+    float acc[8][TN];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    load_a(0);
+    load_w(0);
+    store_tiles(0);
+    __syncthreads();
+    for (int kt = 0; kt < KT; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < KT) {
+            load_a(kt + 1);
+            load_w(kt + 1);
+        }
+        const float *Ab = As + buf * BK * kPitchA;
+        const float *Wb = Ws + buf * BK * kPitchW;
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float av[8], bv[TN];
+            const float4 a0 = *reinterpret_cast<const float4 *>(Ab + k * kPitchA + ty * 4);
+            const float4 a1 = *reinterpret_cast<const float4 *>(Ab + k * kPitchA + 64 + ty * 4);
+            av[0] = a0.x; av[1] = a0.y; av[2] = a0.z; av[3] = a0.w;
+            av[4] = a1.x; av[5] = a1.y; av[6] = a1.z; av[7] = a1.w;
+            const float4 b0 = *reinterpret_cast<const float4 *>(Wb + k * kPitchW + tx * 4);
+            bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w;
+            if (TN == 8) {
+                const float4 b1 = *reinterpret_cast<const float4 *>(Wb + k * kPitchW + 64 + tx * 4);
+                bv[TN - 4] = b1.x; bv[TN - 3] = b1.y; bv[TN - 2] = b1.z; bv[TN - 1] = b1.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (kt + 1 < KT) store_tiles(buf ^ 1);
+        __syncthreads();
+    }
+
+    // ---- epilogue --------------------------------------------------------------------------
+    // thread rows: ty*4+i (i<4), 64+ty*4+(i-4);   cols: tx*4+j (j<4), 64+tx*4+(j-4)
+    int colv[TN];
+    float bias[TN];
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+        colv[j] = n0 + ((j < 4) ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+        bias[j] = (a.bias != nullptr && colv[j] < a.cout) ? a.bias[colv[j]] : 0.f;
+    }
+    bool rvalid[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = (i < 4) ? ty * 4 + i : 64 + ty * 4 + (i - 4);
+        rvalid[i] = (m0 + r) < a.M;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] += bias[j];
+    }
+
+    if (a.y != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (!rvalid[i]) continue;
+            const int r = (i < 4) ? ty * 4 + i : 64 + ty * 4 + (i - 4);
+            float *yr = a.y + (m0 + r) * a.cout;
+#pragma unroll
+            for (int jc = 0; jc < TN / 4; ++jc) {
+                const int c = colv[jc * 4];
+                if (a.vec_y && c + 3 < a.cout) {
+                    *reinterpret_cast<float4 *>(yr + c) = make_float4(
+                        acc[i][jc * 4 + 0], acc[i][jc * 4 + 1], acc[i][jc * 4 + 2], acc[i][jc * 4 + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (c + j < a.cout) yr[c + j] = acc[i][jc * 4 + j];
+                }
+            }
+        }
+    }
+
+    // batch statistics: per-thread fp32 sums over its 8 rows, then a fixed-order fp64 column sum
+    if (a.stats_partial != nullptr) {
+        float *red_s = smem;            // [16][BN]
+        float *red_q = smem + 16 * BN;  // [16][BN]
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            float s = 0.f, q = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float v = rvalid[i] ? acc[i][j] : 0.f;
+                s += v;
+                q = fmaf(v, v, q);
+            }
+            const int cl = colv[j] - n0;
+            red_s[ty * BN + cl] = s;
+            red_q[ty * BN + cl] = q;
+        }
+        __syncthreads();
+        if (tid < BN && n0 + tid < a.cout) {
+            double S = 0.0, Q = 0.0;
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+                S += (double)red_s[t * BN + tid];
+                Q += (double)red_q[t * BN + tid];
+            }
+            double *sp = a.stats_partial + tile_m * 2 * a.cout;
+            sp[n0 + tid] = S;
+            sp[a.cout + n0 + tid] = Q;
+        }
+        __syncthreads();
+    }
+
+    if (a.pool_mode == POOL_TILE) {
+        // K % 4 == 0 and BM % K == 0: every 4-row chunk lies inside one group of this tile.
+        float *red_mx = smem;            // [32 chunks][BN]
+        float *red_mn = smem + 32 * BN;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int rc = h * 16 + ty;
+#pragma unroll
+            for (int j = 0; j < TN; ++j) {
+                float mx = -INFINITY, mn = INFINITY;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (rvalid[h * 4 + i]) {
+                        mx = fmaxf(mx, acc[h * 4 + i][j]);
+                        mn = fminf(mn, acc[h * 4 + i][j]);
+                    }
+                }
+                const int cl = colv[j] - n0;
+                red_mx[rc * BN + cl] = mx;
+                red_mn[rc * BN + cl] = mn;
+            }
+        }
+        __syncthreads();
+        const int gpt = BM / a.K;  // groups per tile
+        const int cpg = a.K / 4;   // chunks per group
+        for (int t = tid; t < gpt * BN; t += kThreads) {
+            const int gl = t / BN;
+            const int cl = t - gl * BN;
+            const long long grow = m0 + (long long)gl * a.K;
+            if (grow >= a.M || n0 + cl >= a.cout) continue;
+            float mx = -INFINITY, mn = INFINITY;
+            for (int c = 0; c < cpg; ++c) {
+                mx = fmaxf(mx, red_mx[(gl * cpg + c) * BN + cl]);
+                mn = fminf(mn, red_mn[(gl * cpg + c) * BN + cl]);
+            }
+            const long long g = grow / a.K;
+            a.pool_max[g * a.cout + n0 + cl] = mx;
+            a.pool_min[g * a.cout + n0 + cl] = mn;
+        }
+    } else if (a.pool_mode == POOL_ATOMIC) {
+        // generic K: pool buffers were initialised to -inf / +inf by the host wrapper
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (!rvalid[i]) continue;
+            const int r = (i < 4) ? ty * 4 + i : 64 + ty * 4 + (i - 4);
+            const long long g = (m0 + r) / a.K;
+#pragma unroll
+            for (int j = 0; j < TN; ++j) {
+                if (colv[j] < a.cout) {
+                    atomic_max_f32(a.pool_max + g * a.cout + colv[j], acc[i][j]);
+                    atomic_min_f32(a.pool_min + g * a.cout + colv[j], acc[i][j]);
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ small kernels
+__global__ void fill_f32_kernel(float *p, float v, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) p[i] = v;
+}
+
+// partial [T][2*C] doubles -> sums [2*C]; block = (32 columns, 16 row-lanes), fixed order.
+__global__ void __launch_bounds__(512)
+stats_reduce_kernel(const double *__restrict__ partial, long long T, int C2,
+                    double *__restrict__ sums) {
+    __shared__ double s[16][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    double acc = 0.0;
+    if (c < C2)
+        for (long long t = threadIdx.y; t < T; t += 16) acc += partial[t * C2 + c];
+    s[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C2) {
+        double tot = 0.0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) tot += s[i][threadIdx.x];
+        sums[c] = tot;
+    }
+}
+
+__global__ void bn_scale_shift_kernel(const double *__restrict__ sums, double count,
+                                      const float *__restrict__ gamma,
+                                      const float *__restrict__ beta, float eps, int C,
+                                      float *__restrict__ scale, float *__restrict__ shift,
+                                      float *__restrict__ mean_out, float *__restrict__ var_out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double mean = sums[c] / count;
+    double var = sums[C + c] / count - mean * mean;  // biased, as Paddle's training BN
+    var = var > 0.0 ? var : 0.0;
+    const double g = gamma ? (double)gamma[c] : 1.0;
+    const double b = beta ? (double)beta[c] : 0.0;
+    const double sc = g / sqrt(var + (double)eps);
+    scale[c] = (float)sc;
+    shift[c] = (float)(b - mean * sc);
+    if (mean_out) mean_out[c] = (float)mean;
+    if (var_out) var_out[c] = (float)var;
+}
+
+__global__ void bn_running_scale_shift_kernel(const float *__restrict__ rm,
+                                              const float *__restrict__ rv,
+                                              const float *__restrict__ gamma,
+                                              const float *__restrict__ beta, float eps, int C,
+                                              float *__restrict__ scale,
+                                              float *__restrict__ shift) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double g = gamma ? (double)gamma[c] : 1.0;
+    const double b = beta ? (double)beta[c] : 0.0;
+    const double sc = g / sqrt((double)rv[c] + (double)eps);
+    scale[c] = (float)sc;
+    shift[c] = (float)(b - (double)rm[c] * sc);
+}
+
+// out = relu(scale * (scale >= 0 ? max : min) + shift); BSC: [G,C]; BCS: [B,C,S] via a 32x32 transpose
+__global__ void __launch_bounds__(256)
+pool_finish_bsc_kernel(const float *__restrict__ pmax, const float *__restrict__ pmin,
+                       const float *__restrict__ scale, const float *__restrict__ shift, size_t total,
+                       int C, float *__restrict__ out) {
+    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; e < total; e += stride) {
+        const int c = (int)(e % C);
+        const float sc = scale[c];
+        const float v = sc >= 0.f ? pmax[e] : pmin[e];
+        out[e] = fmaxf(fmaf(v, sc, shift[c]), 0.f);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+pool_finish_bcs_kernel(const float *__restrict__ pmax, const float *__restrict__ pmin,
+                       const float *__restrict__ scale, const float *__restrict__ shift, int S, int C,
+                       float *__restrict__ out) {
+    __shared__ float t[32][33];
+    const int b = blockIdx.z;
+    const int s0 = blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    const int lx = threadIdx.x & 31;
+    const int ly = threadIdx.x >> 5;  // 0..7
+    for (int i = ly; i < 32; i += 8) {
+        const int s = s0 + i, c = c0 + lx;
+        float v = 0.f;
+        if (s < S && c < C) {
+            const size_t e = ((size_t)b * S + s) * C + c;
+            const float sc = scale[c];
+            const float x = sc >= 0.f ? pmax[e] : pmin[e];
+            v = fmaxf(fmaf(x, sc, shift[c]), 0.f);
+        }
+        t[i][lx] = v;
+    }
+    __syncthreads();
+    for (int i = ly; i < 32; i += 8) {
+        const int c = c0 + i, s = s0 + lx;
+        if (s < S && c < C) out[((size_t)b * C + c) * S + s] = t[lx][i];
+    }
+}
+
+static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static int launch_layer(const LayerArgs &a, bool gather, cudaStream_t st) {
+    const long long tiles_m = ceil_div<long long>(a.M, BM);
+    if (a.cout <= 64) {
+        const long long grid = tiles_m * ceil_div(a.cout, 64);
+        if (grid > 0x7fffffffLL) return PAPC_EUNSUPPORTED;
+        if (gather) mlp_layer_kernel<64, true><<<(unsigned)grid, kThreads, 0, st>>>(a);
+        else mlp_layer_kernel<64, false><<<(unsigned)grid, kThreads, 0, st>>>(a);
+    } else {
+        const long long grid = tiles_m * ceil_div(a.cout, 128);
+        if (grid > 0x7fffffffLL) return PAPC_EUNSUPPORTED;
+        if (gather) mlp_layer_kernel<128, true><<<(unsigned)grid, kThreads, 0, st>>>(a);
+        else mlp_layer_kernel<128, false><<<(unsigned)grid, kThreads, 0, st>>>(a);
+    }
+    PAPC_LAUNCH_CHECK();
+    return PAPC_OK;
+}
+
+static int fill(float *p, float v, size_t n, cudaStream_t st) {
+    if (n == 0) return PAPC_OK;
+    size_t blocks = (n + 255) / 256;
+    if (blocks > (size_t)kNumSMs * 8) blocks = (size_t)kNumSMs * 8;
+    fill_f32_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, v, n);
+    PAPC_LAUNCH_CHECK();
+    return PAPC_OK;
+}
+
+static int validate_src(const papc_group_source *s, int cin) {
+    if (!s) return PAPC_EINVAL;
+    if (s->B < 0 || s->S <= 0 || s->K <= 0) return PAPC_EINVAL;
+    if (s->grouped) return PAPC_OK;
+    if (!s->xyz || s->N <= 0 || s->D < 0 || (s->D > 0 && !s->feats)) return PAPC_EINVAL;
+    if (s->order != PAPC_XYZ_FIRST && s->order != PAPC_FEATS_FIRST) return PAPC_EINVAL;
+    if (!s->idx && s->K > s->N) return PAPC_EINVAL;
+    if (cin != 3 + s->D) return PAPC_EINVAL;
+    return PAPC_OK;
+}
+
+}  // namespace papc
+
+using namespace papc;
+
+extern "C" int64_t papc_mlp_stats_partial_rows(int64_t M) { return ceil_div<long long>(M, BM); }
+
+extern "C" int papc_mlp_layer_forward_f32(const papc_group_source *src, const float *x,
+                                          const float *in_scale, const float *in_shift, int64_t M,
+                                          int32_t cin, int32_t cout, int32_t K, const float *weight,
+                                          const float *bias, float *y, float *pool_max,
+                                          float *pool_min, double *stats_partial,
+                                          papc_stream_t stream) {
+    if (M < 0 || cin <= 0 || cout <= 0 || K <= 0 || !weight) return PAPC_EINVAL;
+    if (M == 0) return PAPC_OK;
+    if ((pool_max == nullptr) != (pool_min == nullptr)) return PAPC_EINVAL;
+    if ((in_scale == nullptr) != (in_shift == nullptr)) return PAPC_EINVAL;
+    cudaStream_t st = as_stream(stream);
+    LayerArgs a{};
+    bool gather = false;
+    if (src != nullptr) {
+        int rc = validate_src(src, cin);
+        if (rc != PAPC_OK) return rc;
+        if ((int64_t)src->B * src->S * src->K != M || src->K != K) return PAPC_EINVAL;
+        if (src->grouped) {
+            a.x = src->grouped;
+        } else {
+            gather = true;
+            a.xyz = src->xyz; a.new_xyz = src->new_xyz; a.feats = src->feats; a.idx = src->idx;
+            a.N = src->N; a.S = src->S; a.D = src->D; a.order = src->order;
+        }
+    } else {
+        if (!x) return PAPC_EINVAL;
+        a.x = x; a.in_scale = in_scale; a.in_shift = in_shift;
+    }
+    a.K = K; a.M = M; a.cin = cin; a.cout = cout; a.W = weight; a.bias = bias;
+    a.y = y; a.pool_max = pool_max; a.pool_min = pool_min; a.stats_partial = stats_partial;
+    a.pool_mode = POOL_NONE;
+    if (pool_max) {
+        if (M % K != 0) return PAPC_EINVAL;
+        if (K % 4 == 0 && K <= BM && BM % K == 0) {
+            a.pool_mode = POOL_TILE;
+        } else {
+            a.pool_mode = POOL_ATOMIC;
+            const size_t n = (size_t)(M / K) * cout;
+            int rc = fill(pool_max, -INFINITY, n, st);
+            if (rc != PAPC_OK) return rc;
+            rc = fill(pool_min, INFINITY, n, st);
+            if (rc != PAPC_OK) return rc;
+        }
+    }
+    if (gather) a.vec_a = (a.D % 4 == 0) && a.D > 0 && aligned16(a.feats);
+    else a.vec_a = (cin % 4 == 0) && aligned16(a.x);
+    a.vec_w = (cin % 4 == 0) && aligned16(weight);
+    a.vec_y = (cout % 4 == 0) && (y == nullptr || aligned16(y));
+    return launch_layer(a, gather, st);
+}
+
+extern "C" int papc_mlp_stats_reduce_f64(const double *stats_partial, int64_t partial_rows,
+                                         int32_t cout, double *sums, papc_stream_t stream) {
+    if (!stats_partial || !sums || partial_rows < 0 || cout <= 0) return PAPC_EINVAL;
+    const int C2 = 2 * cout;
+    stats_reduce_kernel<<<ceil_div(C2, 32), dim3(32, 16), 0, as_stream(stream)>>>(
+        stats_partial, partial_rows, C2, sums);
+    PAPC_LAUNCH_CHECK();
+    return PAPC_OK;
+}
+
+extern "C" int papc_bn_scale_shift_f32(const double *sums, double count, const float *gamma,
+                                       const float *beta, float eps, int32_t cout, float *scale,
+                                       float *shift, float *mean_out, float *var_out,
+                                       papc_stream_t stream) {
+    if (!sums || !scale || !shift || cout <= 0 || !(count > 0)) return PAPC_EINVAL;
+    bn_scale_shift_kernel<<<ceil_div(cout, 128), 128, 0, as_stream(stream)>>>(
+        sums, count, gamma, beta, eps, cout, scale, shift, mean_out, var_out);
+    PAPC_LAUNCH_CHECK();
+    return PAPC_OK;
+}
+
+extern "C" int papc_bn_running_scale_shift_f32(const float *running_mean, const float *running_var,
+                                               const float *gamma, const float *beta, float eps,
+                                               int32_t cout, float *scale, float *shift,
+                                               papc_stream_t stream) {
+    if (!running_mean || !running_var || !scale || !shift || cout <= 0) return PAPC_EINVAL;
+    bn_running_scale_shift_kernel<<<ceil_div(cout, 128), 128, 0, as_stream(stream)>>>(
+        running_mean, running_var, gamma, beta, eps, cout, scale, shift);
+    PAPC_LAUNCH_CHECK();
+    return PAPC_OK;
+}
+
+extern "C" int papc_sa_pool_finish_f32(const float *pool_max, const float *pool_min,
+                                       const float *scale, const float *shift, int32_t B, int32_t S,
+                                       int32_t cout, float *out, int out_layout,
+                                       papc_stream_t stream) {
+    if (B < 0 || S <= 0 || cout <= 0) return PAPC_EINVAL;
+    if (out_layout != PAPC_OUT_BSC && out_layout != PAPC_OUT_BCS) return PAPC_EINVAL;
+    if (B == 0) return PAPC_OK;
+    if (!pool_max || !pool_min || !scale || !shift || !out) return PAPC_EINVAL;
+    cudaStream_t st = as_stream(stream);
+    if (out_layout == PAPC_OUT_BSC || S == 1) {  // [B,C,1] and [B,1,C] are the same bytes
+        const size_t total = (size_t)B * S * cout;
+        size_t blocks = (total + 255) / 256;
+        if (blocks > (size_t)kNumSMs * 16) blocks = (size_t)kNumSMs * 16;
+        pool_finish_bsc_kernel<<<(unsigned)blocks, 256, 0, st>>>(pool_max, pool_min, scale, shift,
+                                                                 total, cout, out);
+    } else {
+        if (B > 65535) return PAPC_EUNSUPPORTED;
+        dim3 grid(ceil_div(S, 32), ceil_div(cout, 32), B);
+        pool_finish_bcs_kernel<<<grid, 256, 0, st>>>(pool_max, pool_min, scale, shift, S, cout, out);
+    }
+    PAPC_LAUNCH_CHECK();
+    return PAPC_OK;
+}
+
+// ---- monolithic driver: workspace carving ------------------------------------------------
+namespace {
+struct WsPlan {
+    size_t y[2], pool_max, pool_min, partial, sums, scale, shift, total;
+};
+static int plan_ws(const papc_group_source *src, const papc_mlp *mlp, WsPlan *p) {
+    if (!src || !mlp) return PAPC_EINVAL;
+    if (mlp->num_layers < 1 || mlp->num_layers > PAPC_MAX_MLP_LAYERS) return PAPC_EINVAL;
+    const long long M = (long long)src->B * src->S * src->K;
+    const long long G = (long long)src->B * src->S;
+    int maxc = 0;
+    size_t ybytes[2] = {0, 0};
+    for (int l = 0; l < mlp->num_layers; ++l) {
+        const int c = mlp->layers[l].cout;
+        if (c <= 0) return PAPC_EINVAL;
+        maxc = c > maxc ? c : maxc;
+        if (l + 1 < mlp->num_layers) {
+            const size_t b = (size_t)M * c * sizeof(float);
+            if (b > ybytes[l & 1]) ybytes[l & 1] = b;
+        }
+    }
+    const int clast = mlp->layers[mlp->num_layers - 1].cout;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    p->y[0] = take(ybytes[0]);
+    p->y[1] = take(ybytes[1]);
+    p->pool_max = take((size_t)G * clast * sizeof(float));
+    p->pool_min = take((size_t)G * clast * sizeof(float));
+    p->partial = take((size_t)ceil_div<long long>(M, BM) * 2 * maxc * sizeof(double));
+    p->sums = take((size_t)2 * maxc * sizeof(double));
+    p->scale = take((size_t)maxc * sizeof(float));
+    p->shift = take((size_t)maxc * sizeof(float));
+    p->total = off;
+    return PAPC_OK;
+}
+}  // namespace
+
+extern "C" size_t papc_sa_mlp_workspace_bytes(const papc_group_source *src, const papc_mlp *mlp) {
+    WsPlan p;
+    if (plan_ws(src, mlp, &p) != PAPC_OK) return 0;
+    return p.total;
+}
+
+extern "C" int papc_sa_mlp_f32(const papc_group_source *src, const papc_mlp *mlp, float *out,
+                               int out_layout, void *workspace, size_t workspace_bytes,
+                               papc_stream_t stream) {
+    WsPlan p;
+    int rc = plan_ws(src, mlp, &p);
+    if (rc != PAPC_OK) return rc;
+    rc = validate_src(src, mlp->cin);
+    if (rc != PAPC_OK) return rc;
+    if (mlp->bn_mode != PAPC_BN_BATCH && mlp->bn_mode != PAPC_BN_RUNNING) return PAPC_EINVAL;
+    if (out_layout != PAPC_OUT_BSC && out_layout != PAPC_OUT_BCS) return PAPC_EINVAL;
+    const long long M = (long long)src->B * src->S * src->K;
+    if (M == 0) return PAPC_OK;
+    if (!out) return PAPC_EINVAL;
+    if (!workspace || workspace_bytes < p.total) return PAPC_EWORKSPACE;
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255u) != 0) return PAPC_EINVAL;
+    char *ws = reinterpret_cast<char *>(workspace);
+    float *ybuf[2] = {reinterpret_cast<float *>(ws + p.y[0]), reinterpret_cast<float *>(ws + p.y[1])};
+    float *pmax = reinterpret_cast<float *>(ws + p.pool_max);
+    float *pmin = reinterpret_cast<float *>(ws + p.pool_min);
+    double *partial = reinterpret_cast<double *>(ws + p.partial);
+    double *sums = reinterpret_cast<double *>(ws + p.sums);
+    float *scale = reinterpret_cast<float *>(ws + p.scale);
+    float *shift = reinterpret_cast<float *>(ws + p.shift);
+    const bool batch = mlp->bn_mode == PAPC_BN_BATCH;
+    const int L = mlp->num_layers;
+    int cin = mlp->cin;
+    const float *xprev = nullptr;
+    for (int l = 0; l < L; ++l) {
+        const papc_mlp_layer &ly = mlp->layers[l];
+        if (!ly.weight) return PAPC_EINVAL;
+        if (!batch && (!ly.running_mean || !ly.running_var)) return PAPC_EINVAL;
+        const bool last = (l == L - 1);
+        float *y = last ? nullptr : ybuf[l & 1];
+        rc = papc_mlp_layer_forward_f32(l == 0 ? src : nullptr, xprev, l == 0 ? nullptr : scale,
+                                        l == 0 ? nullptr : shift, M, cin, ly.cout, src->K, ly.weight,
+                                        ly.bias, y, last ? pmax : nullptr, last ? pmin : nullptr,
+                                        batch ? partial : nullptr, stream);
+        if (rc != PAPC_OK) return rc;
+        if (batch) {
+            rc = papc_mlp_stats_reduce_f64(partial, papc_mlp_stats_partial_rows(M), ly.cout, sums,
+                                           stream);
+            if (rc != PAPC_OK) return rc;
+            rc = papc_bn_scale_shift_f32(sums, (double)M, ly.gamma, ly.beta, mlp->eps, ly.cout, scale,
+                                         shift, ly.batch_mean, ly.batch_var, stream);
+        } else {
+            rc = papc_bn_running_scale_shift_f32(ly.running_mean, ly.running_var, ly.gamma, ly.beta,
+                                                 mlp->eps, ly.cout, scale, shift, stream);
+        }
+        if (rc != PAPC_OK) return rc;
+        xprev = y;
+        cin = ly.cout;
+    }
+    return papc_sa_pool_finish_f32(pmax, pmin, scale, shift, src->B, src->S,
+                                   mlp->layers[L - 1].cout, out, out_layout, stream);
+}

@@ -1,0 +1,55 @@
+"""Batch sharding over one process per GPU.
+
+Every op on the hot path indexes ``[b, ...]`` only, so clouds / frames are independent: rank r
+of G takes the contiguous slice ``[r*B/G, (r+1)*B/G)`` of the batch, weights are replicated, and
+the only data-path collective is ONE all-gather of the per-shard SetAbstraction output.  The one
+coupling -- training-mode BatchNorm statistics -- is handled by ``sync_bn_group`` on the layers
+(an all-reduce of the per-layer [2,C] fp64 sums); without it each shard normalises with its own
+batch statistics.  Works with the ``nccl`` backend on GPUs and ``gloo`` in the CPU tests.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(B, rank, world):
+    if B % world != 0:
+        raise ValueError(f"batch {B} does not divide over {world} ranks")
+    per = B // world
+    return rank * per, (rank + 1) * per
+
+
+def shard_batch(x, rank=None, world=None):
+    """Contiguous slice of the batch dimension owned by this rank."""
+    rank = dist.get_rank() if rank is None else rank
+    world = dist.get_world_size() if world is None else world
+    lo, hi = shard_range(x.shape[0], rank, world)
+    return x[lo:hi]
+
+
+def all_gather_features(local, group=None):
+    """[B/G, ...] per rank -> [B, ...] on every rank, rank-major (one all-gather)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local
+    local = local.contiguous()
+    world = dist.get_world_size(group)
+    out = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype,
+                      device=local.device)
+    dist.all_gather_into_tensor(out, local, group=group)
+    return out
+
+
+def all_reduce_sums_(sums, group=None):
+    """In-place SUM of the per-layer BatchNorm partial sums over the ranks."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    return sums
+
+
+def set_sync_bn(module, group):
+    """Enable SyncBN over the batch shards on every SetAbstraction layer under ``module``."""
+    for m in module.modules():
+        if hasattr(m, "sync_bn_group"):
+            m.sync_bn_group = group
+    return module

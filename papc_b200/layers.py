@@ -1,0 +1,447 @@
+"""Host-side mirror of PAPC/models/layers/pointnet2_basic_layers.py over the sm_100a kernels.
+
+Same callables, argument order, shapes and dtypes as the reference (file:line cited per
+function), with torch CUDA tensors where the reference has Paddle tensors -- PaddlePaddle is
+not installable in this environment, see INTEGRATION.md for the Paddle-side stub.  Every op
+launches hand-written CUDA through the C ABI (include/papc_b200.h); nothing here computes on
+the CPU and nothing falls back to PyTorch ops for the hot path.
+
+Differences a caller can see (all opt-in):
+  * ``farthest_point_sample`` / ``sample_and_group`` / the layer ``forward`` accept an explicit
+    ``start_idx`` so runs are reproducible; omitted, it is drawn with ``torch.randint`` exactly
+    where the reference calls ``paddle.randint`` (layers.py:76).
+  * the SetAbstraction layers never materialise the ``[B,S,K,3+D]`` grouped tensor and return
+    ``[B,D',S]`` as a transposed *view* of channels-last storage (same shape and values).
+  * ``bn_mode``: ``'batch'`` (default) reproduces what the reference's unregistered conv/bn lists
+    always do -- training-mode batch statistics, even after ``model.eval()``;
+    ``'running'`` normalises with the stored running statistics.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+import torch.distributed as dist
+
+from . import _lib as L
+
+
+# ----------------------------------------------------------------------------------------------
+def _ws(nbytes, device):
+    """Scratch buffer from torch's stream-aware caching allocator (256-byte aligned)."""
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def square_distance(src, dst):
+    """layers.py:26-40.  src [B,N,3], dst [B,M,3] -> [B,N,M] fp32."""
+    L.require_cuda(src, dst)
+    src, dst = L.f32c(src), L.f32c(dst)
+    B, N, Cc = src.shape
+    _, M, _ = dst.shape
+    if Cc != 3 or dst.shape[2] != 3 or dst.shape[0] != B:
+        raise ValueError("square_distance expects src [B,N,3] and dst [B,M,3]")
+    out = torch.empty((B, N, M), dtype=torch.float32, device=src.device)
+    L.check(L.lib().papc_square_distance_f32(L.ptr(src), L.ptr(dst), B, N, M, L.ptr(out),
+                                             L.stream_ptr(src.device)), "square_distance")
+    return out
+
+
+def index_points(points, idx):
+    """layers.py:43-62.  points [B,N,C]; idx [B,S] or [B,S,K] (float32 or integer, cast to int64
+    as :59 does) -> [B,S,C] / [B,S,K,C]."""
+    L.require_cuda(points, idx)
+    points = L.f32c(points)
+    B, N, Cc = points.shape
+    idx64 = idx.to(torch.int64).contiguous()
+    if idx64.shape[0] != B:
+        raise ValueError("index_points: batch mismatch")
+    M = idx64.numel() // max(B, 1)
+    out = torch.empty(tuple(idx64.shape) + (Cc,), dtype=torch.float32, device=points.device)
+    L.check(L.lib().papc_gather_f32(L.ptr(points), L.ptr(idx64), B, N, Cc, M, L.ptr(out),
+                                    L.stream_ptr(points.device)), "index_points")
+    return out
+
+
+def _draw_start(B, N, device, start_idx):
+    if start_idx is None:
+        return torch.randint(0, N, (B,), device=device, dtype=torch.int64)  # layers.py:76
+    s = torch.as_tensor(start_idx, device=device).to(torch.int64).reshape(B).contiguous()
+    return s
+
+
+def farthest_point_sample_idx(xyz, npoint, start_idx=None, return_xyz=False, init_dist=1.0):
+    """Native form of layers.py:65-95: int64 indices [B,npoint] (and the gathered new_xyz)."""
+    L.require_cuda(xyz)
+    xyz = L.f32c(xyz)
+    B, N, Cc = xyz.shape
+    if Cc != 3:
+        raise ValueError("farthest_point_sample expects xyz [B,N,3]")
+    if npoint < 0:
+        raise ValueError("npoint must be >= 0")
+    start = _draw_start(B, N, xyz.device, start_idx)
+    out = torch.empty((B, npoint), dtype=torch.int64, device=xyz.device)
+    new_xyz = torch.empty((B, npoint, 3), dtype=torch.float32, device=xyz.device) if return_xyz else None
+    lib = L.lib()
+    wsb = lib.papc_fps_workspace_bytes(B, N)
+    ws = _ws(wsb, xyz.device) if wsb else None
+    L.check(lib.papc_fps_f32(L.ptr(xyz), B, N, npoint, L.ptr(start), float(init_dist), L.ptr(out),
+                             L.ptr(new_xyz), L.ptr(ws), wsb, L.stream_ptr(xyz.device)),
+            "farthest_point_sample")
+    return (out, new_xyz) if return_xyz else out
+
+
+def farthest_point_sample(xyz, npoint, start_idx=None):
+    """layers.py:65-95.  Returns float32-encoded indices [B,npoint] as the reference does
+    (``centroids = paddle.zeros([B, npoint])``, :74); ``index_points`` casts them back."""
+    return farthest_point_sample_idx(xyz, npoint, start_idx).to(torch.float32)
+
+
+def radius2_f32(radius):
+    """``radius ** 2`` is a Python double compared against an fp32 tensor (layers.py:112)."""
+    return float(torch.tensor(float(radius) ** 2, dtype=torch.float32).item())
+
+
+def _ball_query(radius, nsample, xyz, new_xyz, idx_dtype, check_empty=False):
+    B, N, _ = xyz.shape
+    S = new_xyz.shape[1]
+    if nsample > N:
+        # the reference fails with a shape mismatch at layers.py:118-123
+        raise ValueError(f"query_ball_point: nsample ({nsample}) > N ({N})")
+    out = torch.empty((B, S, nsample), dtype=idx_dtype, device=xyz.device)
+    empty = torch.zeros((1,), dtype=torch.int32, device=xyz.device) if check_empty else None
+    L.check(L.lib().papc_ball_query_f32(L.ptr(xyz), L.ptr(new_xyz), B, N, S, radius2_f32(radius),
+                                        nsample, L.ptr(out), 64 if idx_dtype == torch.int64 else 32,
+                                        L.ptr(empty), L.stream_ptr(xyz.device)), "query_ball_point")
+    if check_empty and int(empty.item()) > 0:
+        # the reference raises IndexError in index_points (index N out of range)
+        raise IndexError(f"query_ball_point: {int(empty.item())} query points have no neighbour "
+                         f"within radius {radius}")
+    return out
+
+
+def query_ball_point(radius, nsample, xyz, new_xyz, check_empty=False):
+    """layers.py:98-126.  xyz [B,N,3], new_xyz [B,S,3] -> int64 [B,S,nsample]."""
+    L.require_cuda(xyz, new_xyz)
+    return _ball_query(radius, nsample, L.f32c(xyz), L.f32c(new_xyz), torch.int64, check_empty)
+
+
+def _group_gather(xyz, new_xyz, feats, idx64, order):
+    B, N, _ = xyz.shape
+    _, S, K = idx64.shape
+    D = 0 if feats is None else feats.shape[2]
+    out = torch.empty((B, S, K, 3 + D), dtype=torch.float32, device=xyz.device)
+    L.check(L.lib().papc_group_gather_f32(L.ptr(xyz), L.ptr(new_xyz), L.ptr(feats), L.ptr(idx64), B, N,
+                                          S, K, D, order, L.ptr(out), L.stream_ptr(xyz.device)),
+            "group_gather")
+    return out
+
+
+def sample_and_group(npoint, radius, nsample, xyz, points, returnfps=False, start_idx=None):
+    """layers.py:129-157.  -> new_xyz [B,S,3], new_points [B,S,K,3+D] (xyz-first concat, :151)."""
+    L.require_cuda(xyz, points)
+    xyz = L.f32c(xyz)
+    points = L.f32c(points)
+    fps_idx, new_xyz = farthest_point_sample_idx(xyz, npoint, start_idx, return_xyz=True)  # :143-144
+    idx = _ball_query(radius, nsample, xyz, new_xyz, torch.int64)                           # :145
+    new_points = _group_gather(xyz, new_xyz, points, idx, L.XYZ_FIRST)                      # :146-151
+    if returnfps:
+        grouped_xyz = index_points(xyz, idx)
+        return new_xyz, new_points, grouped_xyz, fps_idx.to(torch.float32)
+    return new_xyz, new_points
+
+
+def sample_and_group_all(xyz, points):
+    """layers.py:160-176.  new_xyz zeros [B,1,3]; new_points [B,1,N,3+D], no centring."""
+    L.require_cuda(xyz, points)
+    xyz = L.f32c(xyz)
+    B, N, Cc = xyz.shape
+    new_xyz = torch.zeros((B, 1, Cc), dtype=torch.float32, device=xyz.device)
+    if points is None:
+        return new_xyz, xyz.reshape(B, 1, N, Cc)
+    points = L.f32c(points)
+    idx = torch.arange(N, device=xyz.device, dtype=torch.int64).reshape(1, 1, N).expand(B, 1, N).contiguous()
+    return new_xyz, _group_gather(xyz, new_xyz, points, idx, L.XYZ_FIRST)
+
+
+# ---------------------------------------------------------------------------------------------
+class Conv2D:
+    """Parameter holder mirroring ``paddle.nn.Conv2D(cin, cout, 1)``: weight [cout,cin,1,1], bias
+    [cout].  Default init as Paddle: Normal(0, sqrt(2/fan_in)) weight, zero bias."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=1, device=None, generator=None):
+        assert kernel_size == 1
+        std = math.sqrt(2.0 / in_channels)
+        self.weight = (torch.randn((out_channels, in_channels, 1, 1), generator=generator) * std).to(device)
+        self.bias = torch.zeros((out_channels,), device=device)
+
+    def _apply(self, fn):
+        self.weight, self.bias = fn(self.weight), fn(self.bias)
+
+
+class BatchNorm2D:
+    """Parameter holder mirroring ``paddle.nn.BatchNorm2D(c)`` (epsilon 1e-5, momentum 0.9):
+    weight/bias and the running ``_mean`` / ``_variance`` under Paddle's attribute names."""
+
+    def __init__(self, num_features, momentum=0.9, epsilon=1e-5, device=None):
+        self.weight = torch.ones((num_features,), device=device)
+        self.bias = torch.zeros((num_features,), device=device)
+        self._mean = torch.zeros((num_features,), device=device)
+        self._variance = torch.ones((num_features,), device=device)
+        self._momentum = momentum
+        self._epsilon = epsilon
+
+    def _apply(self, fn):
+        self.weight, self.bias = fn(self.weight), fn(self.bias)
+        self._mean, self._variance = fn(self._mean), fn(self._variance)
+
+
+class _MlpRunner:
+    """Builds the C-ABI descriptors for one conv/bn stack and runs the grouped MLP."""
+
+    def __init__(self, convs, bns):
+        self.convs, self.bns = convs, bns
+        self.last_batch_stats = None
+
+    def _mlp_struct(self, cin, bn_mode, device, want_stats):
+        mlp = L.Mlp()
+        mlp.num_layers = len(self.convs)
+        mlp.cin = cin
+        mlp.bn_mode = L.BN_BATCH if bn_mode == "batch" else L.BN_RUNNING
+        mlp.eps = float(self.bns[0]._epsilon)
+        keep = []
+        stats = []
+        for l, (conv, bn) in enumerate(zip(self.convs, self.bns)):
+            w = L.f32c(conv.weight.reshape(conv.weight.shape[0], -1))
+            tensors = [w, L.f32c(conv.bias) if conv.bias is not None else None, L.f32c(bn.weight),
+                       L.f32c(bn.bias), L.f32c(bn._mean), L.f32c(bn._variance)]
+            keep.append(tensors)
+            ly = mlp.layers[l]
+            ly.weight, ly.bias, ly.gamma, ly.beta, ly.running_mean, ly.running_var = [
+                (t.data_ptr() if t is not None else None) for t in tensors]
+            ly.cout = w.shape[0]
+            if want_stats and bn_mode == "batch":
+                bm = torch.empty((w.shape[0],), dtype=torch.float32, device=device)
+                bv = torch.empty((w.shape[0],), dtype=torch.float32, device=device)
+                ly.batch_mean, ly.batch_var = bm.data_ptr(), bv.data_ptr()
+                stats.append((bm, bv))
+        return mlp, keep, stats
+
+    def run(self, src, keep_src, cin, B, S, bn_mode, device, update_running=False, sync_group=None):
+        """-> [B,S,cout] channels-last."""
+        if bn_mode not in ("batch", "running"):
+            raise ValueError("bn_mode must be 'batch' or 'running'")
+        if any(c.weight.device != device for c in self.convs):
+            raise L.PapcError("layer parameters are not on the input's device; call .to(device)")
+        cout = self.convs[-1].weight.shape[0]
+        out = torch.empty((B, S, cout), dtype=torch.float32, device=device)
+        lib = L.lib()
+        st = L.stream_ptr(device)
+        world = dist.get_world_size(sync_group) if (sync_group is not None and dist.is_initialized()) else 1
+        if bn_mode == "batch" and world > 1:
+            self._run_stepwise_synced(src, cin, B, S, out, device, sync_group, update_running)
+            return out
+        mlp, keep, stats = self._mlp_struct(cin, bn_mode, device, update_running)
+        wsb = lib.papc_sa_mlp_workspace_bytes(C.byref(src), C.byref(mlp))
+        ws = _ws(wsb, device)
+        L.check(lib.papc_sa_mlp_f32(C.byref(src), C.byref(mlp), L.ptr(out), L.OUT_BSC, L.ptr(ws), wsb, st),
+                "sa_mlp")
+        if stats:
+            self.last_batch_stats = stats
+            self._update_running(stats)
+        del keep, keep_src
+        return out
+
+    def _update_running(self, stats):
+        # Paddle: running = momentum*running + (1-momentum)*batch, biased batch variance
+        for bn, (bm, bv) in zip(self.bns, stats):
+            bn._mean.mul_(bn._momentum).add_(bm, alpha=1.0 - bn._momentum)
+            bn._variance.mul_(bn._momentum).add_(bv, alpha=1.0 - bn._momentum)
+
+    def _run_stepwise_synced(self, src, cin, B, S, out, device, group, update_running):
+        """Batch-sharded SyncBN: per layer, all-reduce the [2,cout] fp64 sums over the ranks
+         so sharded == unsharded results."""
+        lib = L.lib()
+        st = L.stream_ptr(device)
+        K = src.K
+        M = B * S * K
+        total = float(M) * dist.get_world_size(group)  # equal shards (papc_b200.dist.shard_range)
+        prows = lib.papc_mlp_stats_partial_rows(M)
+        x = None
+        scale = shift = None
+        stats = []
+        G = B * S
+        for l, (conv, bn) in enumerate(zip(self.convs, self.bns)):
+            w = L.f32c(conv.weight.reshape(conv.weight.shape[0], -1))
+            cout = w.shape[0]
+            last = l == len(self.convs) - 1
+            y = None if last else torch.empty((M, cout), dtype=torch.float32, device=device)
+            pmax = torch.empty((G, cout), dtype=torch.float32, device=device) if last else None
+            pmin = torch.empty((G, cout), dtype=torch.float32, device=device) if last else None
+            partial = torch.empty((prows, 2, cout), dtype=torch.float64, device=device)
+            bias = L.f32c(conv.bias) if conv.bias is not None else None
+            L.check(lib.papc_mlp_layer_forward_f32(C.byref(src) if l == 0 else None, L.ptr(x),
+                                                   L.ptr(scale), L.ptr(shift), M, cin, cout, K, L.ptr(w),
+                                                   L.ptr(bias), L.ptr(y), L.ptr(pmax), L.ptr(pmin),
+                                                   L.ptr(partial), st), "mlp_layer_forward")
+            sums = torch.empty((2, cout), dtype=torch.float64, device=device)
+            L.check(lib.papc_mlp_stats_reduce_f64(L.ptr(partial), prows, cout, L.ptr(sums), st),
+                    "mlp_stats_reduce")
+            dist.all_reduce(sums, group=group)
+            scale = torch.empty((cout,), dtype=torch.float32, device=device)
+            shift = torch.empty((cout,), dtype=torch.float32, device=device)
+            bm = torch.empty((cout,), dtype=torch.float32, device=device)
+            bv = torch.empty((cout,), dtype=torch.float32, device=device)
+            L.check(lib.papc_bn_scale_shift_f32(L.ptr(sums), total, L.ptr(L.f32c(bn.weight)),
+                                                L.ptr(L.f32c(bn.bias)), float(bn._epsilon), cout,
+                                                L.ptr(scale), L.ptr(shift), L.ptr(bm), L.ptr(bv), st),
+                    "bn_scale_shift")
+            stats.append((bm, bv))
+            x, cin = y, cout
+        L.check(lib.papc_sa_pool_finish_f32(L.ptr(pmax), L.ptr(pmin), L.ptr(scale), L.ptr(shift), B, S,
+                                            cout, L.ptr(out), L.OUT_BSC, st), "sa_pool_finish")
+        self.last_batch_stats = stats
+        if update_running:
+            self._update_running(stats)
+
+
+def _make_src(xyz, new_xyz, feats, idx32, B, N, S, K, order):
+    src = L.GroupSource()
+    src.grouped = None
+    src.xyz = xyz.data_ptr()
+    src.new_xyz = new_xyz.data_ptr() if new_xyz is not None else None
+    src.feats = feats.data_ptr() if feats is not None else None
+    src.idx = idx32.data_ptr() if idx32 is not None else None
+    src.B, src.N, src.S, src.K = B, N, S, K
+    src.D = 0 if feats is None else feats.shape[2]
+    src.order = order
+    return src
+
+
+def grouped_mlp(new_points, convs, bns, bn_mode="batch"):
+    """The MLP + max-pool tail of a SetAbstraction layer on an explicit grouped tensor
+    ``new_points [B,S,K,Cin]`` (what ``sample_and_group`` returns) -> ``[B,Cout,S]``;
+    layers.py:214-219."""
+    L.require_cuda(new_points)
+    new_points = L.f32c(new_points)
+    B, S, K, Cin = new_points.shape
+    src = L.GroupSource()
+    src.grouped = new_points.data_ptr()
+    src.B, src.N, src.S, src.K, src.D, src.order = B, K, S, K, Cin - 3, L.XYZ_FIRST
+    out = _MlpRunner(convs, bns).run(src, new_points, Cin, B, S, bn_mode, new_points.device)
+    return out.transpose(1, 2)
+
+
+class _SAMixin(torch.nn.Module):
+    """Shared plumbing.  The conv/bn holders live in plain Python lists exactly like the reference
+    (layers.py:185-190, 230-241), so they are invisible to ``parameters()`` / ``state_dict()``;
+    ``_apply`` is overridden so ``.to()`` / ``.cuda()`` still move them."""
+
+    bn_mode = "batch"
+    update_running_stats = False
+    sync_bn_group = None  # a torch.distributed process group -> SyncBN over the batch shards
+
+    def _holders(self):
+        raise NotImplementedError
+
+    def _apply(self, fn, *args, **kwargs):
+        super()._apply(fn, *args, **kwargs)
+        for h in self._holders():
+            h._apply(fn)
+        return self
+
+
+class PointNetSetAbstraction(_SAMixin):
+    """layers.py:179-221 (SSG / group_all)."""
+
+    def __init__(self, npoint, radius, nsample, in_channel, mlp, group_all):
+        super().__init__()
+        self.npoint = npoint
+        self.radius = radius
+        self.nsample = nsample
+        self.mlp_convs = []
+        self.mlp_bns = []
+        last_channel = in_channel
+        for out_channel in mlp:
+            self.mlp_convs.append(Conv2D(last_channel, out_channel, 1))
+            self.mlp_bns.append(BatchNorm2D(out_channel))
+            last_channel = out_channel
+        self.group_all = group_all
+        self.in_channel = in_channel
+
+    def _holders(self):
+        return list(self.mlp_convs) + list(self.mlp_bns)
+
+    def forward(self, xyz, points, start_idx=None):
+        """xyz [B,3,N], points [B,D,N] | None -> (new_xyz [B,3,S], new_points [B,D',S])."""
+        L.require_cuda(xyz, points)
+        xyz = L.f32c(xyz.transpose(1, 2))                                  # :203
+        feats = L.f32c(points.transpose(1, 2)) if points is not None else None  # :205
+        B, N, Cc = xyz.shape
+        if Cc != 3:
+            raise ValueError("xyz must be [B,3,N]")
+        D = 0 if feats is None else feats.shape[2]
+        if 3 + D != self.in_channel:
+            raise ValueError(f"in_channel={self.in_channel} but input has 3+{D} channels")
+        dev = xyz.device
+        if self.group_all:                                                 # :211
+            new_xyz = torch.zeros((B, 1, 3), dtype=torch.float32, device=dev)
+            S = 1
+            src = _make_src(xyz, None, feats, None, B, N, 1, N, L.XYZ_FIRST)
+            keep = (xyz, feats)
+        else:                                                              # :213
+            S = self.npoint
+            _, new_xyz = farthest_point_sample_idx(xyz, S, start_idx, return_xyz=True)
+            idx = _ball_query(self.radius, self.nsample, xyz, new_xyz, torch.int32)
+            src = _make_src(xyz, new_xyz, feats, idx, B, N, S, self.nsample, L.XYZ_FIRST)
+            keep = (xyz, feats, new_xyz, idx)
+        out = _MlpRunner(self.mlp_convs, self.mlp_bns).run(                # :214-219
+            src, keep, 3 + D, B, S, self.bn_mode, dev, self.update_running_stats, self.sync_bn_group)
+        return new_xyz.transpose(1, 2), out.transpose(1, 2)               # :220-221
+
+
+class PointNetSetAbstractionMsg(_SAMixin):
+    """layers.py:224-281 (multi-scale grouping; features-first concat, :267)."""
+
+    def __init__(self, npoint, radius_list, nsample_list, in_channel, mlp_list):
+        super().__init__()
+        self.npoint = npoint
+        self.radius_list = radius_list
+        self.nsample_list = nsample_list
+        self.conv_blocks = []
+        self.bn_blocks = []
+        for i in range(len(mlp_list)):
+            convs, bns = [], []
+            last_channel = in_channel + 3
+            for out_channel in mlp_list[i]:
+                convs.append(Conv2D(last_channel, out_channel, 1))
+                bns.append(BatchNorm2D(out_channel))
+                last_channel = out_channel
+            self.conv_blocks.append(convs)
+            self.bn_blocks.append(bns)
+        self.in_channel = in_channel
+
+    def _holders(self):
+        return [h for blk in self.conv_blocks for h in blk] + [h for blk in self.bn_blocks for h in blk]
+
+    def forward(self, xyz, points, start_idx=None):
+        L.require_cuda(xyz, points)
+        xyz = L.f32c(xyz.transpose(1, 2))
+        feats = L.f32c(points.transpose(1, 2)) if points is not None else None
+        B, N, Cc = xyz.shape
+        D = 0 if feats is None else feats.shape[2]
+        if D != self.in_channel:
+            raise ValueError(f"in_channel={self.in_channel} but points has {D} channels")
+        dev = xyz.device
+        S = self.npoint
+        _, new_xyz = farthest_point_sample_idx(xyz, S, start_idx, return_xyz=True)   # :258
+        outs = []
+        for i, radius in enumerate(self.radius_list):
+            K = self.nsample_list[i]
+            idx = _ball_query(radius, K, xyz, new_xyz, torch.int32)                  # :262
+            src = _make_src(xyz, new_xyz, feats, idx, B, N, S, K, L.FEATS_FIRST)     # :263-267
+            outs.append(_MlpRunner(self.conv_blocks[i], self.bn_blocks[i]).run(     # :271-276
+                src, (xyz, feats, new_xyz, idx), 3 + D, B, S, self.bn_mode, dev,
+                self.update_running_stats, self.sync_bn_group))
+        new_points_concat = torch.cat(outs, dim=2)                                   # :280 (channels-last)
+        return new_xyz.transpose(1, 2), new_points_concat.transpose(1, 2)

@@ -1,0 +1,62 @@
+"""The three SetAbstraction layers of PointNet2_SSG_Clas / PointNet2_MSG_Seg wired exactly as the
+reference model definitions wire them (the FC heads are outside the metric):
+  SSG: PAPC/models/classify/pointnet2/pointnet2.py:11-16, forward :33-35
+  MSG: PAPC/models/segment/pointnet2/pointnet2.py:62-64, forward :84-86
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .layers import PointNetSetAbstraction, PointNetSetAbstractionMsg
+
+
+def load_conv_bn(convs, bns, params):
+    """Install explicit parameters (list of dicts with weight [cout,cin], bias, gamma, beta)."""
+    for conv, bn, p in zip(convs, bns, params):
+        w = torch.as_tensor(np.asarray(p["weight"]))
+        conv.weight = w.reshape(w.shape[0], w.shape[1], 1, 1).to(conv.weight.device)
+        conv.bias = torch.as_tensor(np.asarray(p["bias"])).to(conv.bias.device)
+        bn.weight = torch.as_tensor(np.asarray(p["gamma"])).to(bn.weight.device)
+        bn.bias = torch.as_tensor(np.asarray(p["beta"])).to(bn.bias.device)
+
+
+class SSGSetAbstractionStack(torch.nn.Module):
+    """sa1 -> sa2 -> sa3 of PointNet2_SSG_Clas (normal_channel=False): [B,3,N] -> l3_points [B,1024,1]."""
+
+    def __init__(self, in_channel=3):
+        super().__init__()
+        self.sa1 = PointNetSetAbstraction(npoint=512, radius=0.2, nsample=32, in_channel=in_channel,
+                                          mlp=[64, 64, 128], group_all=False)
+        self.sa2 = PointNetSetAbstraction(npoint=128, radius=0.4, nsample=64, in_channel=128 + 3,
+                                          mlp=[128, 128, 256], group_all=False)
+        self.sa3 = PointNetSetAbstraction(npoint=None, radius=None, nsample=None, in_channel=256 + 3,
+                                          mlp=[256, 512, 1024], group_all=True)
+
+    def layers_(self):
+        return [self.sa1, self.sa2, self.sa3]
+
+    def forward(self, xyz, norm=None, start_idx=(None, None)):
+        l1_xyz, l1_points = self.sa1(xyz, norm, start_idx=start_idx[0])
+        l2_xyz, l2_points = self.sa2(l1_xyz, l1_points, start_idx=start_idx[1])
+        l3_xyz, l3_points = self.sa3(l2_xyz, l2_points)
+        return l3_xyz, l3_points
+
+
+class MSGSegSetAbstractionStack(torch.nn.Module):
+    """sa1 -> sa2 -> sa3 of PointNet2_MSG_Seg (normal_channel=False; features = xyz, 3 ch)."""
+
+    def __init__(self, additional_channel=0):
+        super().__init__()
+        self.sa1 = PointNetSetAbstractionMsg(512, [0.1, 0.2, 0.4], [32, 64, 128], 3 + additional_channel,
+                                             [[32, 32, 64], [64, 64, 128], [64, 96, 128]])
+        self.sa2 = PointNetSetAbstractionMsg(128, [0.4, 0.8], [64, 128], 128 + 128 + 64,
+                                             [[128, 128, 256], [128, 196, 256]])
+        self.sa3 = PointNetSetAbstraction(npoint=None, radius=None, nsample=None, in_channel=512 + 3,
+                                          mlp=[256, 512, 1024], group_all=True)
+
+    def forward(self, xyz, points, start_idx=(None, None)):
+        l1_xyz, l1_points = self.sa1(xyz, points, start_idx=start_idx[0])
+        l2_xyz, l2_points = self.sa2(l1_xyz, l1_points, start_idx=start_idx[1])
+        l3_xyz, l3_points = self.sa3(l2_xyz, l2_points)
+        return l3_xyz, l3_points

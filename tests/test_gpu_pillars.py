@@ -1,0 +1,151 @@
+"""GPU parity tests of the pillar path: voxeliser bit-exact vs the golden vectors produced by the
+reference's own numba kernel (and vs the oracle on random cases); PFN / scatter vs the oracle."""
+import glob
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import capi, pillars_np  # noqa: E402
+from papc_b200 import pillars, synth  # noqa: E402
+
+DEV = "cuda:0"
+TOL = dict(rtol=1e-5, atol=1e-5)
+
+
+def _cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def test_voxelize_small_golden(golden_dir):
+    paths = sorted(glob.glob(os.path.join(golden_dir, "voxel_small_*.npz")))
+    assert len(paths) >= 5
+    for path in paths:
+        g = np.load(path)
+        v, c, n = pillars.points_to_voxel(g["points"], g["voxel_size"], g["coors_range"],
+                                          int(g["max_points"]), bool(g["reverse_index"]), int(g["max_voxels"]))
+        assert v.shape == g["voxels"].shape and c.dtype == np.int32 and n.dtype == np.int32, path
+        np.testing.assert_array_equal(c, g["coors"], err_msg=path)
+        np.testing.assert_array_equal(n, g["num_points"], err_msg=path)
+        np.testing.assert_array_equal(v, g["voxels"], err_msg=path)
+
+
+@pytest.mark.parametrize("name,points", [
+    ("k5", lambda: synth.lidar_frame(20000, 0, False)),
+    ("k5_shuffled", lambda: synth.lidar_frame(20000, 0, True)),
+    ("k5_uniform", lambda: synth.lidar_uniform(20000, 0)),
+])
+def test_voxelize_k5_golden(golden_dir, name, points):
+    """BASELINE config 4 at full size against the reference's own output."""
+    g = np.load(os.path.join(golden_dir, f"voxel_{name}.npz"))
+    v, c, n = pillars.points_to_voxel(points(), synth.KITTI_VOXEL_SIZE, synth.KITTI_PC_RANGE,
+                                      synth.KITTI_MAX_POINTS, True, synth.KITTI_MAX_VOXELS)
+    np.testing.assert_array_equal(c, g["coors"])
+    np.testing.assert_array_equal(n, g["num_points"])
+    assert hashlib.sha256(np.ascontiguousarray(v).tobytes()).hexdigest() == str(g["voxels_sha256"])
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_voxelize_random_vs_oracle(seed):
+    rng = np.random.default_rng(100 + seed)
+    N = int(rng.integers(1, 30000))
+    F = int(rng.integers(3, 7))
+    pts = rng.uniform(-3, 3, (N, F)).astype(np.float32)
+    if seed % 2:
+        pts[:, :3] = np.round(pts[:, :3] * 4) / 4  # many points exactly on cell edges, dense cells
+    vs = np.array([0.3, 0.25, 0.7], np.float32)
+    cr = np.array([-2, -2.25, -2.1, 2.2, 2, 2.1], np.float32)
+    mp, mv, rev = int(rng.integers(1, 40)), int(rng.integers(1, 3000)), bool(seed % 3)
+    ov, oc, on = capi.points_to_voxel(pts, vs, cr, mp, rev, mv)
+    gv, gc, gn = pillars.points_to_voxel(pts, vs, cr, mp, rev, mv)
+    np.testing.assert_array_equal(gc, oc)
+    np.testing.assert_array_equal(gn, on)
+    np.testing.assert_array_equal(gv, ov)
+
+
+def test_voxelize_edge_cases():
+    vs, cr = synth.KITTI_VOXEL_SIZE, synth.KITTI_PC_RANGE
+    v, c, n = pillars.points_to_voxel(np.zeros((0, 4), np.float32), vs, cr, 5, True, 10)
+    assert v.shape == (0, 5, 4) and c.shape == (0, 3) and n.shape == (0,)
+    v, c, n = pillars.points_to_voxel(np.full((7, 4), 1000.0, np.float32), vs, cr, 5, True, 10)
+    assert v.shape[0] == 0
+    # everything in ONE cell, far more points than max_points: first max_points in input order
+    pts = np.tile(np.array([[1.0, 1.0, 0.0, 0.0]], np.float32), (5000, 1))
+    pts[:, 3] = np.arange(5000)
+    v, c, n = pillars.points_to_voxel(pts, vs, cr, 100, True, 10)
+    assert v.shape[0] == 1 and n.tolist() == [100]
+    np.testing.assert_array_equal(v[0, :, 3], np.arange(100, dtype=np.float32))
+    # device-resident form: padded outputs, rows >= voxel_num are zero
+    dv, dc, dn, dnum = pillars.points_to_voxel_device(_cu(synth.lidar_frame(3000, 2)), vs, cr, 20, True, 4000)
+    m = int(dnum.item())
+    assert 0 < m < 4000
+    assert dv[m:].abs().sum().item() == 0 and dc[m:].abs().sum().item() == 0 and dn[m:].sum().item() == 0
+
+
+def _pfn_pair(seed, use_norm=True, F=4, cout=64, vsz=(0.16, 0.16, 4), pcr=synth.KITTI_PC_RANGE):
+    rng = np.random.default_rng(seed)
+    gpu = pillars.PillarFeatureNet(F, use_norm, (cout,), False, vsz, pcr)
+    ref = pillars_np.PillarFeatureNet(F, use_norm, (cout,), False, vsz, pcr)
+    w = synth.pfn_weight(F + 5, cout, seed)
+    gamma = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    gamma[::5] *= -1
+    beta = rng.uniform(-0.2, 0.2, cout).astype(np.float32)
+    g, r = gpu.pfn_layers[0], ref.pfn_layers[0]
+    g.weight.data = torch.from_numpy(w)
+    g.bn_weight.data, g.bn_bias.data = torch.from_numpy(gamma), torch.from_numpy(beta)
+    r.weight, r.gamma, r.beta = w, gamma, beta
+    if not use_norm:
+        b = rng.uniform(-0.1, 0.1, cout).astype(np.float32)
+        g.bias.data = torch.from_numpy(b)
+        r.bias = b
+    return gpu.to(DEV), ref
+
+
+@pytest.mark.parametrize("mode", ["train", "eval", "nonorm"])
+def test_pfn_vs_oracle(mode):
+    pts = np.concatenate([synth.lidar_frame(6000, 1), synth.lidar_frame(5000, 2)])
+    v0, c0, n0 = capi.points_to_voxel(pts[:6000], synth.KITTI_VOXEL_SIZE, synth.KITTI_PC_RANGE, 100, True, 12000)
+    v1, c1, n1 = capi.points_to_voxel(pts[6000:], synth.KITTI_VOXEL_SIZE, synth.KITTI_PC_RANGE, 100, True, 12000)
+    voxels = np.concatenate([v0, v1]); num = np.concatenate([n0, n1])
+    coors = pillars_np.merge_coordinates([c0, c1])
+    gpu, ref = _pfn_pair(3, use_norm=(mode != "nonorm"))
+    if mode == "eval":
+        rng = np.random.default_rng(8)
+        m = rng.uniform(-1, 1, 64).astype(np.float32); var = rng.uniform(20, 60, 64).astype(np.float32)
+        gpu.pfn_layers[0]._mean.copy_(torch.from_numpy(m)); gpu.pfn_layers[0]._variance.copy_(torch.from_numpy(var))
+        ref.pfn_layers[0]._mean, ref.pfn_layers[0]._variance = m, var
+        gpu.eval(); ref.pfn_layers[0].training = False
+    out = gpu(_cu(voxels), _cu(num), _cu(coors))
+    exp = ref(voxels, num, coors)
+    assert tuple(out.shape) == exp.shape == (voxels.shape[0], 64)
+    np.testing.assert_allclose(out.cpu().numpy(), exp, **TOL)
+
+
+def test_scatter_bit_exact_and_fused_device_path():
+    frames = [synth.lidar_frame(20000, 0), synth.lidar_frame(20000, 5, shuffle=True)]
+    vox = [capi.points_to_voxel(f, synth.KITTI_VOXEL_SIZE, synth.KITTI_PC_RANGE, 100, True, 12000) for f in frames]
+    coors = pillars_np.merge_coordinates([v[1] for v in vox])
+    P = coors.shape[0]
+    feat = np.random.default_rng(1).standard_normal((P, 64)).astype(np.float32)
+    ref = pillars_np.PointPillarsScatter([1, 1, 496, 432], 64)(feat, coors, 2)
+    out = pillars.PointPillarsScatter([1, 1, 496, 432], 64)(_cu(feat), _cu(coors), 2)
+    assert tuple(out.shape) == (2, 64, 496, 432)
+    np.testing.assert_array_equal(out.cpu().numpy(), ref)
+    # an empty frame in the batch stays all-zero (pillars.py:127, 135-136)
+    out3 = pillars.PointPillarsScatter([1, 1, 496, 432], 64)(_cu(feat), _cu(coors), 3)
+    assert out3[2].abs().sum().item() == 0
+    # end to end on device without host sync: voxelise -> PFN -> scatter via num_valid
+    gpu, ref_pfn = _pfn_pair(4)
+    dv, dc, dn, dnum = pillars.points_to_voxel_device(_cu(frames[0]), synth.KITTI_VOXEL_SIZE,
+                                                      synth.KITTI_PC_RANGE, 100, True, 12000)
+    dcoors = torch.cat([torch.zeros((dc.shape[0], 1), dtype=torch.int32, device=DEV), dc], 1)
+    f = gpu(dv, dn, dcoors, num_valid=dnum)
+    canvas = pillars.PointPillarsScatter([1, 1, 496, 432], 64)(f, dcoors, 1, num_valid=dnum)
+    v, c, n = vox[0]
+    cc = pillars_np.merge_coordinates([c])
+    exp = pillars_np.PointPillarsScatter([1, 1, 496, 432], 64)(ref_pfn(v, n, cc), cc, 1)
+    np.testing.assert_allclose(canvas.cpu().numpy(), exp, **TOL)

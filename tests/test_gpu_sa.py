@@ -1,0 +1,242 @@
+"""GPU parity tests of the SetAbstraction path: CUDA (through the C ABI) vs the CPU oracle on the
+same seeded inputs.  Bit-exact for indices / gathers; fp32 features within 1e-5 (abs + rel)."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import capi, layers_np  # noqa: E402
+from papc_b200 import layers, synth  # noqa: E402
+
+DEV = "cuda:0"
+TOL = dict(rtol=1e-5, atol=1e-5)  # the north-star tolerance for fp32 MLP / pool outputs
+
+
+def _cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def _xyz(B, N, seed=0):
+    return np.ascontiguousarray(synth.clouds(B, N, seed).transpose(0, 2, 1))
+
+
+# ------------------------------------------------------------------ KATs through the C ABI
+def _line(xs):
+    return np.array([[[x, 0.0, 0.0] for x in xs]], np.float32)
+
+
+def test_kat_k1_k2_fps():
+    out = layers.farthest_point_sample(_cu(_line([0, .1, .5, .9])), 3, start_idx=[0])
+    assert out.dtype == torch.float32 and out.cpu().tolist() == [[0.0, 3.0, 2.0]]
+    out = layers.farthest_point_sample_idx(_cu(_line([0, 2, 3])), 3, start_idx=[0])
+    assert out.cpu().tolist() == [[0, 1, 2]]  # clamp quirk (distance initialised to 1.0)
+
+
+def test_kat_k3_k4_ball_query():
+    xyz = _line([0, .1, .15, .3, .19, .7])
+    q = xyz[:, :1, :]
+    assert layers.query_ball_point(0.2, 3, _cu(xyz), _cu(q)).cpu().tolist() == [[[0, 1, 2]]]
+    assert layers.query_ball_point(0.2, 6, _cu(xyz), _cu(q)).cpu().tolist() == [[[0, 1, 2, 4, 0, 0]]]
+    xyz4 = _line([0, .1, .15, .3, .2, .7])
+    assert layers.query_ball_point(0.2, 6, _cu(xyz4), _cu(q)).cpu().tolist() == [[[0, 1, 2, 0, 0, 0]]]
+
+
+# ------------------------------------------------------------------ primitives vs oracle
+@pytest.mark.parametrize("B,N,npoint", [(32, 1024, 512), (32, 512, 128), (16, 2048, 512), (3, 100, 100),
+                                        (2, 33, 7), (2, 5000, 64), (1, 9000, 16), (5, 1, 1)])
+def test_fps_bit_exact(B, N, npoint):
+    xyz = _xyz(B, N, seed=B + N)
+    for start in (synth.fps_start(B, N, seed=1), np.zeros(B, np.int64)):
+        ref = capi.farthest_point_sample(xyz, npoint, start)
+        idx, new_xyz = layers.farthest_point_sample_idx(_cu(xyz), npoint, _cu(start), return_xyz=True)
+        np.testing.assert_array_equal(idx.cpu().numpy(), ref)
+        np.testing.assert_array_equal(new_xyz.cpu().numpy(), layers_np.index_points(xyz, ref))
+
+
+def test_fps_duplicates_and_ties():
+    # duplicated points and an all-equal cloud: ties must resolve to the lowest index
+    xyz = _xyz(2, 64, seed=9)
+    xyz[:, 32:] = xyz[:, :32]
+    start = np.array([5, 40], np.int64)
+    np.testing.assert_array_equal(layers.farthest_point_sample_idx(_cu(xyz), 64, _cu(start)).cpu().numpy(),
+                                  capi.farthest_point_sample(xyz, 64, start))
+    same = np.zeros((1, 16, 3), np.float32)
+    np.testing.assert_array_equal(layers.farthest_point_sample_idx(_cu(same), 4, [3]).cpu().numpy(),
+                                  capi.farthest_point_sample(same, 4, [3]))
+
+
+@pytest.mark.parametrize("B,N,S,r,K", [(32, 1024, 512, 0.2, 32), (32, 512, 128, 0.4, 64),
+                                       (16, 2048, 512, 0.1, 32), (16, 2048, 512, 0.4, 128),
+                                       (2, 5000, 77, 0.3, 48), (3, 37, 37, 0.5, 37), (2, 64, 9, 10.0, 64)])
+def test_ball_query_bit_exact(B, N, S, r, K):
+    xyz = _xyz(B, N, seed=N + S)
+    fps = capi.farthest_point_sample(xyz, S, synth.fps_start(B, N))
+    new_xyz = layers_np.index_points(xyz, fps)
+    ref, empty = capi.query_ball_point(r, K, xyz, new_xyz)
+    assert empty == 0
+    out = layers.query_ball_point(r, K, _cu(xyz), _cu(new_xyz), check_empty=True)
+    assert out.dtype == torch.int64
+    np.testing.assert_array_equal(out.cpu().numpy(), ref)
+    out32 = layers._ball_query(r, K, _cu(xyz), _cu(new_xyz), torch.int32)
+    np.testing.assert_array_equal(out32.cpu().numpy().astype(np.int64), ref)
+
+
+def test_ball_query_errors():
+    xyz = _xyz(1, 16)
+    with pytest.raises(ValueError):
+        layers.query_ball_point(0.2, 17, _cu(xyz), _cu(xyz[:, :2]))
+    far = np.full((1, 1, 3), 50.0, np.float32)
+    with pytest.raises(IndexError):
+        layers.query_ball_point(0.2, 4, _cu(xyz), _cu(far), check_empty=True)
+    out = layers.query_ball_point(0.2, 4, _cu(xyz), _cu(far))
+    assert (out.cpu().numpy() == 16).all()  # N in every slot, as the reference's sort leaves it
+
+
+def test_square_distance_and_index_points():
+    rng = np.random.default_rng(0)
+    a = rng.uniform(-1, 1, (3, 50, 3)).astype(np.float32)
+    b = rng.uniform(-1, 1, (3, 70, 3)).astype(np.float32)
+    np.testing.assert_array_equal(layers.square_distance(_cu(a), _cu(b)).cpu().numpy(),
+                                  capi.square_distance(a, b))
+    pts = rng.standard_normal((3, 50, 7)).astype(np.float32)
+    idx2 = rng.integers(0, 50, (3, 11))
+    idx3 = rng.integers(0, 50, (3, 11, 5))
+    np.testing.assert_array_equal(layers.index_points(_cu(pts), _cu(idx2)).cpu().numpy(),
+                                  layers_np.index_points(pts, idx2))
+    np.testing.assert_array_equal(layers.index_points(_cu(pts), _cu(idx3.astype(np.float32))).cpu().numpy(),
+                                  layers_np.index_points(pts, idx3))
+    pts8 = rng.standard_normal((3, 50, 8)).astype(np.float32)  # float4 path
+    np.testing.assert_array_equal(layers.index_points(_cu(pts8), _cu(idx3)).cpu().numpy(),
+                                  layers_np.index_points(pts8, idx3))
+
+
+@pytest.mark.parametrize("D", [0, 5, 8])
+def test_sample_and_group_bit_exact(D):
+    B, N, S, K = 3, 300, 40, 12
+    xyz = _xyz(B, N, seed=4)
+    feats = np.random.default_rng(5).standard_normal((B, N, D)).astype(np.float32) if D else None
+    start = synth.fps_start(B, N, seed=6)
+    rx, rp, rg, rf = layers_np.sample_and_group(S, 0.35, K, xyz, feats, returnfps=True, start_idx=start)
+    gx, gp, gg, gf = layers.sample_and_group(S, 0.35, K, _cu(xyz), _cu(feats) if D else None,
+                                             returnfps=True, start_idx=_cu(start))
+    np.testing.assert_array_equal(gx.cpu().numpy(), rx)
+    np.testing.assert_array_equal(gf.cpu().numpy(), rf)
+    np.testing.assert_array_equal(gg.cpu().numpy(), rg)
+    np.testing.assert_array_equal(gp.cpu().numpy(), rp)
+    ax, ap = layers.sample_and_group_all(_cu(xyz), _cu(feats) if D else None)
+    ox, op = layers_np.sample_and_group_all(xyz, feats)
+    np.testing.assert_array_equal(ax.cpu().numpy(), ox)
+    np.testing.assert_array_equal(ap.cpu().numpy(), op)
+
+
+# ------------------------------------------------------------------ grouped MLP vs oracle
+def _set_params(gpu_convs, gpu_bns, ref_convs, ref_bns, params, rng):
+    for l, p in enumerate(params):
+        w4 = p["weight"].reshape(*p["weight"].shape, 1, 1)
+        gamma = rng.uniform(0.5, 1.5, p["gamma"].shape).astype(np.float32)
+        gamma[::7] *= -1  # negative BN scales exercise the min-pool branch
+        beta = rng.uniform(-0.2, 0.2, p["beta"].shape).astype(np.float32)
+        gpu_convs[l].weight, gpu_convs[l].bias = _cu(w4), _cu(p["bias"])
+        gpu_bns[l].weight, gpu_bns[l].bias = _cu(gamma), _cu(beta)
+        ref_convs[l].weight, ref_convs[l].bias = w4, p["bias"]
+        ref_bns[l].weight, ref_bns[l].bias = gamma, beta
+
+
+@pytest.mark.parametrize("B,S,K,cin,mlp", [(2, 16, 32, 3, [64, 64, 128]), (2, 8, 64, 131, [128, 128, 256]),
+                                           (3, 1, 128, 259, [256, 512, 1024]), (2, 5, 12, 10, [20, 36]),
+                                           (1, 3, 7, 6, [9]), (2, 4, 256, 19, [32, 48])])
+def test_grouped_mlp_explicit_input(B, S, K, cin, mlp):
+    rng = np.random.default_rng(cin)
+    x = rng.standard_normal((B, S, K, cin)).astype(np.float32)
+    params = synth.mlp_params(cin, mlp, seed=cin)
+    convs = [layers.Conv2D(1, 1) for _ in mlp]
+    bns = [layers.BatchNorm2D(c) for c in mlp]
+    rconvs = [layers_np.Conv2D1x1(1, 1) for _ in mlp]
+    rbns = [layers_np.BatchNorm2D(c) for c in mlp]
+    _set_params(convs, bns, rconvs, rbns, params, rng)
+    ref, stats = layers_np.grouped_mlp(x, [c.weight.reshape(c.weight.shape[0], -1) for c in rconvs],
+                                       [c.bias for c in rconvs], [b.weight for b in rbns],
+                                       [b.bias for b in rbns])
+    out = layers.grouped_mlp(_cu(x), convs, bns)
+    assert tuple(out.shape) == (B, mlp[-1], S)
+    np.testing.assert_allclose(out.cpu().numpy(), ref, **TOL)
+
+
+@pytest.mark.parametrize("cfg", ["ssg_sa1", "ssg_sa2", "group_all", "msg"])
+@pytest.mark.parametrize("bn_mode", ["batch", "running"])
+def test_set_abstraction_layer(cfg, bn_mode):
+    rng = np.random.default_rng(11)
+    B, N = 4, 512
+    xyz = synth.clouds(B, N, seed=3)
+    start = synth.fps_start(B, N, seed=4)
+    if cfg == "ssg_sa1":
+        D, args = 0, (128, 0.2, 32, 3, [64, 64, 128], False)
+    elif cfg == "ssg_sa2":
+        D, args = 128, (64, 0.4, 64, 131, [128, 128, 256], False)
+    elif cfg == "group_all":
+        D, args = 61, (None, None, None, 64, [64, 128, 256], True)
+    else:
+        D, args = 6, None
+    feats = rng.standard_normal((B, D, N)).astype(np.float32) if D else None
+    if cfg != "msg":
+        gpu = layers.PointNetSetAbstraction(*args)
+        ref = layers_np.PointNetSetAbstraction(*args)
+        _set_params(gpu.mlp_convs, gpu.mlp_bns, ref.mlp_convs, ref.mlp_bns,
+                    synth.mlp_params(args[3], args[4], seed=5), rng)
+        blocks = [(gpu.mlp_bns, ref.mlp_bns)]
+    else:
+        margs = (64, [0.2, 0.4, 0.8], [16, 32, 64], D, [[32, 32, 64], [64, 64, 128], [64, 96, 128]])
+        gpu = layers.PointNetSetAbstractionMsg(*margs)
+        ref = layers_np.PointNetSetAbstractionMsg(*margs)
+        for i, m in enumerate(margs[4]):
+            _set_params(gpu.conv_blocks[i], gpu.bn_blocks[i], ref.conv_blocks[i], ref.bn_blocks[i],
+                        synth.mlp_params(D + 3, m, seed=6 + i), rng)
+        blocks = list(zip(gpu.bn_blocks, ref.bn_blocks))
+    if bn_mode == "running":
+        gpu.bn_mode = "running"
+        for gb, rb in blocks:
+            for g, r in zip(gb, rb):
+                m = rng.uniform(-0.3, 0.3, r._mean.shape).astype(np.float32)
+                v = rng.uniform(0.5, 2.0, r._variance.shape).astype(np.float32)
+                g._mean, g._variance = _cu(m), _cu(v)
+                r._mean, r._variance, r.training = m, v, False
+    gpu.to(DEV)
+    gx, gp = gpu(_cu(xyz), _cu(feats) if D else None, start_idx=_cu(start))
+    rx, rp = ref(xyz, feats, start_idx=start)
+    assert tuple(gx.shape) == rx.shape and tuple(gp.shape) == rp.shape
+    np.testing.assert_array_equal(gx.cpu().numpy(), rx)
+    np.testing.assert_allclose(gp.cpu().numpy(), rp, **TOL)
+
+
+def test_ssg_stack_c2_full_size_vs_oracle():
+    """BASELINE config 2 at full size (B=32, N=1024, the three SSG SetAbstraction layers of
+    PointNet2_SSG_Clas, classify/pointnet2/pointnet2.py:11-16) against the oracle."""
+    B, N = 32, 1024
+    rng = np.random.default_rng(21)
+    xyz = synth.clouds(B, N, seed=0)
+    start = synth.fps_start(B, N, seed=1)
+    cfgs = [(512, 0.2, 32, 3, [64, 64, 128], False), (128, 0.4, 64, 131, [128, 128, 256], False),
+            (None, None, None, 259, [256, 512, 1024], True)]
+    gpu_layers, ref_layers = [], []
+    for i, c in enumerate(cfgs):
+        g, r = layers.PointNetSetAbstraction(*c), layers_np.PointNetSetAbstraction(*c)
+        _set_params(g.mlp_convs, g.mlp_bns, r.mlp_convs, r.mlp_bns, synth.mlp_params(c[3], c[4], seed=2 + i), rng)
+        gpu_layers.append(g.to(DEV))
+        ref_layers.append(r)
+    starts = [start, np.zeros(B, np.int64), None]
+    gx, gp = _cu(xyz), None
+    rx, rp = xyz, None
+    for g, r, st in zip(gpu_layers, ref_layers, starts):
+        gx, gp = g(gx, gp, start_idx=_cu(st) if st is not None else None)
+        rx, rp = r(rx, rp, start_idx=st)
+        assert tuple(gx.shape) == rx.shape and tuple(gp.shape) == rp.shape
+        np.testing.assert_array_equal(gx.cpu().numpy(), rx)
+        np.testing.assert_allclose(gp.cpu().numpy(), rp, **TOL)
+        # feed the ORACLE's features forward on both sides so each layer is judged on equal inputs
+        gp = _cu(rp)
+    assert tuple(gp.shape) == (B, 1024, 1)
+    # determinism: same inputs -> bit-identical outputs
+    a = gpu_layers[0](_cu(xyz), None, start_idx=_cu(start))[1]
+    b = gpu_layers[0](_cu(xyz), None, start_idx=_cu(start))[1]
+    assert torch.equal(a, b)

@@ -1,0 +1,24 @@
+#!/bin/bash
+# One gpurun call: GPU parity tests, smoke, bench, ncu launch list.  Logs land in gpurun_out/.
+# usage: gpurun --timeout 1500 -- 'bash tools/gpu_check.sh [tests] [bench] [ncu]'
+mkdir -p gpurun_out
+what="${*:-tests smoke bench ncu}"
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
+if [[ "$what" == *tests* ]]; then
+  timeout 1200 python -m pytest tests -m gpu -q --timeout 600 -p no:cacheprovider > gpurun_out/pytest.log 2>&1
+  echo "pytest exit $?" >> gpurun_out/pytest.log
+  tail -60 gpurun_out/pytest.log
+fi
+if [[ "$what" == *smoke* ]]; then
+  timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
+  echo "smoke exit $?" >> gpurun_out/smoke.log; tail -5 gpurun_out/smoke.log
+fi
+if [[ "$what" == *bench* ]]; then
+  timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err
+  echo "bench exit $?"; tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json
+fi
+if [[ "$what" == *ncu* ]]; then
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
+     --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_bench.log 2>&1
+  echo "ncu exit $?"; tail -3 gpurun_out/ncu_bench.log | cut -c1-300
+fi
