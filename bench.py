@@ -362,11 +362,14 @@ def layer_roofline(torch, lib, layers, synth, dev, B):
             pmax = torch.empty((B * s, co), device=dev) if last else None
             pmin = torch.empty((B * s, co), device=dev) if last else None
             partial = torch.empty((lib.papc_mlp_stats_partial_rows(M), 2, co), dtype=torch.float64, device=dev)
+            lwsb = lib.papc_mlp_layer_workspace_bytes(c, co)
+            lws = torch.empty(max(lwsb, 256), dtype=torch.uint8, device=dev)
 
             def launch():
                 L.check(lib.papc_mlp_layer_forward_f32(C.byref(src) if li == 0 else None, L.ptr(x), L.ptr(scale),
                                                        L.ptr(shift), M, c, co, k, L.ptr(w), L.ptr(bias), L.ptr(y),
-                                                       L.ptr(pmax), L.ptr(pmin), L.ptr(partial), st), "layer")
+                                                       L.ptr(pmax), L.ptr(pmin), L.ptr(partial), L.ptr(lws), lwsb,
+                                                       st), "layer")
             for _ in range(3):
                 launch()
             torch.cuda.synchronize()

@@ -167,18 +167,22 @@ int papc_sa_mlp_f32(const papc_group_source *src, const papc_mlp *mlp, float *ou
  *     y [M,cout] (nullable when pooling) receives the pre-BN output; pool_max / pool_min
  *     [M/K,cout] (nullable) receive the per-group extrema of y (valid because BN+ReLU is
  *     monotone per channel, so max_k relu(bn(y_k)) = relu(bn(max_k y_k or min_k y_k))).
- *     stats_partial: double [papc_mlp_stats_partial_rows(M), 2, cout] per-tile sums of y, y^2.
+ *     stats_partial: double [papc_mlp_stats_partial_rows(M), 2, cout] per-CTA sums of y, y^2.
+ *     workspace: papc_mlp_layer_workspace_bytes(cin, cout) bytes (the hi/lo-split, swizzled weight
+ *     image of the tcgen05 kernel); without it the layer runs on the fp32 SIMT kernel.
  *   papc_mlp_stats_reduce_f64: fixed-order reduction -> sums double [2,cout].
  *   papc_bn_scale_shift_f32: sums (already summed over ranks) + count -> scale, shift (and
  *     optionally mean / biased var).
  *   papc_sa_pool_finish_f32: out = relu(scale * (scale>=0 ? pool_max : pool_min) + shift).
  */
 int64_t papc_mlp_stats_partial_rows(int64_t M);
+size_t papc_mlp_layer_workspace_bytes(int32_t cin, int32_t cout);
 int papc_mlp_layer_forward_f32(const papc_group_source *src, const float *x,
                                const float *in_scale, const float *in_shift, int64_t M,
                                int32_t cin, int32_t cout, int32_t K, const float *weight,
                                const float *bias, float *y, float *pool_max, float *pool_min,
-                               double *stats_partial, papc_stream_t stream);
+                               double *stats_partial, void *workspace, size_t workspace_bytes,
+                               papc_stream_t stream);
 int papc_mlp_stats_reduce_f64(const double *stats_partial, int64_t partial_rows, int32_t cout,
                               double *sums, papc_stream_t stream);
 int papc_bn_scale_shift_f32(const double *sums, double count, const float *gamma,

@@ -64,8 +64,10 @@ _SIGNATURES = {
     "papc_sa_mlp_workspace_bytes": (_SZ, [C.POINTER(GroupSource), C.POINTER(Mlp)]),
     "papc_sa_mlp_f32": (_I, [C.POINTER(GroupSource), C.POINTER(Mlp), _vp, _I, _vp, _SZ, _vp]),
     "papc_mlp_stats_partial_rows": (_I64, [_I64]),
+    "papc_mlp_layer_workspace_bytes": (_SZ, [C.c_int32, C.c_int32]),
     "papc_mlp_layer_forward_f32": (_I, [C.POINTER(GroupSource), _vp, _vp, _vp, _I64, C.c_int32,
-                                         C.c_int32, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+                                         C.c_int32, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _SZ,
+                                         _vp]),
     "papc_mlp_stats_reduce_f64": (_I, [_vp, _I64, C.c_int32, _vp, _vp]),
     "papc_bn_scale_shift_f32": (_I, [_vp, _D, _vp, _vp, _F, C.c_int32, _vp, _vp, _vp, _vp, _vp]),
     "papc_bn_running_scale_shift_f32": (_I, [_vp, _vp, _vp, _vp, _F, C.c_int32, _vp, _vp, _vp]),

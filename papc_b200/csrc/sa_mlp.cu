@@ -13,7 +13,10 @@
 //              max-pool is taken before BN+ReLU (exact: BN+ReLU is monotone per channel).
 // The train-mode BatchNorm is the only grid-wide dependency, hence one launch per layer plus
 // a tiny statistics kernel in between.
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "sa_mlp_tc.cuh"
 
 namespace papc {
 
@@ -37,7 +40,7 @@ struct LayerArgs {
     float *y;
     float *pool_max, *pool_min;
     int pool_mode;
-    double *stats_partial;  // [tiles_m][2][cout]
+    double *stats_partial;  // [row CTAs][2][cout]
     int vec_a, vec_w, vec_y;  // 16-byte fast paths allowed
 };
 
@@ -66,13 +69,24 @@ mlp_layer_kernel(const LayerArgs a) {
     const int tx = tid & 15;
     const int ty = tid >> 4;
     const int nt = ceil_div(a.cout, BN);
-    const long long tile_m = blockIdx.x / nt;
     const int tile_n = blockIdx.x % nt;
-    const long long m0 = tile_m * BM;
     const int n0 = tile_n * BN;
     const int cin = a.cin;
     const int KT = ceil_div(cin, BK);
+    // persistent over the row tiles: CTA (mi, tile_n) handles tiles mi, mi+gm, ... so the batch
+    // statistics leave the kernel as ONE fp64 partial row per CTA (fixed order -> deterministic)
+    const long long tiles_m = ceil_div<long long>(a.M, BM);
+    const long long gm = gridDim.x / nt;
+    long long m0 = 0;
+    double acc_s = 0.0, acc_q = 0.0;  // threads tid < BN: running column sums over this CTA's tiles
 
+    // ---- global -> register staging ------------------------------------------------------
+    // A tile: 128 rows x 16 k = 512 float4; thread handles (row = q/4, k4 = q%4) for q = tid, tid+256.
+    // W tile: BN cols x 16 k; thread handles (n = q/4, k4 = q%4) for q = tid (+256 if BN == 128).
+    float4 ra[2];
+    float4 rw[BN / 64];
+
+    auto stage_gather_rows = [&]() {
     if (GATHER) {
         for (int r = tid; r < BM; r += kThreads) {
             const long long row = m0 + r;
@@ -92,12 +106,7 @@ mlp_layer_kernel(const LayerArgs a) {
         }
         __syncthreads();
     }
-
-    // ---- global -> register staging ------------------------------------------------------
-    // A tile: 128 rows x 16 k = 512 float4; thread handles (row = q/4, k4 = q%4) for q = tid, tid+256.
-    // W tile: BN cols x 16 k; thread handles (n = q/4, k4 = q%4) for q = tid (+256 if BN == 128).
-    float4 ra[2];
-    float4 rw[BN / 64];
+    };
 
     auto load_a = [&](int kt) {
 #pragma unroll
@@ -205,6 +214,10 @@ mlp_layer_kernel(const LayerArgs a) {
         }
     };
 
+    for (long long tile_m = blockIdx.x / nt; tile_m < tiles_m; tile_m += gm) {
+    m0 = tile_m * BM;
+    stage_gather_rows();
+
     float acc[8][TN];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -309,9 +322,8 @@ mlp_layer_kernel(const LayerArgs a) {
                 S += (double)red_s[t * BN + tid];
                 Q += (double)red_q[t * BN + tid];
             }
-            double *sp = a.stats_partial + tile_m * 2 * a.cout;
-            sp[n0 + tid] = S;
-            sp[a.cout + n0 + tid] = Q;
+            acc_s += S;
+            acc_q += Q;
         }
         __syncthreads();
     }
@@ -371,6 +383,14 @@ mlp_layer_kernel(const LayerArgs a) {
             }
         }
     }
+    __syncthreads();  // the scratch aliases the operand tiles of the next row tile
+    }  // row-tile loop
+
+    if (a.stats_partial != nullptr && tid < BN && n0 + tid < a.cout) {
+        double *sp = a.stats_partial + (long long)(blockIdx.x / nt) * 2 * a.cout;
+        sp[n0 + tid] = acc_s;
+        sp[a.cout + n0 + tid] = acc_q;
+    }
 }
 
 // ------------------------------------------------------------------ small kernels
@@ -396,6 +416,44 @@ stats_reduce_kernel(const double *__restrict__ partial, long long T, int C2,
 #pragma unroll
         for (int i = 0; i < 16; ++i) tot += s[i][threadIdx.x];
         sums[c] = tot;
+    }
+}
+
+// Fused form of the two kernels below for the single-GPU driver: fixed-order reduction of the
+// per-CTA partials for 32 channels per block, then scale / shift (and mean / var) directly.
+__global__ void __launch_bounds__(512)
+bn_from_partials_kernel(const double *__restrict__ partial, long long T, int C, double count,
+                        const float *__restrict__ gamma, const float *__restrict__ beta, float eps,
+                        float *__restrict__ scale, float *__restrict__ shift,
+                        float *__restrict__ mean_out, float *__restrict__ var_out) {
+    __shared__ double s_s[16][33], s_q[16][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    double as = 0.0, aq = 0.0;
+    if (c < C)
+        for (long long t = threadIdx.y; t < T; t += 16) {
+            as += partial[t * 2 * C + c];
+            aq += partial[t * 2 * C + C + c];
+        }
+    s_s[threadIdx.y][threadIdx.x] = as;
+    s_q[threadIdx.y][threadIdx.x] = aq;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        double S = 0.0, Q = 0.0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            S += s_s[i][threadIdx.x];
+            Q += s_q[i][threadIdx.x];
+        }
+        const double mean = S / count;
+        double var = Q / count - mean * mean;
+        var = var > 0.0 ? var : 0.0;
+        const double g = gamma ? (double)gamma[c] : 1.0;
+        const double b = beta ? (double)beta[c] : 0.0;
+        const double sc = g / sqrt(var + (double)eps);
+        scale[c] = (float)sc;
+        shift[c] = (float)(b - mean * sc);
+        if (mean_out) mean_out[c] = (float)mean;
+        if (var_out) var_out[c] = (float)var;
     }
 }
 
@@ -478,8 +536,15 @@ pool_finish_bcs_kernel(const float *__restrict__ pmax, const float *__restrict__
 
 static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// Row-tile CTAs per launch: persistent beyond 2 resident CTAs per SM.
+static long long grid_rows(long long M) {
+    const long long tiles_m = ceil_div<long long>(M, BM);
+    const long long cap = 2LL * kNumSMs;
+    return tiles_m < cap ? tiles_m : cap;
+}
+
 static int launch_layer(const LayerArgs &a, bool gather, cudaStream_t st) {
-    const long long tiles_m = ceil_div<long long>(a.M, BM);
+    const long long tiles_m = grid_rows(a.M);
     if (a.cout <= 64) {
         const long long grid = tiles_m * ceil_div(a.cout, 64);
         if (grid > 0x7fffffffLL) return PAPC_EUNSUPPORTED;
@@ -519,14 +584,24 @@ static int validate_src(const papc_group_source *s, int cin) {
 
 using namespace papc;
 
-extern "C" int64_t papc_mlp_stats_partial_rows(int64_t M) { return ceil_div<long long>(M, BM); }
+extern "C" int64_t papc_mlp_stats_partial_rows(int64_t M) { return grid_rows(M); }
+
+static bool tc_enabled() {
+    const char *e = getenv("PAPC_MLP_TC");  // "0" forces the fp32 SIMT kernel (A/B testing)
+    return !(e && e[0] == '0');
+}
+
+extern "C" size_t papc_mlp_layer_workspace_bytes(int32_t cin, int32_t cout) {
+    if (cin <= 0 || cout <= 0) return 0;
+    return align_up(tc::wimg_bytes(cin, cout), 256);
+}
 
 extern "C" int papc_mlp_layer_forward_f32(const papc_group_source *src, const float *x,
                                           const float *in_scale, const float *in_shift, int64_t M,
                                           int32_t cin, int32_t cout, int32_t K, const float *weight,
                                           const float *bias, float *y, float *pool_max,
-                                          float *pool_min, double *stats_partial,
-                                          papc_stream_t stream) {
+                                          float *pool_min, double *stats_partial, void *workspace,
+                                          size_t workspace_bytes, papc_stream_t stream) {
     if (M < 0 || cin <= 0 || cout <= 0 || K <= 0 || !weight) return PAPC_EINVAL;
     if (M == 0) return PAPC_OK;
     if ((pool_max == nullptr) != (pool_min == nullptr)) return PAPC_EINVAL;
@@ -552,8 +627,32 @@ extern "C" int papc_mlp_layer_forward_f32(const papc_group_source *src, const fl
     a.K = K; a.M = M; a.cin = cin; a.cout = cout; a.W = weight; a.bias = bias;
     a.y = y; a.pool_max = pool_max; a.pool_min = pool_min; a.stats_partial = stats_partial;
     a.pool_mode = POOL_NONE;
+    if (pool_max && M % K != 0) return PAPC_EINVAL;
+    if (gather) a.vec_a = (a.D % 4 == 0) && a.D > 0 && aligned16(a.feats);
+    else a.vec_a = (cin % 4 == 0) && aligned16(a.x);
+    a.vec_w = (cin % 4 == 0) && aligned16(weight);
+    a.vec_y = (cout % 4 == 0) && (y == nullptr || aligned16(y));
+
+    // ---- tensor-core path (tcgen05, 3xTF32) whenever the shape fits; else fp32 SIMT
+    tc::TcProblem prob{cin, cout, K, gather ? a.D : 0, gather, pool_max != nullptr};
+    const size_t wneed = papc_mlp_layer_workspace_bytes(cin, cout);
+    const bool a_ok = gather ? (a.D == 0 || aligned16(a.feats))
+                             : (aligned16(a.x) && (a.in_scale == nullptr ||
+                                                   (aligned16(a.in_scale) && aligned16(a.in_shift))));
+    if (tc_enabled() && workspace != nullptr && workspace_bytes >= wneed && aligned16(workspace) &&
+        a_ok && M >= 128 && tc::eligible(prob)) {
+        tc::TcArgs t{};
+        t.xyz = a.xyz; t.new_xyz = a.new_xyz; t.feats = a.feats; t.idx = a.idx;
+        t.N = a.N; t.S = a.S; t.K = K; t.D = a.D;
+        t.x = a.x; t.in_scale = a.in_scale; t.in_shift = a.in_shift;
+        t.M = M; t.cin = cin; t.cout = cout; t.bias = bias; t.y = y;
+        t.pool_max = pool_max; t.pool_min = pool_min; t.stats_partial = stats_partial;
+        t.partial_rows = grid_rows(M);
+        t.vec_y = a.vec_y;
+        return tc::launch(t, weight, reinterpret_cast<float *>(workspace), gather, a.order, st);
+    }
+
     if (pool_max) {
-        if (M % K != 0) return PAPC_EINVAL;
         if (K % 4 == 0 && K <= BM && BM % K == 0) {
             a.pool_mode = POOL_TILE;
         } else {
@@ -565,10 +664,6 @@ extern "C" int papc_mlp_layer_forward_f32(const papc_group_source *src, const fl
             if (rc != PAPC_OK) return rc;
         }
     }
-    if (gather) a.vec_a = (a.D % 4 == 0) && a.D > 0 && aligned16(a.feats);
-    else a.vec_a = (cin % 4 == 0) && aligned16(a.x);
-    a.vec_w = (cin % 4 == 0) && aligned16(weight);
-    a.vec_y = (cout % 4 == 0) && (y == nullptr || aligned16(y));
     return launch_layer(a, gather, st);
 }
 
@@ -631,7 +726,7 @@ extern "C" int papc_sa_pool_finish_f32(const float *pool_max, const float *pool_
 // ---- monolithic driver: workspace carving ------------------------------------------------
 namespace {
 struct WsPlan {
-    size_t y[2], pool_max, pool_min, partial, sums, scale, shift, total;
+    size_t y[2], pool_max, pool_min, partial, sums, scale, shift, wimg, wimg_bytes, total;
 };
 static int plan_ws(const papc_group_source *src, const papc_mlp *mlp, WsPlan *p) {
     if (!src || !mlp) return PAPC_EINVAL;
@@ -656,10 +751,19 @@ static int plan_ws(const papc_group_source *src, const papc_mlp *mlp, WsPlan *p)
     p->y[1] = take(ybytes[1]);
     p->pool_max = take((size_t)G * clast * sizeof(float));
     p->pool_min = take((size_t)G * clast * sizeof(float));
-    p->partial = take((size_t)ceil_div<long long>(M, BM) * 2 * maxc * sizeof(double));
+    p->partial = take((size_t)grid_rows(M) * 2 * maxc * sizeof(double));
     p->sums = take((size_t)2 * maxc * sizeof(double));
     p->scale = take((size_t)maxc * sizeof(float));
     p->shift = take((size_t)maxc * sizeof(float));
+    size_t wb = 0;
+    int c_in = mlp->cin;
+    for (int l = 0; l < mlp->num_layers; ++l) {
+        const size_t b = papc_mlp_layer_workspace_bytes(c_in, mlp->layers[l].cout);
+        wb = b > wb ? b : wb;
+        c_in = mlp->layers[l].cout;
+    }
+    p->wimg_bytes = wb;
+    p->wimg = take(wb);
     p->total = off;
     return PAPC_OK;
 }
@@ -707,14 +811,14 @@ extern "C" int papc_sa_mlp_f32(const papc_group_source *src, const papc_mlp *mlp
         rc = papc_mlp_layer_forward_f32(l == 0 ? src : nullptr, xprev, l == 0 ? nullptr : scale,
                                         l == 0 ? nullptr : shift, M, cin, ly.cout, src->K, ly.weight,
                                         ly.bias, y, last ? pmax : nullptr, last ? pmin : nullptr,
-                                        batch ? partial : nullptr, stream);
+                                        batch ? partial : nullptr, ws + p.wimg, p.wimg_bytes, stream);
         if (rc != PAPC_OK) return rc;
         if (batch) {
-            rc = papc_mlp_stats_reduce_f64(partial, papc_mlp_stats_partial_rows(M), ly.cout, sums,
-                                           stream);
-            if (rc != PAPC_OK) return rc;
-            rc = papc_bn_scale_shift_f32(sums, (double)M, ly.gamma, ly.beta, mlp->eps, ly.cout, scale,
-                                         shift, ly.batch_mean, ly.batch_var, stream);
+            (void)sums;
+            bn_from_partials_kernel<<<ceil_div(ly.cout, 32), dim3(32, 16), 0, as_stream(stream)>>>(
+                partial, papc_mlp_stats_partial_rows(M), ly.cout, (double)M, ly.gamma, ly.beta, mlp->eps,
+                scale, shift, ly.batch_mean, ly.batch_var);
+            PAPC_LAUNCH_CHECK();
         } else {
             rc = papc_bn_running_scale_shift_f32(ly.running_mean, ly.running_var, ly.gamma, ly.beta,
                                                  mlp->eps, ly.cout, scale, shift, stream);

@@ -280,10 +280,13 @@ class _MlpRunner:
             pmin = torch.empty((G, cout), dtype=torch.float32, device=device) if last else None
             partial = torch.empty((prows, 2, cout), dtype=torch.float64, device=device)
             bias = L.f32c(conv.bias) if conv.bias is not None else None
+            lwsb = lib.papc_mlp_layer_workspace_bytes(cin, cout)
+            lws = _ws(lwsb, device)
             L.check(lib.papc_mlp_layer_forward_f32(C.byref(src) if l == 0 else None, L.ptr(x),
                                                    L.ptr(scale), L.ptr(shift), M, cin, cout, K, L.ptr(w),
                                                    L.ptr(bias), L.ptr(y), L.ptr(pmax), L.ptr(pmin),
-                                                   L.ptr(partial), st), "mlp_layer_forward")
+                                                   L.ptr(partial), L.ptr(lws), lwsb, st),
+                    "mlp_layer_forward")
             sums = torch.empty((2, cout), dtype=torch.float64, device=device)
             L.check(lib.papc_mlp_stats_reduce_f64(L.ptr(partial), prows, cout, L.ptr(sums), st),
                     "mlp_stats_reduce")

@@ -49,7 +49,8 @@ def test_pure_host_queries(built):
     lib = _lib.lib()
     assert lib.papc_fps_workspace_bytes(32, 1024) == 0
     assert lib.papc_fps_workspace_bytes(2, 10000) == 2 * 10000 * 4
-    assert lib.papc_mlp_stats_partial_rows(524288) == 4096
+    assert lib.papc_mlp_stats_partial_rows(524288) == 296
+    assert lib.papc_mlp_stats_partial_rows(4096) == 32
     vs = (ctypes.c_float * 3)(0.16, 0.16, 4.0)
     cr = (ctypes.c_float * 6)(0, -39.68, -3, 69.12, 39.68, 1)
     assert lib.papc_voxelize_workspace_bytes(20000, vs, cr, 12000) >= 432 * 496 * 4

@@ -4,8 +4,13 @@
 mkdir -p gpurun_out
 what="${*:-tests smoke bench ncu}"
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
+if [[ "$what" == *tc* ]]; then
+  timeout 600 python -m pytest tests/test_gpu_tc.py -m gpu -q --timeout 300 -p no:cacheprovider > gpurun_out/pytest_tc.log 2>&1
+  echo "pytest_tc exit $?" >> gpurun_out/pytest_tc.log
+  tail -80 gpurun_out/pytest_tc.log | cut -c1-400
+fi
 if [[ "$what" == *tests* ]]; then
-  timeout 1200 python -m pytest tests -m gpu -q --timeout 600 -p no:cacheprovider > gpurun_out/pytest.log 2>&1
+  timeout 1200 python -m pytest tests -m gpu -q --timeout 600 --deselect tests/test_gpu_tc.py -p no:cacheprovider > gpurun_out/pytest.log 2>&1
   echo "pytest exit $?" >> gpurun_out/pytest.log
   tail -60 gpurun_out/pytest.log
 fi
