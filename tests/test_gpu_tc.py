@@ -88,8 +88,10 @@ def test_tc_plain_layer_vs_fp64(M, cin, cout, K):
         y, pmax, pmin, sums = _run_layer(x, w, bias, scale, shift, K, True, pool, tc=tc)
         name = "tcgen05" if tc else "simt"
         assert np.allclose(y, ref, rtol=2e-6, atol=2e-6 * np.sqrt(cin)), _describe(y, ref, name)
-        np.testing.assert_allclose(sums[0], ref.sum(0), rtol=1e-5, atol=1e-3, err_msg=name)
-        np.testing.assert_allclose(sums[1], (ref ** 2).sum(0), rtol=1e-5, atol=1e-3, err_msg=name)
+        # the tensor-core fp32 accumulator truncates (a ~1e-7 relative bias toward zero per element),
+        # so the statistic sums are checked against sum|y|, not against the (cancelling) sum itself
+        np.testing.assert_allclose(sums[0], ref.sum(0), rtol=0, atol=2e-6 * np.abs(ref).sum(0).max(), err_msg=name)
+        np.testing.assert_allclose(sums[1], (ref ** 2).sum(0), rtol=4e-6, atol=1e-3, err_msg=name)
         if pool:
             g = y.reshape(M // K, K, cout)  # pooled extrema must be exactly those of the stored y
             assert np.array_equal(pmax, g.max(1)) and np.array_equal(pmin, g.min(1)), name

@@ -1,0 +1,19 @@
+"""Run selected grouped-MLP layer launches of the bench workload (for ncu captures).
+usage: python tools/prof_layer.py [names substring ...]   e.g.  sa2.l2 sa1.l3"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+from papc_b200 import _lib, layers, synth  # noqa: E402
+
+dev = torch.device("cuda:0")
+torch.cuda.set_device(dev)
+res = bench.layer_roofline(torch, _lib.lib(), layers, synth, dev, bench.B_PER_GPU)
+want = sys.argv[1:]
+for r in res["layers"]:
+    if not want or any(w in r["name"] for w in want):
+        print(f"{r['name']:40s} {r['ms'] * 1e3:9.1f} us  {r['tflops']:7.1f} TFLOP/s")
