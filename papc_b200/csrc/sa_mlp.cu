@@ -17,6 +17,7 @@
 
 #include "common.cuh"
 #include "sa_mlp_tc.cuh"
+#include "sa_mlp_tt.cuh"
 
 namespace papc {
 
@@ -586,22 +587,91 @@ using namespace papc;
 
 extern "C" int64_t papc_mlp_stats_partial_rows(int64_t M) { return grid_rows(M); }
 
-static bool tc_enabled() {
-    const char *e = getenv("PAPC_MLP_TC");  // "0" forces the fp32 SIMT kernel (A/B testing)
-    return !(e && e[0] == '0');
+// PAPC_MLP_TC selects the grouped-MLP kernel for A/B testing: "0" forces the fp32 SIMT kernel,
+// "1" the shared/shared tcgen05 kernel (sa_mlp_tc.cu); default = the transposed tcgen05 kernel
+// with tensor-memory-resident weights (sa_mlp_tt.cu) wherever the shape fits, then the others.
+static int tc_level() {
+    const char *e = getenv("PAPC_MLP_TC");
+    if (e && e[0] == '0') return 0;
+    if (e && e[0] == '1') return 1;
+    return 2;
 }
+static bool tc_enabled() { return tc_level() >= 1; }
+
+namespace {
+// BatchNorm finalisation fused into the layer kernel (the last CTA computes scale / shift).
+struct FusedBn {
+    unsigned int *counter;
+    const float *gamma, *beta;
+    float eps;
+    double count;
+    float *scale, *shift, *mean_out, *var_out;
+};
+
+// Tries the transposed tcgen05 kernel.  Returns 1 if launched, 0 if the shape is not eligible,
+// < 0 on error.
+static int try_tt(const LayerArgs &a, bool gather, int K, const FusedBn *bn, const float *l0_fold,
+                  cudaStream_t st) {
+    if (tc_level() < 2) return 0;
+    tt::TtArgs t{};
+    t.M = a.M; t.K = K; t.cout = a.cout;
+    t.bias = a.bias; t.y = a.y; t.pool_max = a.pool_max; t.pool_min = a.pool_min;
+    t.stats_partial = a.stats_partial; t.partial_rows = grid_rows(a.M);
+    t.W = a.W; t.wld = a.cin; t.wk0 = 0; t.wxyz = -1;
+    if (l0_fold != nullptr) {
+        // `a` describes the SECOND layer (cin = first layer's cout); rows come from the points
+        t.mode = tt::SRC_POINTMLP;
+        t.cin = a.cin;
+        t.xyz = a.xyz; t.new_xyz = a.new_xyz; t.idx = a.idx; t.N = a.N; t.S = a.S; t.D = 0;
+        t.l0_fold = l0_fold;
+    } else if (gather) {
+        if (a.D < 4 || !aligned16(a.feats)) return 0;
+        t.mode = tt::SRC_GATHER;
+        t.cin = a.D;
+        t.xyz = a.xyz; t.new_xyz = a.new_xyz; t.feats = a.feats; t.idx = a.idx;
+        t.N = a.N; t.S = a.S; t.D = a.D;
+        t.wk0 = a.order == PAPC_XYZ_FIRST ? 3 : 0;
+        t.wxyz = a.order == PAPC_XYZ_FIRST ? 0 : a.D;
+    } else {
+        if (!aligned16(a.x)) return 0;
+        t.mode = tt::SRC_PLAIN;
+        t.cin = a.cin;
+        t.x = a.x; t.in_scale = a.in_scale; t.in_shift = a.in_shift;
+    }
+    const tt::TtProblem prob{t.mode, t.cin, t.cout, K, t.D, a.pool_max != nullptr};
+    if (!tt::eligible(prob)) return 0;
+    if (bn != nullptr && a.stats_partial != nullptr) {
+        t.counter = bn->counter; t.gamma = bn->gamma; t.beta = bn->beta; t.eps = bn->eps;
+        t.count = bn->count; t.scale = bn->scale; t.shift = bn->shift;
+        t.mean_out = bn->mean_out; t.var_out = bn->var_out;
+    }
+    const int rc = tt::launch(t, st);
+    return rc == PAPC_OK ? 1 : rc;
+}
+
+// Shared body of the step-wise entry point and the monolithic driver.  *fused_done is set when the
+// layer kernel also produced the BatchNorm scale / shift.
+static int layer_forward(const papc_group_source *src, const float *x, const float *in_scale,
+                         const float *in_shift, int64_t M, int32_t cin, int32_t cout, int32_t K,
+                         const float *weight, const float *bias, float *y, float *pool_max,
+                         float *pool_min, double *stats_partial, void *workspace,
+                         size_t workspace_bytes, const FusedBn *bn, bool *fused_done,
+                         papc_stream_t stream);
+}  // namespace
 
 extern "C" size_t papc_mlp_layer_workspace_bytes(int32_t cin, int32_t cout) {
     if (cin <= 0 || cout <= 0) return 0;
     return align_up(tc::wimg_bytes(cin, cout), 256);
 }
 
-extern "C" int papc_mlp_layer_forward_f32(const papc_group_source *src, const float *x,
-                                          const float *in_scale, const float *in_shift, int64_t M,
-                                          int32_t cin, int32_t cout, int32_t K, const float *weight,
-                                          const float *bias, float *y, float *pool_max,
-                                          float *pool_min, double *stats_partial, void *workspace,
-                                          size_t workspace_bytes, papc_stream_t stream) {
+namespace {
+static int layer_forward(const papc_group_source *src, const float *x, const float *in_scale,
+                         const float *in_shift, int64_t M, int32_t cin, int32_t cout, int32_t K,
+                         const float *weight, const float *bias, float *y, float *pool_max,
+                         float *pool_min, double *stats_partial, void *workspace,
+                         size_t workspace_bytes, const FusedBn *bn, bool *fused_done,
+                         papc_stream_t stream) {
+    if (fused_done) *fused_done = false;
     if (M < 0 || cin <= 0 || cout <= 0 || K <= 0 || !weight) return PAPC_EINVAL;
     if (M == 0) return PAPC_OK;
     if ((pool_max == nullptr) != (pool_min == nullptr)) return PAPC_EINVAL;
@@ -633,7 +703,18 @@ extern "C" int papc_mlp_layer_forward_f32(const papc_group_source *src, const fl
     a.vec_w = (cin % 4 == 0) && aligned16(weight);
     a.vec_y = (cout % 4 == 0) && (y == nullptr || aligned16(y));
 
-    // ---- tensor-core path (tcgen05, 3xTF32) whenever the shape fits; else fp32 SIMT
+    // ---- tensor-core paths (tcgen05, 3xTF32) whenever the shape fits; else fp32 SIMT
+    if (!(pool_max && M % K != 0)) {
+        const bool sc_ok = a.in_scale == nullptr || (aligned16(a.in_scale) && aligned16(a.in_shift));
+        if (sc_ok) {
+            const int r = try_tt(a, gather, K, bn, nullptr, st);
+            if (r < 0) return r;
+            if (r == 1) {
+                if (fused_done) *fused_done = (bn != nullptr && stats_partial != nullptr);
+                return PAPC_OK;
+            }
+        }
+    }
     tc::TcProblem prob{cin, cout, K, gather ? a.D : 0, gather, pool_max != nullptr};
     const size_t wneed = papc_mlp_layer_workspace_bytes(cin, cout);
     const bool a_ok = gather ? (a.D == 0 || aligned16(a.feats))
@@ -665,6 +746,17 @@ extern "C" int papc_mlp_layer_forward_f32(const papc_group_source *src, const fl
         }
     }
     return launch_layer(a, gather, st);
+}
+}  // namespace
+
+extern "C" int papc_mlp_layer_forward_f32(const papc_group_source *src, const float *x,
+                                          const float *in_scale, const float *in_shift, int64_t M,
+                                          int32_t cin, int32_t cout, int32_t K, const float *weight,
+                                          const float *bias, float *y, float *pool_max,
+                                          float *pool_min, double *stats_partial, void *workspace,
+                                          size_t workspace_bytes, papc_stream_t stream) {
+    return layer_forward(src, x, in_scale, in_shift, M, cin, cout, K, weight, bias, y, pool_max,
+                         pool_min, stats_partial, workspace, workspace_bytes, nullptr, nullptr, stream);
 }
 
 extern "C" int papc_mlp_stats_reduce_f64(const double *stats_partial, int64_t partial_rows,
@@ -726,7 +818,8 @@ extern "C" int papc_sa_pool_finish_f32(const float *pool_max, const float *pool_
 // ---- monolithic driver: workspace carving ------------------------------------------------
 namespace {
 struct WsPlan {
-    size_t y[2], pool_max, pool_min, partial, sums, scale, shift, wimg, wimg_bytes, total;
+    size_t y[2], pool_max, pool_min, partial, sums, scale, shift, wimg, wimg_bytes;
+    size_t counters, fold, mom_partial, total;
 };
 static int plan_ws(const papc_group_source *src, const papc_mlp *mlp, WsPlan *p) {
     if (!src || !mlp) return PAPC_EINVAL;
@@ -764,8 +857,24 @@ static int plan_ws(const papc_group_source *src, const papc_mlp *mlp, WsPlan *p)
     }
     p->wimg_bytes = wb;
     p->wimg = take(wb);
+    p->counters = take(256);
+    p->fold = take((size_t)128 * 4 * sizeof(float));
+    p->mom_partial = take((size_t)2 * kNumSMs * 9 * sizeof(double));
     p->total = off;
     return PAPC_OK;
+}
+
+// Can layer 0 (cin = 3, points only) be folded into layer 1's producer?  (SRC_POINTMLP)
+static bool pointmlp_ok(const papc_group_source *src, const papc_mlp *mlp) {
+    if (tc_level() < 2) return false;
+    if (src->grouped || src->D != 0 || mlp->cin != 3 || mlp->num_layers < 2) return false;
+    const int c0 = mlp->layers[0].cout;
+    if (c0 < 4 || c0 > 128 || c0 % 4 != 0) return false;
+    const bool pool = mlp->num_layers == 2;
+    const tt::TtProblem prob{tt::SRC_POINTMLP, c0, mlp->layers[1].cout, src->K, 0, pool};
+    if (!tt::eligible(prob)) return false;
+    const long long M = (long long)src->B * src->S * src->K;
+    return !(pool && M % src->K != 0);
 }
 }  // namespace
 
@@ -790,40 +899,90 @@ extern "C" int papc_sa_mlp_f32(const papc_group_source *src, const papc_mlp *mlp
     if (!out) return PAPC_EINVAL;
     if (!workspace || workspace_bytes < p.total) return PAPC_EWORKSPACE;
     if ((reinterpret_cast<uintptr_t>(workspace) & 255u) != 0) return PAPC_EINVAL;
+    cudaStream_t st = as_stream(stream);
     char *ws = reinterpret_cast<char *>(workspace);
     float *ybuf[2] = {reinterpret_cast<float *>(ws + p.y[0]), reinterpret_cast<float *>(ws + p.y[1])};
     float *pmax = reinterpret_cast<float *>(ws + p.pool_max);
     float *pmin = reinterpret_cast<float *>(ws + p.pool_min);
     double *partial = reinterpret_cast<double *>(ws + p.partial);
-    double *sums = reinterpret_cast<double *>(ws + p.sums);
     float *scale = reinterpret_cast<float *>(ws + p.scale);
     float *shift = reinterpret_cast<float *>(ws + p.shift);
+    unsigned int *counters = reinterpret_cast<unsigned int *>(ws + p.counters);
+    float *fold = reinterpret_cast<float *>(ws + p.fold);
     const bool batch = mlp->bn_mode == PAPC_BN_BATCH;
     const int L = mlp->num_layers;
-    int cin = mlp->cin;
-    const float *xprev = nullptr;
     for (int l = 0; l < L; ++l) {
         const papc_mlp_layer &ly = mlp->layers[l];
         if (!ly.weight) return PAPC_EINVAL;
         if (!batch && (!ly.running_mean || !ly.running_var)) return PAPC_EINVAL;
+    }
+    // the in-kernel "last CTA" counters start at zero (they clean themselves afterwards)
+    PAPC_CUDA_TRY(cudaMemsetAsync(counters, 0, 256, st));
+
+    int cin = mlp->cin;
+    const float *xprev = nullptr;
+    int l_first = 0;
+    bool folded = false;
+    if (pointmlp_ok(src, mlp)) {
+        // Layer 0 (3 -> c0) is never materialised: its BatchNorm statistics follow analytically
+        // from the moments of the centred points, and layer 1's producer recomputes it per row.
+        const papc_mlp_layer &l0 = mlp->layers[0];
+        tt::MomentArgs m{};
+        m.xyz = src->xyz; m.new_xyz = src->new_xyz; m.idx = src->idx;
+        m.N = src->N; m.S = src->S; m.K = src->K; m.M = M;
+        m.W0 = l0.weight; m.b0 = l0.bias; m.gamma = l0.gamma; m.beta = l0.beta;
+        m.running_mean = batch ? nullptr : l0.running_mean;
+        m.running_var = batch ? nullptr : l0.running_var;
+        m.eps = mlp->eps; m.c0 = l0.cout;
+        m.partial = reinterpret_cast<double *>(ws + p.mom_partial);
+        m.counter = counters + PAPC_MAX_MLP_LAYERS;
+        m.scale = scale; m.shift = shift; m.mean_out = l0.batch_mean; m.var_out = l0.batch_var;
+        m.l0_fold = fold;
+        rc = tt::launch_moments(m, st);
+        if (rc != PAPC_OK) return rc;
+        l_first = 1;
+        cin = l0.cout;
+        folded = true;
+    }
+    for (int l = l_first; l < L; ++l) {
+        const papc_mlp_layer &ly = mlp->layers[l];
         const bool last = (l == L - 1);
         float *y = last ? nullptr : ybuf[l & 1];
-        rc = papc_mlp_layer_forward_f32(l == 0 ? src : nullptr, xprev, l == 0 ? nullptr : scale,
-                                        l == 0 ? nullptr : shift, M, cin, ly.cout, src->K, ly.weight,
-                                        ly.bias, y, last ? pmax : nullptr, last ? pmin : nullptr,
-                                        batch ? partial : nullptr, ws + p.wimg, p.wimg_bytes, stream);
-        if (rc != PAPC_OK) return rc;
+        FusedBn bn{counters + l, ly.gamma, ly.beta, mlp->eps, (double)M,
+                   scale, shift, ly.batch_mean, ly.batch_var};
+        bool fused_done = false;
+        if (folded && l == 1) {
+            LayerArgs a{};
+            a.xyz = src->xyz; a.new_xyz = src->new_xyz; a.idx = src->idx;
+            a.N = src->N; a.S = src->S; a.K = src->K; a.D = 0; a.order = src->order;
+            a.M = M; a.cin = cin; a.cout = ly.cout; a.W = ly.weight; a.bias = ly.bias;
+            a.y = y; a.pool_max = last ? pmax : nullptr; a.pool_min = last ? pmin : nullptr;
+            a.stats_partial = batch ? partial : nullptr;
+            const int r = try_tt(a, true, src->K, batch ? &bn : nullptr, fold, st);
+            if (r < 0) return r;
+            if (r == 0) return PAPC_EUNSUPPORTED;  // pointmlp_ok() promised eligibility
+            fused_done = batch;
+        } else {
+            // in_scale / in_shift alias the scale / shift this layer's finalisation rewrites: safe,
+            // the last CTA writes them only after every CTA (hence every producer) has finished.
+            rc = layer_forward(l == 0 ? src : nullptr, xprev, l == 0 ? nullptr : scale,
+                               l == 0 ? nullptr : shift, M, cin, ly.cout, src->K, ly.weight, ly.bias, y,
+                               last ? pmax : nullptr, last ? pmin : nullptr, batch ? partial : nullptr,
+                               ws + p.wimg, p.wimg_bytes, batch ? &bn : nullptr, &fused_done, stream);
+            if (rc != PAPC_OK) return rc;
+        }
         if (batch) {
-            (void)sums;
-            bn_from_partials_kernel<<<ceil_div(ly.cout, 32), dim3(32, 16), 0, as_stream(stream)>>>(
-                partial, papc_mlp_stats_partial_rows(M), ly.cout, (double)M, ly.gamma, ly.beta, mlp->eps,
-                scale, shift, ly.batch_mean, ly.batch_var);
-            PAPC_LAUNCH_CHECK();
+            if (!fused_done) {
+                bn_from_partials_kernel<<<ceil_div(ly.cout, 32), dim3(32, 16), 0, st>>>(
+                    partial, papc_mlp_stats_partial_rows(M), ly.cout, (double)M, ly.gamma, ly.beta,
+                    mlp->eps, scale, shift, ly.batch_mean, ly.batch_var);
+                PAPC_LAUNCH_CHECK();
+            }
         } else {
             rc = papc_bn_running_scale_shift_f32(ly.running_mean, ly.running_var, ly.gamma, ly.beta,
                                                  mlp->eps, ly.cout, scale, shift, stream);
+            if (rc != PAPC_OK) return rc;
         }
-        if (rc != PAPC_OK) return rc;
         xprev = y;
         cin = ly.cout;
     }

@@ -1,0 +1,73 @@
+// sa_mlp_tt.cuh -- interface of the transposed tcgen05 layer kernel (weights resident in tensor
+// memory) and of the point-moment kernel that lets a cin<=8 first layer be recomputed on the fly.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace papc {
+namespace tt {
+
+enum { SRC_PLAIN = 0,     // x [M,cin] (+ optional relu(in_scale*x + in_shift))
+       SRC_GATHER = 1,    // feats[b, idx] rows through the tensor core, centred xyz in the epilogue
+       SRC_POINTMLP = 2 };// relu(bn(W0 * centred xyz + b0)) recomputed per row from the folded W0
+
+struct TtArgs {
+    int mode;
+    long long M;
+    int K;          // rows per group (pooling)
+    int cin;        // reduction length on the tensor core (PLAIN: columns of x, GATHER: D, POINTMLP: c0)
+    int cout;
+    // SRC_PLAIN
+    const float *x, *in_scale, *in_shift;
+    // SRC_GATHER / SRC_POINTMLP
+    const float *xyz, *new_xyz, *feats;
+    const int32_t *idx;
+    int N, S, D;
+    const float *l0_fold;  // SRC_POINTMLP: [cin][4] = scale*w_x, scale*w_y, scale*w_z, scale*b + shift
+    // weights of THIS layer: W[c*wld + wk0 + k] multiplies tensor column k; W[c*wld + wxyz + {0,1,2}]
+    // the centred xyz (SRC_GATHER, -1 = none)
+    const float *W;
+    int wld, wk0, wxyz;
+    const float *bias;
+    float *y;                    // [M,cout] pre-BN output (nullable)
+    float *pool_max, *pool_min;  // [M/K,cout] (nullable)
+    double *stats_partial;       // [partial_rows][2][cout] (nullable)
+    long long partial_rows;
+    // fused BatchNorm finalisation by the last CTA to finish (counter nullable = off)
+    unsigned int *counter;
+    const float *gamma, *beta;
+    float eps;
+    double count;
+    float *scale, *shift, *mean_out, *var_out;
+};
+
+struct TtProblem {
+    int mode, cin, cout, K, D;
+    bool pool;
+};
+bool eligible(const TtProblem &p);
+int launch(const TtArgs &a, cudaStream_t st);
+
+// Moments of the centred grouped points p = xyz[b, idx] - new_xyz over all M rows, then -- in the
+// last block -- BatchNorm statistics of y0 = W0 p + b0 derived analytically in fp64
+// (mean = W0 mu + b0, var = W0 Cov W0^T), the resulting scale / shift and the folded first layer.
+struct MomentArgs {
+    const float *xyz, *new_xyz;
+    const int32_t *idx;
+    int N, S, K;
+    long long M;
+    const float *W0, *b0;  // [c0,3], [c0] (nullable)
+    const float *gamma, *beta;
+    const float *running_mean, *running_var;  // used instead of the batch moments when non-null
+    float eps;
+    int c0;
+    double *partial;        // [blocks][9]
+    unsigned int *counter;
+    float *scale, *shift, *mean_out, *var_out;  // [c0] (mean/var nullable)
+    float *l0_fold;         // [c0][4]
+};
+int moment_blocks(long long M);
+int launch_moments(const MomentArgs &a, cudaStream_t st);
+
+}  // namespace tt
+}  // namespace papc

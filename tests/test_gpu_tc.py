@@ -21,7 +21,12 @@ def _cu(a):
 
 def _run_layer(x, w, bias, scale, shift, K, want_y, want_pool, tc, src=None, M=None):
     lib = L.lib()
-    os.environ["PAPC_MLP_TC"] = "1" if tc else "0"
+    # tc: "tt" (default: transposed kernel, weights in tensor memory), True / "tc" (shared/shared
+    # tcgen05 kernel), False / "simt" (fp32 CUDA-core kernel)
+    mode = {True: "tc", False: "simt"}.get(tc, tc)
+    os.environ.pop("PAPC_MLP_TC", None)
+    if mode != "tt":
+        os.environ["PAPC_MLP_TC"] = "1" if mode == "tc" else "0"
     try:
         cout, cin = w.shape
         M = x.shape[0] if M is None else M
@@ -67,13 +72,15 @@ def test_tc_identity_layout_probe():
     M, Cn = 256, 64
     x = (np.arange(M)[:, None] * 100.0 + np.arange(Cn)[None, :]).astype(np.float32) / 8.0
     w = np.eye(Cn, dtype=np.float32)
-    y, _, _, _ = _run_layer(x, w, None, None, None, 32, True, False, tc=True)
-    assert np.array_equal(y, x), _describe(y, x, "identity")
+    for mode in ("tt", "tc"):
+        y, _, _, _ = _run_layer(x, w, None, None, None, 32, True, False, tc=mode)
+        assert np.array_equal(y, x), _describe(y, x, "identity " + mode)
 
 
 @pytest.mark.parametrize("M,cin,cout,K", [(1024, 64, 64, 32), (4096, 64, 128, 32), (2048, 128, 128, 64),
                                           (4096, 128, 256, 64), (640, 96, 48, 32), (1000, 32, 200, 8),
-                                          (128 * 300 + 77, 64, 64, 1)])
+                                          (128 * 300 + 77, 64, 64, 1), (128 * 700, 128, 128, 128),
+                                          (96, 8, 16, 32), (128 * 149 + 32, 72, 300, 32)])
 def test_tc_plain_layer_vs_fp64(M, cin, cout, K):
     rng = np.random.default_rng(M + cin)
     x = rng.standard_normal((M, cin)).astype(np.float32)
@@ -84,9 +91,9 @@ def test_tc_plain_layer_vs_fp64(M, cin, cout, K):
     act = np.maximum(x.astype(np.float64) * scale + shift, 0.0).astype(np.float32).astype(np.float64)
     ref = act @ w.T.astype(np.float64) + bias
     pool = (M % K == 0) and K in (32, 64, 128)
-    for tc in (True, False):
+    for tc in ("tt", "tc", "simt"):
         y, pmax, pmin, sums = _run_layer(x, w, bias, scale, shift, K, True, pool, tc=tc)
-        name = "tcgen05" if tc else "simt"
+        name = tc
         assert np.allclose(y, ref, rtol=2e-6, atol=2e-6 * np.sqrt(cin)), _describe(y, ref, name)
         # the tensor-core fp32 accumulator truncates (a ~1e-7 relative bias toward zero per element),
         # so the statistic sums are checked against sum|y|, not against the (cancelling) sum itself
@@ -110,7 +117,7 @@ def test_tc_gather_layer_vs_simt(D, order):
     src = layers._make_src(keep[0], keep[1], keep[2], keep[3], B, N, S, K, order)
     M = B * S * K
     outs = {}
-    for tc in (True, False):
+    for tc in ("tt", "tc", "simt"):
         outs[tc] = _run_layer(None, w, None, None, None, K, True, True, tc=tc, src=src, M=M)
     # fp64 reference of the gathered rows
     g_xyz = np.stack([xyz[b][idx[b].reshape(-1)] for b in range(B)]).reshape(B, S, K, 3) - new_xyz[:, :, None]
@@ -120,6 +127,8 @@ def test_tc_gather_layer_vs_simt(D, order):
     else:
         rows = g_xyz
     ref = rows.reshape(M, 3 + D).astype(np.float64) @ w.T.astype(np.float64)
-    for tc in (True, False):
+    for tc in ("tt", "tc", "simt"):
         y = outs[tc][0]
-        assert np.allclose(y, ref, rtol=2e-6, atol=2e-5), _describe(y, ref, "tcgen05" if tc else "simt")
+        assert np.allclose(y, ref, rtol=2e-6, atol=2e-5), _describe(y, ref, tc)
+        g = y.reshape(M // K, K, cout)
+        assert np.array_equal(outs[tc][1], g.max(1)) and np.array_equal(outs[tc][2], g.min(1)), tc

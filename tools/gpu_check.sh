@@ -14,6 +14,11 @@ if [[ "$what" == *tests* ]]; then
   echo "pytest exit $?" >> gpurun_out/pytest.log
   tail -60 gpurun_out/pytest.log
 fi
+if [[ "$what" == *layers* ]]; then
+  timeout 300 python tools/prof_layer.py > gpurun_out/layers.log 2>&1
+  echo "layers exit $?"; tail -12 gpurun_out/layers.log
+  PAPC_MLP_TC=0 timeout 300 python tools/prof_layer.py > gpurun_out/layers_simt.log 2>&1
+fi
 if [[ "$what" == *smoke* ]]; then
   timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
   echo "smoke exit $?" >> gpurun_out/smoke.log; tail -5 gpurun_out/smoke.log
