@@ -331,7 +331,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def layer_roofline(torch, lib, layers, synth, dev, B):
+def layer_roofline(torch, lib, layers, synth, dev, B, only=None, reps=5, warm=3):
     """Time each grouped-MLP layer launch (the C-ABI step call papc_mlp_layer_forward_f32 launches
     exactly one GEMM kernel) with CUDA events on the launching stream, on the bench's own shapes."""
     import ctypes as C
@@ -370,11 +370,19 @@ def layer_roofline(torch, lib, layers, synth, dev, B):
                                                        L.ptr(shift), M, c, co, k, L.ptr(w), L.ptr(bias), L.ptr(y),
                                                        L.ptr(pmax), L.ptr(pmin), L.ptr(partial), L.ptr(lws), lwsb,
                                                        st), "layer")
-            for _ in range(3):
+            name = f"sa{si + 1}.l{li + 1} [{M}x{c}]x[{c}x{co}]"
+            if only and not any(o in name for o in only):
+                scale = torch.ones(co, device=dev)
+                shift = torch.zeros(co, device=dev)
+                if y is not None:
+                    y.normal_()
+                x, c = y, co
+                continue
+            for _ in range(warm):
                 launch()
             torch.cuda.synchronize()
             ms = []
-            for _ in range(5):
+            for _ in range(reps):
                 flush.zero_()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
@@ -384,7 +392,7 @@ def layer_roofline(torch, lib, layers, synth, dev, B):
                 ms.append(e0.elapsed_time(e1))
             t = float(np.mean(ms))
             fl = 2.0 * M * c * co
-            res.append({"name": f"sa{si + 1}.l{li + 1} [{M}x{c}]x[{c}x{co}]", "ms": t, "flops": fl,
+            res.append({"name": name, "ms": t, "flops": fl,
                         "tflops": fl / (t / 1e3) / 1e12})
             scale = torch.ones(co, device=dev)
             shift = torch.zeros(co, device=dev)

@@ -32,6 +32,8 @@
 #include "sa_mlp_tt.cuh"
 #include "umma.cuh"
 
+#include <stdlib.h>
+
 #include <type_traits>
 
 namespace papc {
@@ -44,11 +46,11 @@ constexpr int kChunkK = 32;       // fp32 per K chunk == one 128-byte swizzle ro
 constexpr int kHalfBytes = kTile * 128;       // hi (or lo) half of one chunk stage
 constexpr int kStageBytes = 2 * kHalfBytes;   // 32 KiB
 constexpr int kStages = 6;
-constexpr int kEpiWarps = 4;
+constexpr int kEpiWarps = 8;        // two per TMEM lane quadrant: rows 0-63 / 64-127 of each tile
 constexpr int kProdWarps = 8;
 constexpr int kProdThreads = kProdWarps * 32;
 constexpr int kMmaWarp = kEpiWarps;
-constexpr int kThreads = (kEpiWarps + 1 + kProdWarps) * 32;  // 416
+constexpr int kThreads = (kEpiWarps + 1 + kProdWarps) * 32;  // 544
 constexpr int kMaxK = 128;        // reduction length held in tensor memory
 // tensor-memory columns: two accumulators, then W hi, then W lo
 constexpr uint32_t kColAcc = 0, kColWHi = 2 * kTile, kColWLo = 2 * kTile + kMaxK;
@@ -60,7 +62,8 @@ struct SmemLayout {
     static constexpr uint32_t scale = xyz + 4 * kTile * 16;          // [128] float
     static constexpr uint32_t shift = scale + kMaxK * 4;             // [128] float
     static constexpr uint32_t fold = shift + kMaxK * 4;              // [128] float4
-    static constexpr uint32_t bars = fold + kMaxK * 16;
+    static constexpr uint32_t wst = fold + kMaxK * 16;               // [4 warps][32][33] float
+    static constexpr uint32_t bars = wst + 4 * 32 * 33 * 4;
     static constexpr uint32_t nbars = 2 * kStages + 2 + 2 + 1 + 4;
     static constexpr uint32_t misc = bars + nbars * 8;               // tmem slot, last-CTA flag
     static constexpr uint32_t total = misc + 16;
@@ -86,7 +89,7 @@ struct Chunk {
     float e0, e1, e2;  // SRC_GATHER: centred xyz of this thread's staging row
 };
 
-template <int MODE, bool POOL>
+template <int MODE, bool POOL, bool HAS_Y>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_layer_tt_kernel(const TtArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -95,6 +98,7 @@ mlp_layer_tt_kernel(const TtArgs a) {
     float *s_scale = reinterpret_cast<float *>(smem + SmemLayout::scale);
     float *s_shift = reinterpret_cast<float *>(smem + SmemLayout::shift);
     float4 *s_fold = reinterpret_cast<float4 *>(smem + SmemLayout::fold);
+    float *s_wst = reinterpret_cast<float *>(smem + SmemLayout::wst);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SmemLayout::bars);
     uint64_t *x_full = bars;
     uint64_t *x_empty = bars + kStages;
@@ -126,7 +130,7 @@ mlp_layer_tt_kernel(const TtArgs a) {
             mbar_init(acc_full + b, 1);
             mbar_init(acc_empty + b, kEpiWarps);
         }
-        mbar_init(w_ready, kEpiWarps);
+        mbar_init(w_ready, 4);
         for (int b = 0; b < 4; ++b) mbar_init(xyz_full + b, kProdWarps);
         fence_mbar_init();
     }
@@ -138,25 +142,36 @@ mlp_layer_tt_kernel(const TtArgs a) {
 
     if (warp < kEpiWarps) {
         // ================================ epilogue =========================================
-        const int c = warp * 32 + lane;   // channel inside this CTA's 128-channel tile == TMEM lane
+        const int quad = warp & 3;        // TMEM lane quadrant this warp may access
+        const int half = warp >> 2;       // rows [64*half, 64*half + 64) of every tile
+        const int c = quad * 32 + lane;   // channel inside this CTA's 128-channel tile == TMEM lane
         const int cg = n0 + c;
         const bool cvalid = cg < a.cout;
-        const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-        // ---- stage this channel's W row into tensor memory (hi / lo split)
-        {
-            const float *wrow = a.W + (size_t)(cvalid ? cg : 0) * a.wld + a.wk0;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+        // ---- warps 0-3 stage 32 W rows each into tensor memory (hi / lo split): coalesced row
+        //      loads, transposed through shared memory so that thread = channel owns its row
+        if (half == 0) {
+            float *wst = s_wst + quad * 32 * 33;
             for (int kc = 0; kc < KC; ++kc) {
+                const int k = kc * kChunkK + lane;
+#pragma unroll
+                for (int rr = 0; rr < 32; ++rr) {
+                    const int row = n0 + quad * 32 + rr;
+                    wst[rr * 33 + lane] = (row < a.cout && k < a.cin)
+                                              ? __ldg(a.W + (size_t)row * a.wld + a.wk0 + k) : 0.f;
+                }
+                __syncwarp();
                 uint32_t hi[32], lo[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    const int k = kc * kChunkK + i;
-                    const float v = (cvalid && k < a.cin) ? __ldg(wrow + k) : 0.f;
-                    const float h = tf32_rna(v);
+                    float h, l;
+                    split_tf32(wst[lane * 33 + i], h, l);
                     hi[i] = __float_as_uint(h);
-                    lo[i] = __float_as_uint(tf32_rna(v - h));
+                    lo[i] = __float_as_uint(l);
                 }
                 tmem_st32(lane_base + kColWHi + kc * kChunkK, hi);
                 tmem_st32(lane_base + kColWLo + kc * kChunkK, lo);
+                __syncwarp();
             }
             tmem_wait_st();
             tc_fence_before();
@@ -170,8 +185,15 @@ mlp_layer_tt_kernel(const TtArgs a) {
             const float *wp = a.W + (size_t)cg * a.wld + a.wxyz;
             wx = wp[0]; wy = wp[1]; wz = wp[2];
         }
-        const bool do_y = a.y != nullptr && cvalid;
+        const bool do_y = HAS_Y && cvalid;
         const bool do_pool = POOL && cvalid;
+        const uint64_t bias2 = pack2(bias, bias);
+        const uint64_t wx2 = pack2(wx, wx), wy2 = pack2(wy, wy), wz2 = pack2(wz, wz);
+        const int kshift = POOL ? (a.K == 32 ? 5 : a.K == 64 ? 6 : 7) : 0;  // K in {32, 64, 128}
+        // s_wst is dead once W is staged (all eight warps pass the named barrier below first):
+        // reused to combine the two row-halves (pool extrema for K = 128, final statistics)
+        float *s_comb = s_wst;  // [2 tile parities][2][128] floats
+        named_bar_sync(2, kEpiWarps * 32);
         double acc_s = 0.0, acc_q = 0.0;
         uint32_t tl = 0;
         for (long long tile = mi; tile < tiles_m; tile += gm, ++tl) {
@@ -181,71 +203,120 @@ mlp_layer_tt_kernel(const TtArgs a) {
             if (MODE == SRC_GATHER) mbar_wait(xyz_full + (tl & 3), (tl >> 2) & 1);
             mbar_wait(acc_full + buf, (tl >> 1) & 1);
             tc_fence_after();
-            const float4 *xs = xyz_stage + (tl & 3) * kTile;
-            float *yrow = do_y ? a.y + (size_t)m0 * a.cout + cg : nullptr;
-            float s = 0.f, qq = 0.f, mx = -INFINITY, mn = INFINITY;
+            // this warp's 64 accumulator columns -> registers, then hand the buffer straight back
+            uint32_t r[2][32];
+            tmem_ld32_nowait(lane_base + kColAcc + buf * kTile + half * 64, r[0]);
+            tmem_ld32_nowait(lane_base + kColAcc + buf * kTile + half * 64 + 32, r[1]);
+            tmem_wait_ld();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + buf);
+
+            const float4 *xs = xyz_stage + (tl & 3) * kTile + half * 64;
+            float *yrow = do_y ? a.y + ((size_t)m0 + half * 64) * a.cout + cg : nullptr;
+            const int nr = nrows - half * 64;  // valid rows of this half (may be <= 0)
+            uint64_t s2 = 0ull, q2 = 0ull;     // packed (even rows, odd rows) running sums
+            float mx = -INFINITY, mn = INFINITY;
             auto body = [&](auto full_tag) {
                 constexpr bool FULL = decltype(full_tag)::value;
 #pragma unroll
-                for (int j = 0; j < kTile / 32; ++j) {
-                    uint32_t r[32];
-                    tmem_ld32_nowait(lane_base + kColAcc + buf * kTile + j * 32, r);
-                    tmem_wait_ld();
-                    if (j == kTile / 32 - 1) {
-                        // accumulator fully read: hand the buffer back to the MMA issuer
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(acc_empty + buf);
-                    }
+                for (int j = 0; j < 2; ++j) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
+                    for (int i = 0; i < 32; i += 2) {
                         const int rr = j * 32 + i;
-                        float val = __uint_as_float(r[i]) + bias;
+                        uint64_t v2 = add2(pack2u(r[j][i], r[j][i + 1]), bias2);
                         if (has_xyz) {
-                            const float4 p = xs[rr];
-                            val = fmaf(wx, p.x, val);
-                            val = fmaf(wy, p.y, val);
-                            val = fmaf(wz, p.z, val);
+                            const float4 p0 = xs[rr], p1 = xs[rr + 1];
+                            v2 = fma2(wx2, pack2(p0.x, p1.x), v2);
+                            v2 = fma2(wy2, pack2(p0.y, p1.y), v2);
+                            v2 = fma2(wz2, pack2(p0.z, p1.z), v2);
                         }
-                        const bool rv = FULL || rr < nrows;
-                        if (do_y && rv) yrow[(size_t)rr * a.cout] = val;
-                        if (rv) {
-                            s += val;
-                            qq = fmaf(val, val, qq);
+                        float va, vb;
+                        unpack2(v2, va, vb);
+                        if (FULL) {
+                            s2 = add2(s2, v2);
+                            q2 = fma2(v2, v2, q2);
+                            if (do_y) {
+                                yrow[(size_t)rr * a.cout] = va;
+                                yrow[(size_t)(rr + 1) * a.cout] = vb;
+                            }
                             if (POOL) {
-                                mx = fmaxf(mx, val);
-                                mn = fminf(mn, val);
+                                mx = fmaxf(fmaxf(mx, va), vb);
+                                mn = fminf(fminf(mn, va), vb);
+                            }
+                        } else {
+                            const bool rva = rr < nr, rvb = rr + 1 < nr;
+                            const uint64_t m2 = pack2(rva ? va : 0.f, rvb ? vb : 0.f);
+                            s2 = add2(s2, m2);
+                            q2 = fma2(m2, m2, q2);
+                            if (do_y && rva) yrow[(size_t)rr * a.cout] = va;
+                            if (do_y && rvb) yrow[(size_t)(rr + 1) * a.cout] = vb;
+                            if (POOL) {
+                                if (rva) { mx = fmaxf(mx, va); mn = fminf(mn, va); }
+                                if (rvb) { mx = fmaxf(mx, vb); mn = fminf(mn, vb); }
                             }
                         }
                     }
-                    if (POOL) {
-                        const int done = (j + 1) * 32;
-                        if (done % a.K == 0) {
-                            if (do_pool && (FULL || j * 32 < nrows)) {
-                                const long long g = m0 / a.K + done / a.K - 1;
-                                a.pool_max[g * a.cout + cg] = mx;
-                                a.pool_min[g * a.cout + cg] = mn;
-                            }
-                            mx = -INFINITY;
-                            mn = INFINITY;
+                    if (POOL && kshift == 5) {  // K = 32: one group per 32-row block
+                        if (do_pool && (FULL || j * 32 < nr)) {
+                            const long long g = (m0 >> 5) + half * 2 + j;
+                            a.pool_max[g * a.cout + cg] = mx;
+                            a.pool_min[g * a.cout + cg] = mn;
                         }
+                        mx = -INFINITY;
+                        mn = INFINITY;
                     }
                 }
             };
-            if (nrows == kTile) body(std::true_type{});
+            if (a.dbg & 4) {
+                s2 = pack2u(r[0][0], r[1][31]);
+            } else if (nr >= 64) body(std::true_type{});
             else body(std::false_type{});
-            acc_s += (double)s;
-            acc_q += (double)qq;
-        }
-        if (a.stats_partial != nullptr && cvalid) {
-            a.stats_partial[((long long)mi * 2 + 0) * a.cout + cg] = acc_s;
-            a.stats_partial[((long long)mi * 2 + 1) * a.cout + cg] = acc_q;
-            // partial rows this launch does not own are zeroed (fixed row count per M)
-            for (long long rr = mi + gm; rr < a.partial_rows; rr += gm) {
-                a.stats_partial[(rr * 2 + 0) * a.cout + cg] = 0.0;
-                a.stats_partial[(rr * 2 + 1) * a.cout + cg] = 0.0;
+            if (POOL && kshift == 6) {  // K = 64: this half is exactly one group
+                if (do_pool && nr > 0) {
+                    const long long g = (m0 >> 6) + half;
+                    a.pool_max[g * a.cout + cg] = mx;
+                    a.pool_min[g * a.cout + cg] = mn;
+                }
             }
-            __threadfence();
+            if (POOL && kshift == 7) {  // K = 128: the group spans both halves -> combine
+                float *cb = s_comb + (tl & 1) * 256;
+                if (half == 1) {
+                    cb[c] = mx;
+                    cb[128 + c] = mn;
+                }
+                named_bar_sync(2, kEpiWarps * 32);
+                if (half == 0 && do_pool) {
+                    const long long g = m0 >> 7;
+                    a.pool_max[g * a.cout + cg] = fmaxf(mx, cb[c]);
+                    a.pool_min[g * a.cout + cg] = fminf(mn, cb[128 + c]);
+                }
+            }
+            float sa, sb, qa, qb;
+            unpack2(s2, sa, sb);
+            unpack2(q2, qa, qb);
+            acc_s += (double)sa + (double)sb;
+            acc_q += (double)qa + (double)qb;
+        }
+        if (a.stats_partial != nullptr) {
+            // combine the two row-halves, one partial row per CTA (fixed order -> deterministic)
+            named_bar_sync(2, kEpiWarps * 32);  // every pool exchange through s_comb is finished
+            double *cd = reinterpret_cast<double *>(s_wst);  // [2][128] doubles
+            if (half == 1) {
+                cd[c] = acc_s;
+                cd[128 + c] = acc_q;
+            }
+            named_bar_sync(2, kEpiWarps * 32);
+            if (half == 0 && cvalid) {
+                a.stats_partial[((long long)mi * 2 + 0) * a.cout + cg] = acc_s + cd[c];
+                a.stats_partial[((long long)mi * 2 + 1) * a.cout + cg] = acc_q + cd[128 + c];
+                // partial rows this launch does not own are zeroed (fixed row count per M)
+                for (long long rr = mi + gm; rr < a.partial_rows; rr += gm) {
+                    a.stats_partial[(rr * 2 + 0) * a.cout + cg] = 0.0;
+                    a.stats_partial[(rr * 2 + 1) * a.cout + cg] = 0.0;
+                }
+                __threadfence();
+            }
         }
     } else if (warp == kMmaWarp) {
         // ================================ MMA issuer =======================================
@@ -269,7 +340,7 @@ mlp_layer_tt_kernel(const TtArgs a) {
                     const uint32_t x_lo = x_hi + kHalfBytes;
                     const uint32_t w_hi = tmem_base + kColWHi + c * kChunkK;
                     const uint32_t w_lo = tmem_base + kColWLo + c * kChunkK;
-                    for (int ks = 0; ks * 8 < kreal; ++ks) {
+                    for (int ks = 0; ks * 8 < kreal && !(a.dbg & 2); ++ks) {
                         const uint64_t dxh = make_desc_sw128(x_hi + ks * 32);
                         const uint64_t dxl = make_desc_sw128(x_lo + ks * 32);
                         mma_tf32_ts(d_tmem, w_lo + ks * 8, dxh, idesc, (c | ks) != 0);  // small terms first
@@ -436,10 +507,10 @@ mlp_layer_tt_kernel(const TtArgs a) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 float4 hi, lo;
-                hi.x = tf32_rna(o[j].x); lo.x = tf32_rna(o[j].x - hi.x);
-                hi.y = tf32_rna(o[j].y); lo.y = tf32_rna(o[j].y - hi.y);
-                hi.z = tf32_rna(o[j].z); lo.z = tf32_rna(o[j].z - hi.z);
-                hi.w = tf32_rna(o[j].w); lo.w = tf32_rna(o[j].w - hi.w);
+                split_tf32(o[j].x, hi.x, lo.x);
+                split_tf32(o[j].y, hi.y, lo.y);
+                split_tf32(o[j].z, hi.z, lo.z);
+                split_tf32(o[j].w, hi.w, lo.w);
                 const uint32_t off = (uint32_t)(rb + 32 * j) * 128u + swz;
                 *reinterpret_cast<float4 *>(hi_base + off) = hi;
                 *reinterpret_cast<float4 *>(hi_base + kHalfBytes + off) = lo;
@@ -451,9 +522,8 @@ mlp_layer_tt_kernel(const TtArgs a) {
             if (c == KC - 1) ++ptl;
         };
 
-        long long tile = mi;
-        int c = 0;
-        bool have = tile < tiles_m;
+        const long long tile = mi;
+        const bool have = tile < tiles_m;
         if (have && MODE != SRC_PLAIN) {
             fetch_idx(tile);                       // idx of the first tile
             if (MODE == SRC_POINTMLP) {
@@ -461,24 +531,50 @@ mlp_layer_tt_kernel(const TtArgs a) {
                 fetch_idx(tile + gm < tiles_m ? tile + gm : tile);
             }
         }
-        Chunk ca, cb;
-        ca.e0 = ca.e1 = ca.e2 = cb.e0 = cb.e1 = cb.e2 = 0.f;
-        if (have) load(tile, c, ca);
-        while (have) {
-            long long t1 = tile;
-            int c1 = c + 1;
-            if (c1 == KC) { c1 = 0; t1 += gm; }
-            const bool have1 = t1 < tiles_m;
-            if (have1) load(t1, c1, cb);
-            process(c, ca);
+        // three chunks of global loads in flight per thread (registers ca / cb / cc rotate)
+        Chunk ca, cb, cc;
+        ca.e0 = ca.e1 = ca.e2 = cb.e0 = cb.e1 = cb.e2 = cc.e0 = cc.e1 = cc.e2 = 0.f;
+        auto advance = [&](long long &t, int &ci) {
+            if (++ci == KC) { ci = 0; t += gm; }
+        };
+        long long t0 = tile, t1 = tile, t2;
+        int c0 = 0, c1 = 0, c2;
+        advance(t1, c1);
+        bool have0 = have, have1 = have && t1 < tiles_m;
+        if (a.dbg & 1) {
+            // triage: ring protocol only
+            for (long long t = tile; t < tiles_m; t += gm)
+                for (int cq = 0; cq < KC; ++cq) {
+                    const uint32_t s = it % kStages;
+                    mbar_wait(x_empty + s, ((it / kStages) & 1) ^ 1);
+                    if (MODE == SRC_GATHER && cq == 0) { __syncwarp(); if (lane == 0) mbar_arrive(xyz_full + (ptl & 3)); }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(x_full + s);
+                    ++it;
+                    if (cq == KC - 1) ++ptl;
+                }
+            have0 = false;
+        }
+        if (have0) load(t0, c0, ca);
+        if (have1) load(t1, c1, cb);
+        while (have0) {
+            t2 = t1; c2 = c1; advance(t2, c2);
+            const bool have2 = have1 && t2 < tiles_m;
+            if (have2) load(t2, c2, cc);
+            process(c0, ca);
             if (!have1) break;
-            long long t2 = t1;
-            int c2 = c1 + 1;
-            if (c2 == KC) { c2 = 0; t2 += gm; }
-            const bool have2 = t2 < tiles_m;
-            if (have2) load(t2, c2, ca);
+            long long t3 = t2; int c3 = c2; advance(t3, c3);
+            const bool have3 = have2 && t3 < tiles_m;
+            if (have3) load(t3, c3, ca);
             process(c1, cb);
-            tile = t2; c = c2; have = have2;
+            if (!have2) break;
+            long long t4 = t3; int c4 = c3; advance(t4, c4);
+            const bool have4 = have3 && t4 < tiles_m;
+            if (have4) load(t4, c4, cb);
+            process(c2, cc);
+            t0 = t3; c0 = c3; have0 = have3;
+            t1 = t4; c1 = c4; have1 = have4;
         }
     }
 
@@ -497,24 +593,60 @@ mlp_layer_tt_kernel(const TtArgs a) {
         __syncthreads();
         if (*s_last != 0u) {
             __threadfence();
-            for (int ch = tid; ch < a.cout; ch += kThreads) {
-                double S = 0.0, Q = 0.0;
-                const double *p = a.stats_partial + ch;
-#pragma unroll 8
-                for (int r = 0; r < gm; ++r) {
-                    S += __ldcg(p + ((long long)r * 2 + 0) * a.cout);
-                    Q += __ldcg(p + ((long long)r * 2 + 1) * a.cout);
+            // 2*cout (channel, sum | sum^2) columns x gm partial rows: 256 columns at a time, the
+            // rows split over two thread slices (fixed order -> deterministic), combined in smem
+            double *red = reinterpret_cast<double *>(smem + SmemLayout::ring);  // [2][256]
+            const int col_l = tid & 255, sl = tid >> 8;  // threads >= 512 idle
+            for (int base = 0; base < 2 * a.cout; base += 256) {
+                const int col = base + col_l;  // = which * cout + ch
+                double acc = 0.0;
+                if (sl < 2 && col < 2 * a.cout) {
+                    const int which = col / a.cout, ch = col - which * a.cout;
+                    const double *p = a.stats_partial + (long long)which * a.cout + ch;
+#pragma unroll 16
+                    for (int r = sl; r < gm; r += 2) acc += __ldcg(p + (long long)r * 2 * a.cout);
+                    red[sl * 256 + col_l] = acc;
                 }
-                const double mean = S / a.count;
-                double var = Q / a.count - mean * mean;  // biased, as Paddle's training BN
-                var = var > 0.0 ? var : 0.0;
-                const double g = a.gamma ? (double)a.gamma[ch] : 1.0;
-                const double b = a.beta ? (double)a.beta[ch] : 0.0;
-                const double sc = g / sqrt(var + (double)a.eps);
-                a.scale[ch] = (float)sc;
-                a.shift[ch] = (float)(b - mean * sc);
-                if (a.mean_out) a.mean_out[ch] = (float)mean;
-                if (a.var_out) a.var_out[ch] = (float)var;
+                __syncthreads();
+                if (sl == 0 && col < 2 * a.cout) red[col_l] = red[col_l] + red[256 + col_l];
+                __syncthreads();
+                // channels whose sum AND sum^2 columns are both inside this 256-column window
+                // (cout >= 128: the two columns of a channel are cout apart -> handled below)
+                if (2 * a.cout <= 256) {
+                    if (tid < a.cout) {
+                        const int ch = tid;
+                        const double mean = red[ch] / a.count;
+                        double var = red[a.cout + ch] / a.count - mean * mean;  // biased (Paddle training BN)
+                        var = var > 0.0 ? var : 0.0;
+                        const double g = a.gamma ? (double)a.gamma[ch] : 1.0;
+                        const double b = a.beta ? (double)a.beta[ch] : 0.0;
+                        const double sc = g / sqrt(var + (double)a.eps);
+                        a.scale[ch] = (float)sc;
+                        a.shift[ch] = (float)(b - mean * sc);
+                        if (a.mean_out) a.mean_out[ch] = (float)mean;
+                        if (a.var_out) a.var_out[ch] = (float)var;
+                    }
+                } else {
+                    // park the reduced columns in the (dead) second ring stage: [2*cout] doubles
+                    double *all = reinterpret_cast<double *>(smem + SmemLayout::ring + kStageBytes);
+                    if (sl == 0 && col < 2 * a.cout) all[col] = red[col_l];
+                }
+                __syncthreads();
+            }
+            if (2 * a.cout > 256) {
+                const double *all = reinterpret_cast<const double *>(smem + SmemLayout::ring + kStageBytes);
+                for (int ch = tid; ch < a.cout; ch += kThreads) {
+                    const double mean = all[ch] / a.count;
+                    double var = all[a.cout + ch] / a.count - mean * mean;
+                    var = var > 0.0 ? var : 0.0;
+                    const double g = a.gamma ? (double)a.gamma[ch] : 1.0;
+                    const double b = a.beta ? (double)a.beta[ch] : 0.0;
+                    const double sc = g / sqrt(var + (double)a.eps);
+                    a.scale[ch] = (float)sc;
+                    a.shift[ch] = (float)(b - mean * sc);
+                    if (a.mean_out) a.mean_out[ch] = (float)mean;
+                    if (a.var_out) a.var_out[ch] = (float)var;
+                }
             }
             if (tid == 0) *a.counter = 0u;  // self-cleaning for the next launch
         }
@@ -631,9 +763,9 @@ bool eligible(const TtProblem &p) {
     return true;
 }
 
-template <int MODE, bool POOL>
+template <int MODE, bool POOL, bool HAS_Y>
 static int launch_inst(const TtArgs &a, int grid, cudaStream_t st) {
-    auto k = mlp_layer_tt_kernel<MODE, POOL>;
+    auto k = mlp_layer_tt_kernel<MODE, POOL, HAS_Y>;
     static bool configured = false;
     if (!configured) {
         PAPC_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
@@ -644,7 +776,12 @@ static int launch_inst(const TtArgs &a, int grid, cudaStream_t st) {
     return PAPC_OK;
 }
 
-int launch(const TtArgs &a, cudaStream_t st) {
+int launch(const TtArgs &a_in, cudaStream_t st) {
+    TtArgs a = a_in;
+    {
+        const char *e = getenv("PAPC_TT_DBG");
+        a.dbg = e ? atoi(e) : 0;
+    }
     const bool pool = a.pool_max != nullptr;
     const int nt = ceil_div(a.cout, kTile);
     const long long tiles_m = ceil_div<long long>(a.M, kTile);
@@ -653,15 +790,19 @@ int launch(const TtArgs &a, cudaStream_t st) {
     if (gm > tiles_m) gm = tiles_m;
     if (a.stats_partial != nullptr && gm > a.partial_rows) gm = a.partial_rows;
     const int grid = (int)(gm * nt);
+    const bool has_y = a.y != nullptr;
+#define PAPC_TT_CASE(MODE_)                                                        \
+    case MODE_:                                                                    \
+        if (pool && has_y) return launch_inst<MODE_, true, true>(a, grid, st);     \
+        if (pool) return launch_inst<MODE_, true, false>(a, grid, st);             \
+        if (has_y) return launch_inst<MODE_, false, true>(a, grid, st);            \
+        return launch_inst<MODE_, false, false>(a, grid, st);
     switch (a.mode) {
-        case SRC_PLAIN:
-            return pool ? launch_inst<SRC_PLAIN, true>(a, grid, st) : launch_inst<SRC_PLAIN, false>(a, grid, st);
-        case SRC_GATHER:
-            return pool ? launch_inst<SRC_GATHER, true>(a, grid, st) : launch_inst<SRC_GATHER, false>(a, grid, st);
-        case SRC_POINTMLP:
-            return pool ? launch_inst<SRC_POINTMLP, true>(a, grid, st)
-                        : launch_inst<SRC_POINTMLP, false>(a, grid, st);
+        PAPC_TT_CASE(SRC_PLAIN)
+        PAPC_TT_CASE(SRC_GATHER)
+        PAPC_TT_CASE(SRC_POINTMLP)
     }
+#undef PAPC_TT_CASE
     return PAPC_EINVAL;
 }
 

@@ -39,6 +39,8 @@ struct TtArgs {
     float eps;
     double count;
     float *scale, *shift, *mean_out, *var_out;
+    int dbg;  // PAPC_TT_DBG bit mask (performance triage only): 1 = producers skip loads+math,
+              // 2 = no MMAs issued, 4 = epilogue skips its math / stores
 };
 
 struct TtProblem {

@@ -141,6 +141,38 @@ __device__ __forceinline__ float tf32_rna(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
+// fp32 -> (hi, lo) with hi a TF32 value (round to nearest, ties away: integer add + mask, no
+// inf/nan special-casing -- two ALU ops instead of the ~6 of cvt.rna.tf32.f32) and lo = v - hi
+// exact in fp32.  lo is fed to the tensor core as is: kind::tf32 ignores the low 13 mantissa bits,
+// a 2^-21 relative truncation of a term whose sign is random.
+__device__ __forceinline__ void split_tf32(float v, float &hi, float &lo) {
+    hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
+    lo = v - hi;
+}
+// packed 2 x fp32 arithmetic (sm_100 FADD2 / FFMA2): one FMA-pipe issue slot for two lanes of work
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ uint64_t pack2u(uint32_t lo, uint32_t hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

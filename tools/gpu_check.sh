@@ -32,3 +32,10 @@ if [[ "$what" == *ncu* ]]; then
      --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_bench.log 2>&1
   echo "ncu exit $?"; tail -3 gpurun_out/ncu_bench.log | cut -c1-300
 fi
+if [[ "$what" == *triage* ]]; then
+  for d in 0 1 2 4 3 5 6 7; do
+    echo "== PAPC_TT_DBG=$d" >> gpurun_out/triage.log
+    PAPC_TT_DBG=$d timeout 300 python tools/prof_layer.py sa1.l3 sa2.l2 sa1.l2 >> gpurun_out/triage.log 2>&1
+  done
+  cat gpurun_out/triage.log
+fi

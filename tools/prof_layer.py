@@ -12,8 +12,10 @@ from papc_b200 import _lib, layers, synth  # noqa: E402
 
 dev = torch.device("cuda:0")
 torch.cuda.set_device(dev)
-res = bench.layer_roofline(torch, _lib.lib(), layers, synth, dev, bench.B_PER_GPU)
 want = sys.argv[1:]
+under_ncu = os.environ.get("PAPC_PROF_NCU") == "1"   # one warm-up + one launch per selected layer
+res = bench.layer_roofline(torch, _lib.lib(), layers, synth, dev, bench.B_PER_GPU, only=want or None,
+                           reps=1 if under_ncu else 5, warm=1 if under_ncu else 3)
 for r in res["layers"]:
-    if not want or any(w in r["name"] for w in want):
+    if True:
         print(f"{r['name']:40s} {r['ms'] * 1e3:9.1f} us  {r['tflops']:7.1f} TFLOP/s")
