@@ -606,24 +606,37 @@ struct FusedBn {
     float eps;
     double count;
     float *scale, *shift, *mean_out, *var_out;
+    float *out_colscale;  // non-null: the NEXT layer runs the fp16 split (see tt::TtArgs)
 };
 
-// Tries the transposed tcgen05 kernel.  Returns 1 if launched, 0 if the shape is not eligible,
-// < 0 on error.
-static int try_tt(const LayerArgs &a, bool gather, int K, const FusedBn *bn, const float *l0_fold,
+// Per-launch options of the transposed tcgen05 kernel.
+struct TtOpts {
+    int prec;                 // tt::PREC_TF32 / tt::PREC_F16
+    const float *w_colscale;  // PREC_F16: column scale written by the producer layer's finalisation
+    const float *l0_fold;     // non-null: SRC_POINTMLP
+    void *wimg;               // workspace for the streamed-W image
+    size_t wimg_bytes;
+    bool dry_run;             // only report eligibility
+};
+
+// Tries the transposed tcgen05 kernel.  Returns 1 if launched (or, dry_run, launchable), 0 if the
+// shape is not eligible, < 0 on error.
+static int try_tt(const LayerArgs &a, bool gather, int K, const FusedBn *bn, const TtOpts &o,
                   cudaStream_t st) {
     if (tc_level() < 2) return 0;
     tt::TtArgs t{};
+    t.prec = o.prec;
     t.M = a.M; t.K = K; t.cout = a.cout;
     t.bias = a.bias; t.y = a.y; t.pool_max = a.pool_max; t.pool_min = a.pool_min;
     t.stats_partial = a.stats_partial; t.partial_rows = grid_rows(a.M);
     t.W = a.W; t.wld = a.cin; t.wk0 = 0; t.wxyz = -1;
-    if (l0_fold != nullptr) {
+    t.w_colscale = o.w_colscale;
+    if (o.l0_fold != nullptr) {
         // `a` describes the SECOND layer (cin = first layer's cout); rows come from the points
         t.mode = tt::SRC_POINTMLP;
         t.cin = a.cin;
         t.xyz = a.xyz; t.new_xyz = a.new_xyz; t.idx = a.idx; t.N = a.N; t.S = a.S; t.D = 0;
-        t.l0_fold = l0_fold;
+        t.l0_fold = o.l0_fold;
     } else if (gather) {
         if (a.D < 4 || !aligned16(a.feats)) return 0;
         t.mode = tt::SRC_GATHER;
@@ -638,12 +651,17 @@ static int try_tt(const LayerArgs &a, bool gather, int K, const FusedBn *bn, con
         t.cin = a.cin;
         t.x = a.x; t.in_scale = a.in_scale; t.in_shift = a.in_shift;
     }
-    const tt::TtProblem prob{t.mode, t.cin, t.cout, K, t.D, a.pool_max != nullptr};
+    const tt::TtProblem prob{t.mode, t.prec, t.cin, t.cout, K, t.D, a.pool_max != nullptr};
     if (!tt::eligible(prob)) return 0;
+    if (!a.pool_max && !a.y) return 0;
+    const size_t wneed = tt::wimg_bytes(t.prec, t.cin, t.cout);
+    if (wneed > 0 && (o.wimg == nullptr || o.wimg_bytes < wneed || !aligned16(o.wimg))) return 0;
+    t.wimg = o.wimg;
+    if (o.dry_run) return 1;
     if (bn != nullptr && a.stats_partial != nullptr) {
         t.counter = bn->counter; t.gamma = bn->gamma; t.beta = bn->beta; t.eps = bn->eps;
         t.count = bn->count; t.scale = bn->scale; t.shift = bn->shift;
-        t.mean_out = bn->mean_out; t.var_out = bn->var_out;
+        t.mean_out = bn->mean_out; t.var_out = bn->var_out; t.out_colscale = bn->out_colscale;
     }
     const int rc = tt::launch(t, st);
     return rc == PAPC_OK ? 1 : rc;
@@ -655,13 +673,17 @@ static int layer_forward(const papc_group_source *src, const float *x, const flo
                          const float *in_shift, int64_t M, int32_t cin, int32_t cout, int32_t K,
                          const float *weight, const float *bias, float *y, float *pool_max,
                          float *pool_min, double *stats_partial, void *workspace,
-                         size_t workspace_bytes, const FusedBn *bn, bool *fused_done,
-                         papc_stream_t stream);
+                         size_t workspace_bytes, const FusedBn *bn, const TtOpts *opts,
+                         bool *fused_done, papc_stream_t stream);
 }  // namespace
 
 extern "C" size_t papc_mlp_layer_workspace_bytes(int32_t cin, int32_t cout) {
     if (cin <= 0 || cout <= 0) return 0;
-    return align_up(tc::wimg_bytes(cin, cout), 256);
+    size_t b = tc::wimg_bytes(cin, cout);
+    const size_t b1 = tt::wimg_bytes(tt::PREC_TF32, cin, cout), b2 = tt::wimg_bytes(tt::PREC_F16, cin, cout);
+    b = b1 > b ? b1 : b;
+    b = b2 > b ? b2 : b;
+    return align_up(b, 256);
 }
 
 namespace {
@@ -669,8 +691,8 @@ static int layer_forward(const papc_group_source *src, const float *x, const flo
                          const float *in_shift, int64_t M, int32_t cin, int32_t cout, int32_t K,
                          const float *weight, const float *bias, float *y, float *pool_max,
                          float *pool_min, double *stats_partial, void *workspace,
-                         size_t workspace_bytes, const FusedBn *bn, bool *fused_done,
-                         papc_stream_t stream) {
+                         size_t workspace_bytes, const FusedBn *bn, const TtOpts *opts,
+                         bool *fused_done, papc_stream_t stream) {
     if (fused_done) *fused_done = false;
     if (M < 0 || cin <= 0 || cout <= 0 || K <= 0 || !weight) return PAPC_EINVAL;
     if (M == 0) return PAPC_OK;
@@ -707,16 +729,26 @@ static int layer_forward(const papc_group_source *src, const float *x, const flo
     if (!(pool_max && M % K != 0)) {
         const bool sc_ok = a.in_scale == nullptr || (aligned16(a.in_scale) && aligned16(a.in_shift));
         if (sc_ok) {
-            const int r = try_tt(a, gather, K, bn, nullptr, st);
+            TtOpts o{tt::PREC_TF32, nullptr, nullptr, workspace, workspace_bytes, false};
+            if (opts != nullptr) o = *opts;
+            else if (!gather && a.in_scale != nullptr && cin % 8 == 0) {
+                // step-wise API: no bound on the activations is known, so TF32 -- unless the caller
+                // vouches for |relu(in_scale*x+in_shift)| < 2^15 (benchmarks: PAPC_TT_PREC=f16)
+                const char *e = getenv("PAPC_TT_PREC");
+                if (e && e[0] == 'f') o.prec = tt::PREC_F16;
+            }
+            const int r = try_tt(a, gather, K, bn, o, st);
             if (r < 0) return r;
             if (r == 1) {
-                if (fused_done) *fused_done = (bn != nullptr && stats_partial != nullptr);
-                return PAPC_OK;
+                if (!o.dry_run && fused_done) *fused_done = (bn != nullptr && stats_partial != nullptr);
+                return o.dry_run ? 1 : PAPC_OK;
             }
+            if (o.dry_run) return 0;
         }
     }
     tc::TcProblem prob{cin, cout, K, gather ? a.D : 0, gather, pool_max != nullptr};
-    const size_t wneed = papc_mlp_layer_workspace_bytes(cin, cout);
+    if (opts != nullptr && opts->dry_run) return 0;
+    const size_t wneed = align_up(tc::wimg_bytes(cin, cout), 256);
     const bool a_ok = gather ? (a.D == 0 || aligned16(a.feats))
                              : (aligned16(a.x) && (a.in_scale == nullptr ||
                                                    (aligned16(a.in_scale) && aligned16(a.in_shift))));
@@ -756,7 +788,8 @@ extern "C" int papc_mlp_layer_forward_f32(const papc_group_source *src, const fl
                                           float *pool_min, double *stats_partial, void *workspace,
                                           size_t workspace_bytes, papc_stream_t stream) {
     return layer_forward(src, x, in_scale, in_shift, M, cin, cout, K, weight, bias, y, pool_max,
-                         pool_min, stats_partial, workspace, workspace_bytes, nullptr, nullptr, stream);
+                         pool_min, stats_partial, workspace, workspace_bytes, nullptr, nullptr, nullptr,
+                         stream);
 }
 
 extern "C" int papc_mlp_stats_reduce_f64(const double *stats_partial, int64_t partial_rows,
@@ -819,7 +852,7 @@ extern "C" int papc_sa_pool_finish_f32(const float *pool_max, const float *pool_
 namespace {
 struct WsPlan {
     size_t y[2], pool_max, pool_min, partial, sums, scale, shift, wimg, wimg_bytes;
-    size_t counters, fold, mom_partial, total;
+    size_t counters, fold, mom_partial, colscale, colscale_stride, total;
 };
 static int plan_ws(const papc_group_source *src, const papc_mlp *mlp, WsPlan *p) {
     if (!src || !mlp) return PAPC_EINVAL;
@@ -860,6 +893,8 @@ static int plan_ws(const papc_group_source *src, const papc_mlp *mlp, WsPlan *p)
     p->counters = take(256);
     p->fold = take((size_t)128 * 4 * sizeof(float));
     p->mom_partial = take((size_t)2 * kNumSMs * 9 * sizeof(double));
+    p->colscale_stride = align_up((size_t)maxc * sizeof(float), 256);
+    p->colscale = take(2 * p->colscale_stride);
     p->total = off;
     return PAPC_OK;
 }
@@ -871,7 +906,8 @@ static bool pointmlp_ok(const papc_group_source *src, const papc_mlp *mlp) {
     const int c0 = mlp->layers[0].cout;
     if (c0 < 4 || c0 > 128 || c0 % 4 != 0) return false;
     const bool pool = mlp->num_layers == 2;
-    const tt::TtProblem prob{tt::SRC_POINTMLP, c0, mlp->layers[1].cout, src->K, 0, pool};
+    const int prec = (mlp->bn_mode == PAPC_BN_BATCH && c0 % 8 == 0) ? tt::PREC_F16 : tt::PREC_TF32;
+    const tt::TtProblem prob{tt::SRC_POINTMLP, prec, c0, mlp->layers[1].cout, src->K, 0, pool};
     if (!tt::eligible(prob)) return false;
     const long long M = (long long)src->B * src->S * src->K;
     return !(pool && M % src->K != 0);
@@ -923,10 +959,31 @@ extern "C" int papc_sa_mlp_f32(const papc_group_source *src, const papc_mlp *mlp
     const float *xprev = nullptr;
     int l_first = 0;
     bool folded = false;
+    float *colscale[2] = {reinterpret_cast<float *>(ws + p.colscale),
+                          reinterpret_cast<float *>(ws + p.colscale + p.colscale_stride)};
+    // Precision of layer l's tensor-core products: the fp16 split needs bounded inputs, i.e. inputs
+    // that are relu(batch-norm(.)) of a layer whose finalisation was fused (it writes the exact
+    // power-of-two column scale) -- see sa_mlp_tt.cu.  Decided one layer ahead.
+    auto f16_ok = [&](int l, int c_in) -> bool {   // could layer l (PLAIN, act input) run the fp16 split?
+        if (!batch || l <= 0 || l >= L || c_in % 8 != 0) return false;
+        LayerArgs a{};
+        a.x = ybuf[(l - 1) & 1]; a.in_scale = scale; a.in_shift = shift;
+        a.K = src->K; a.M = M; a.cin = c_in; a.cout = mlp->layers[l].cout;
+        a.W = mlp->layers[l].weight; a.bias = mlp->layers[l].bias;
+        const bool last = l == L - 1;
+        a.y = last ? nullptr : ybuf[l & 1];
+        a.pool_max = last ? pmax : nullptr; a.pool_min = last ? pmin : nullptr;
+        a.stats_partial = partial;
+        if (last && M % src->K != 0) return false;
+        const TtOpts o{tt::PREC_F16, colscale[0], nullptr, ws + p.wimg, p.wimg_bytes, true};
+        return try_tt(a, false, src->K, nullptr, o, st) == 1;
+    };
+    bool this_f16 = false;  // precision of the layer about to run
     if (pointmlp_ok(src, mlp)) {
         // Layer 0 (3 -> c0) is never materialised: its BatchNorm statistics follow analytically
         // from the moments of the centred points, and layer 1's producer recomputes it per row.
         const papc_mlp_layer &l0 = mlp->layers[0];
+        this_f16 = batch && l0.cout % 8 == 0;
         tt::MomentArgs m{};
         m.xyz = src->xyz; m.new_xyz = src->new_xyz; m.idx = src->idx;
         m.N = src->N; m.S = src->S; m.K = src->K; m.M = M;
@@ -938,6 +995,7 @@ extern "C" int papc_sa_mlp_f32(const papc_group_source *src, const papc_mlp *mlp
         m.counter = counters + PAPC_MAX_MLP_LAYERS;
         m.scale = scale; m.shift = shift; m.mean_out = l0.batch_mean; m.var_out = l0.batch_var;
         m.l0_fold = fold;
+        m.out_colscale = this_f16 ? colscale[0] : nullptr;
         rc = tt::launch_moments(m, st);
         if (rc != PAPC_OK) return rc;
         l_first = 1;
@@ -948,8 +1006,11 @@ extern "C" int papc_sa_mlp_f32(const papc_group_source *src, const papc_mlp *mlp
         const papc_mlp_layer &ly = mlp->layers[l];
         const bool last = (l == L - 1);
         float *y = last ? nullptr : ybuf[l & 1];
+        const bool next_f16 = f16_ok(l + 1, ly.cout);
         FusedBn bn{counters + l, ly.gamma, ly.beta, mlp->eps, (double)M,
-                   scale, shift, ly.batch_mean, ly.batch_var};
+                   scale, shift, ly.batch_mean, ly.batch_var, next_f16 ? colscale[l & 1] : nullptr};
+        TtOpts o{this_f16 ? tt::PREC_F16 : tt::PREC_TF32, this_f16 ? colscale[(l - 1) & 1] : nullptr,
+                 nullptr, ws + p.wimg, p.wimg_bytes, false};
         bool fused_done = false;
         if (folded && l == 1) {
             LayerArgs a{};
@@ -958,7 +1019,8 @@ extern "C" int papc_sa_mlp_f32(const papc_group_source *src, const papc_mlp *mlp
             a.M = M; a.cin = cin; a.cout = ly.cout; a.W = ly.weight; a.bias = ly.bias;
             a.y = y; a.pool_max = last ? pmax : nullptr; a.pool_min = last ? pmin : nullptr;
             a.stats_partial = batch ? partial : nullptr;
-            const int r = try_tt(a, true, src->K, batch ? &bn : nullptr, fold, st);
+            o.l0_fold = fold;
+            const int r = try_tt(a, true, src->K, batch ? &bn : nullptr, o, st);
             if (r < 0) return r;
             if (r == 0) return PAPC_EUNSUPPORTED;  // pointmlp_ok() promised eligibility
             fused_done = batch;
@@ -968,15 +1030,23 @@ extern "C" int papc_sa_mlp_f32(const papc_group_source *src, const papc_mlp *mlp
             rc = layer_forward(l == 0 ? src : nullptr, xprev, l == 0 ? nullptr : scale,
                                l == 0 ? nullptr : shift, M, cin, ly.cout, src->K, ly.weight, ly.bias, y,
                                last ? pmax : nullptr, last ? pmin : nullptr, batch ? partial : nullptr,
-                               ws + p.wimg, p.wimg_bytes, batch ? &bn : nullptr, &fused_done, stream);
+                               ws + p.wimg, p.wimg_bytes, batch ? &bn : nullptr, &o, &fused_done, stream);
             if (rc != PAPC_OK) return rc;
         }
+        if (this_f16 && !fused_done && batch) {
+            // cannot happen: f16_ok() dry-ran exactly this launch.  Scale / shift of the previous
+            // layer were divided by its column scale, so any other kernel would be wrong.
+            if (!(folded && l == 1)) return PAPC_EUNSUPPORTED;
+        }
+        this_f16 = false;
         if (batch) {
             if (!fused_done) {
                 bn_from_partials_kernel<<<ceil_div(ly.cout, 32), dim3(32, 16), 0, st>>>(
                     partial, papc_mlp_stats_partial_rows(M), ly.cout, (double)M, ly.gamma, ly.beta,
                     mlp->eps, scale, shift, ly.batch_mean, ly.batch_var);
                 PAPC_LAUNCH_CHECK();
+            } else {
+                this_f16 = next_f16;  // the fused finalisation wrote colscale[l & 1]
             }
         } else {
             rc = papc_bn_running_scale_shift_f32(ly.running_mean, ly.running_var, ly.gamma, ly.beta,

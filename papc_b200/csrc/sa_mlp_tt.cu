@@ -5,22 +5,28 @@
 //
 // The M = B*S*K grouped rows are the MMA *N* dimension and the output channels the MMA *M*
 // dimension, so that
-//   * W (hi/lo TF32 split) is the A operand and lives in TENSOR MEMORY for the whole kernel: the
-//     tensor core reads only the activation tile from shared memory (half the operand traffic of a
-//     shared/shared UMMA, which at M=N=128 saturates the 128 B/clk shared-memory port);
+//   * W (hi/lo split) is the A operand and -- whenever it fits -- lives in TENSOR MEMORY for the
+//     whole kernel: the tensor core then reads only the activation tile from shared memory (half
+//     the operand traffic of a shared/shared UMMA, which at M=N=128 saturates the 128 B/clk
+//     shared-memory port).  For longer reductions W chunks are streamed through the same ring by
+//     TMA from a pre-split, pre-swizzled image (shared/shared UMMA);
 //   * the accumulator comes back with lane = channel, column = row: every epilogue thread owns one
-//     channel, so bias, BatchNorm sum / sum^2, the per-group max/min pooling are plain per-thread
-//     running reductions (no shuffles), and a warp stores 32 consecutive channels of one row
-//     (128-byte coalesced) straight from the tcgen05.ld registers.
+//     channel, so bias, BatchNorm sum / sum^2 and the per-group max/min pooling are plain
+//     per-thread running reductions (no shuffles), and a warp stores 32 consecutive channels of one
+//     row (128-byte coalesced) straight from the tcgen05.ld registers.
 //
-// fp32 in / fp32 out inside the 1e-5 parity budget: 3xTF32 (lo*hi + hi*lo + hi*hi, fp32
-// accumulation in tensor memory).
+// fp32 in / fp32 out inside the 1e-5 parity budget through a two-term operand split and three MMAs
+// per product (lo*hi + hi*lo + hi*hi, fp32 accumulation in tensor memory):
+//   PREC_TF32: hi/lo are TF32, K = 8 per MMA -- any finite input;
+//   PREC_F16 : hi/lo are fp16, K = 16 per MMA (half the MMAs, half the shared-memory bytes) --
+//              only for inputs that are relu(batch-norm(.)), whose magnitude is bounded by
+//              |gamma| sqrt(count) + |beta|; an exact power-of-two column scale keeps them < 2^15.
 //
-// Persistent, one CTA per SM, 13 warps:
-//   warps 0-3   epilogue  (TMEM lane quadrant = warp id).  They first stage W into tensor memory.
-//   warp  4     MMA issuer (one thread) + TMEM allocation.
-//   warps 5-12  producers: build the 128-row activation tile in shared memory (UMMA K-major
-//               SWIZZLE_128B, hi and lo halves, ring of 32-column chunks), from one of
+// Persistent, one CTA per SM, 21 warps:
+//   warps 0-3   epilogue  (TMEM lane quadrant = warp).  They first stage W into tensor memory.
+//   warp  20    MMA issuer (one elected lane; highest warp id = issue priority) + TMEM allocation.
+//   warps 4-19  producers: build the 128-row activation tile in shared memory (UMMA K-major
+//               SWIZZLE_128B, hi and lo halves, ring of 128-byte-wide chunks), from one of
 //                 SRC_PLAIN    : x [M,cin] with the previous layer's BatchNorm+ReLU applied on load,
 //                 SRC_GATHER   : feats[b, idx[row]] rows (the grouped tensor is never materialised);
 //                                the 3 centred xyz channels are added in the epilogue in fp32,
@@ -32,6 +38,7 @@
 #include "sa_mlp_tt.cuh"
 #include "umma.cuh"
 
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include <type_traits>
@@ -41,34 +48,104 @@ namespace tt {
 
 using namespace umma;
 
-constexpr int kTile = 128;        // rows per tile == UMMA N
-constexpr int kChunkK = 32;       // fp32 per K chunk == one 128-byte swizzle row
-constexpr int kHalfBytes = kTile * 128;       // hi (or lo) half of one chunk stage
-constexpr int kStageBytes = 2 * kHalfBytes;   // 32 KiB
-constexpr int kStages = 6;
-constexpr int kEpiWarps = 8;        // two per TMEM lane quadrant: rows 0-63 / 64-127 of each tile
-constexpr int kProdWarps = 8;
+constexpr int kTile = 128;                    // rows per tile == UMMA N
+constexpr int kHalfBytes = kTile * 128;       // one [128 rows][128 B] SWIZZLE_128B block
+constexpr int kXBytes = 2 * kHalfBytes;       // X chunk: hi block + lo block
+constexpr int kEpiWarps = 4;                  // one per TMEM lane quadrant (13 warps: 128 regs/thread)
+#ifndef PAPC_TT_PROD_WARPS
+#define PAPC_TT_PROD_WARPS 8
+#endif
+constexpr int kProdWarps = PAPC_TT_PROD_WARPS;  // each thread: kRPT rows x one 16-byte unit per chunk
+constexpr int kRPT = 128 * 8 / (kProdWarps * 32);  // rows per producer thread per chunk
+constexpr int kRowStride = kTile / kRPT;       // rows rb + kRowStride * j
 constexpr int kProdThreads = kProdWarps * 32;
-constexpr int kMmaWarp = kEpiWarps;
-constexpr int kThreads = (kEpiWarps + 1 + kProdWarps) * 32;  // 544
-constexpr int kMaxK = 128;        // reduction length held in tensor memory
-// tensor-memory columns: two accumulators, then W hi, then W lo
-constexpr uint32_t kColAcc = 0, kColWHi = 2 * kTile, kColWLo = 2 * kTile + kMaxK;
+constexpr int kMmaWarp = kEpiWarps + kProdWarps;  // highest warp id: wins issue arbitration
+constexpr int kThreads = (kEpiWarps + 1 + kProdWarps) * 32;  // 672 -> 80 registers / thread
+constexpr int kMaxAct = 512;                  // reduction length with per-column scale / shift in smem
+constexpr int kMaxFold = 128;                 // SRC_POINTMLP: channels of the folded first layer
+static_assert(kRPT == 2 || kRPT == 4, "producer row mapping");
+// tensor-memory columns: two accumulators, then W hi, then W lo (128 columns each)
+constexpr uint32_t kColAcc = 0, kColWHi = 2 * kTile, kColWLo = 2 * kTile + 128;
 constexpr int kTmemCols = 512;
 
-struct SmemLayout {
-    static constexpr uint32_t ring = 0;
-    static constexpr uint32_t xyz = ring + kStages * kStageBytes;   // [4][128] float4
-    static constexpr uint32_t scale = xyz + 4 * kTile * 16;          // [128] float
-    static constexpr uint32_t shift = scale + kMaxK * 4;             // [128] float
-    static constexpr uint32_t fold = shift + kMaxK * 4;              // [128] float4
-    static constexpr uint32_t wst = fold + kMaxK * 16;               // [4 warps][32][33] float
-    static constexpr uint32_t bars = wst + 4 * 32 * 33 * 4;
-    static constexpr uint32_t nbars = 2 * kStages + 2 + 2 + 1 + 4;
-    static constexpr uint32_t misc = bars + nbars * 8;               // tmem slot, last-CTA flag
-    static constexpr uint32_t total = misc + 16;
+template <int PREC> struct Prec;
+template <> struct Prec<PREC_TF32> {
+    static constexpr int kEPC = 32;    // K elements per 128-byte chunk row
+    static constexpr int kEPU = 4;     // K elements per 16-byte unit
+    static constexpr int kMmaK = 8;
+    static constexpr int kTmemK = 128; // longest reduction whose W fits in tensor memory
+    static constexpr uint32_t kFmt = 2;
 };
-constexpr uint32_t kSmemBytes = SmemLayout::total + 1024;  // + alignment slack
+template <> struct Prec<PREC_F16> {
+    static constexpr int kEPC = 64;
+    static constexpr int kEPU = 8;
+    static constexpr int kMmaK = 16;
+    static constexpr int kTmemK = 256;
+    static constexpr uint32_t kFmt = 0;
+};
+// instruction descriptor: D fp32, A/B format fmt, both K-major, M = 128, N = 128
+__host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt) {
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kTile >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f16_ss(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(da), "l"(db),
+                 "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_f16_ts(uint32_t d, uint32_t ta, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(ta), "l"(db),
+                 "r"(idesc), "r"(acc) : "memory");
+}
+// two fp32 -> packed (fp16 hi pair, fp16 lo pair): hi = rn_f16(v), lo = rn_f16(v - hi)
+__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t &hi, uint32_t &lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 f = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
+    hi = *reinterpret_cast<const uint32_t *>(&h);
+    lo = *reinterpret_cast<const uint32_t *>(&l);
+}
+
+// Shared memory: the small fixed tables first, then the operand ring (read by the tensor core) and
+// the raw ring (fp32 activations landed by cp.async, thread-private slots), sized per instantiation.
+struct SmemLayout {
+    static constexpr uint32_t xyz = 0;                               // [4][128] float4 (SRC_GATHER)
+    static constexpr uint32_t scale = xyz + 4 * kTile * 16;          // [512] float
+    static constexpr uint32_t shift = scale + kMaxAct * 4;           // [512] float
+    static constexpr uint32_t fold = shift + kMaxAct * 4;            // [128] float4 (SRC_POINTMLP)
+    static constexpr uint32_t wst = fold + kMaxFold * 16;            // [4 warps][32][33] float
+    static constexpr uint32_t bars = wst + 4 * 32 * 33 * 4;
+    static constexpr uint32_t nbars = 2 * 6 + 2 + 2 + 1 + 4;
+    static constexpr uint32_t misc = bars + nbars * 8;               // tmem slot, last-CTA flag
+    static constexpr uint32_t ring = (misc + 16 + 1023) / 1024 * 1024;  // operand ring (1024-aligned)
+};
+template <int MODE, int PREC, int WMODE>
+struct Cfg {
+    static constexpr int kNV = Prec<PREC>::kEPU / 4;                 // 16-byte loads per row per chunk
+    static constexpr int kStageBytes = WMODE ? 2 * kXBytes : kXBytes;  // [X hi][X lo]([W hi][W lo])
+    static constexpr int kRawStageBytes =
+        MODE == SRC_POINTMLP ? 0 : kProdThreads * 16 * (kRPT * kNV) + (MODE == SRC_GATHER ? kTile * 4 * 6 : 0);
+    // operand stages / raw stages (cp.async groups in flight per thread = kRawStages - 1)
+    static constexpr int kStages = MODE == SRC_POINTMLP ? 6 : WMODE ? 2 : (PREC == PREC_F16 || MODE == SRC_GATHER) ? 3 : 4;
+    static constexpr int kRawStages =
+        MODE == SRC_POINTMLP ? 0 : (PREC == PREC_F16 ? (WMODE ? 2 : 3) : (MODE == SRC_GATHER && WMODE) ? 3 : 4);
+    static constexpr uint32_t raw = SmemLayout::ring + kStages * kStageBytes;
+    static constexpr uint32_t total = raw + kRawStages * kRawStageBytes;
+    static constexpr uint32_t bytes = total + 1024;  // + alignment slack
+    static_assert(bytes <= 227 * 1024, "shared memory budget");
+    static_assert(kStages <= 6, "barrier array");
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst_saddr, const void *src, bool valid) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_saddr), "l"(src),
+                 "r"(valid ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst_saddr, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_saddr), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 struct RowGeom {
     long long bN;  // b * N
@@ -84,25 +161,74 @@ __device__ __forceinline__ RowGeom row_geom(long long row, int K, int S, int N) 
     return r;
 }
 
-struct Chunk {
-    float4 v[4];
-    float e0, e1, e2;  // SRC_GATHER: centred xyz of this thread's staging row
-};
 
-template <int MODE, bool POOL, bool HAS_Y>
+// ------------------------------------------------------------------ streamed-W image (WMODE 1)
+// img: [nt][KC][hi | lo][128 rows][128 B] in the SWIZZLE_128B layout, so that a CTA stages the
+// (tile_n, chunk) operand with ONE linear TMA bulk copy of 32 KiB.
+template <int PREC>
+__global__ void __launch_bounds__(256)
+prep_wimg_kernel(const float *__restrict__ W, int wld, int wk0, int cin, int cout,
+                 const float *__restrict__ colscale, int KC, uint8_t *__restrict__ img) {
+    using P = Prec<PREC>;
+    const int nt = ceil_div(cout, kTile);
+    const long long total = (long long)nt * KC * kTile * 8;  // one 16-byte unit per thread step
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const int u = (int)(e & 7);
+        const int r = (int)((e >> 3) & (kTile - 1));
+        const int c = (int)((e >> 10) % KC);
+        const int tn = (int)((e >> 10) / KC);
+        const int row = tn * kTile + r;
+        float v[P::kEPU];
+#pragma unroll
+        for (int q = 0; q < P::kEPU; ++q) {
+            const int k = c * P::kEPC + u * P::kEPU + q;
+            float w = 0.f;
+            if (row < cout && k < cin) {
+                w = W[(size_t)row * wld + wk0 + k];
+                if (colscale != nullptr) w *= colscale[k];
+            }
+            v[q] = w;
+        }
+        uint32_t hi[4], lo[4];
+        if (PREC == PREC_TF32) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float h, l;
+                split_tf32(v[q], h, l);
+                hi[q] = __float_as_uint(h);
+                lo[q] = __float_as_uint(l);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) split_f16x2(v[(2 * q) % P::kEPU], v[(2 * q + 1) % P::kEPU], hi[q], lo[q]);
+        }
+        uint8_t *blk = img + ((size_t)(tn * KC + c) * 2) * kHalfBytes + (size_t)r * 128 + ((u ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4 *>(blk) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4 *>(blk + kHalfBytes) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+// --------------------------------------------------------------------------------- main kernel
+// WMODE 0: W resident in tensor memory (TS UMMA).  WMODE 1: W chunks streamed through the ring.
+template <int MODE, int PREC, int WMODE, bool POOL>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_layer_tt_kernel(const TtArgs a) {
+    using P = Prec<PREC>;
+    using CF = Cfg<MODE, PREC, WMODE>;
+    constexpr int kStages = CF::kStages;
+    constexpr int kStageBytes = CF::kStageBytes;
+    constexpr int NV = CF::kNV;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    float4 *xyz_stage = reinterpret_cast<float4 *>(smem + SmemLayout::xyz);
     float *s_scale = reinterpret_cast<float *>(smem + SmemLayout::scale);
     float *s_shift = reinterpret_cast<float *>(smem + SmemLayout::shift);
     float4 *s_fold = reinterpret_cast<float4 *>(smem + SmemLayout::fold);
     float *s_wst = reinterpret_cast<float *>(smem + SmemLayout::wst);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SmemLayout::bars);
     uint64_t *x_full = bars;
-    uint64_t *x_empty = bars + kStages;
-    uint64_t *acc_full = bars + 2 * kStages;
+    uint64_t *x_empty = bars + 6;
+    uint64_t *acc_full = bars + 12;
     uint64_t *acc_empty = acc_full + 2;
     uint64_t *w_ready = acc_empty + 2;
     uint64_t *xyz_full = w_ready + 1;
@@ -118,19 +244,19 @@ mlp_layer_tt_kernel(const TtArgs a) {
     const int gm = gridDim.x / nt;
     const int n0 = tile_n * kTile;
     const long long tiles_m = ceil_div<long long>(a.M, kTile);
-    const int KC = ceil_div(a.cin, kChunkK);
-    const int kpad = ceil_div(a.cin, 8) * 8;
+    const int KC = ceil_div(a.cin, P::kEPC);
+    const int kpad = ceil_div(a.cin, P::kMmaK) * P::kMmaK;
 
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) {
-            mbar_init(x_full + s, kProdWarps);
+            mbar_init(x_full + s, kProdWarps + (WMODE ? 1 : 0));  // + the TMA issuer's expect_tx
             mbar_init(x_empty + s, 1);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(acc_full + b, 1);
             mbar_init(acc_empty + b, kEpiWarps);
         }
-        mbar_init(w_ready, 4);
+        mbar_init(w_ready, kEpiWarps);
         for (int b = 0; b < 4; ++b) mbar_init(xyz_full + b, kProdWarps);
         fence_mbar_init();
     }
@@ -142,36 +268,46 @@ mlp_layer_tt_kernel(const TtArgs a) {
 
     if (warp < kEpiWarps) {
         // ================================ epilogue =========================================
-        const int quad = warp & 3;        // TMEM lane quadrant this warp may access
-        const int half = warp >> 2;       // rows [64*half, 64*half + 64) of every tile
+        const int quad = warp;            // TMEM lane quadrant this warp may access
         const int c = quad * 32 + lane;   // channel inside this CTA's 128-channel tile == TMEM lane
         const int cg = n0 + c;
         const bool cvalid = cg < a.cout;
         const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
-        // ---- warps 0-3 stage 32 W rows each into tensor memory (hi / lo split): coalesced row
-        //      loads, transposed through shared memory so that thread = channel owns its row
-        if (half == 0) {
+        // ---- stage 32 W rows per warp into tensor memory (hi / lo split): coalesced row loads,
+        //      transposed through shared memory so that thread = channel owns its row
+        if (WMODE == 0) {
             float *wst = s_wst + quad * 32 * 33;
-            for (int kc = 0; kc < KC; ++kc) {
-                const int k = kc * kChunkK + lane;
-#pragma unroll
-                for (int rr = 0; rr < 32; ++rr) {
-                    const int row = n0 + quad * 32 + rr;
-                    wst[rr * 33 + lane] = (row < a.cout && k < a.cin)
-                                              ? __ldg(a.W + (size_t)row * a.wld + a.wk0 + k) : 0.f;
-                }
-                __syncwarp();
+            for (int kc = 0; kc < KC; ++kc) {       // one 32-column TMEM chunk = kEPC elements
                 uint32_t hi[32], lo[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    float h, l;
-                    split_tf32(wst[lane * 33 + i], h, l);
-                    hi[i] = __float_as_uint(h);
-                    lo[i] = __float_as_uint(l);
+                for (int pass = 0; pass < P::kEPC / 32; ++pass) {
+                    const int k = kc * P::kEPC + pass * 32 + lane;
+                    const float cs = (a.w_colscale != nullptr && k < a.cin) ? __ldg(a.w_colscale + k) : 1.f;
+#pragma unroll
+                    for (int rr = 0; rr < 32; ++rr) {
+                        const int row = n0 + quad * 32 + rr;
+                        wst[rr * 33 + lane] = (row < a.cout && k < a.cin)
+                                                  ? __ldg(a.W + (size_t)row * a.wld + a.wk0 + k) * cs : 0.f;
+                    }
+                    __syncwarp();
+                    if (PREC == PREC_TF32) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            float h, l;
+                            split_tf32(wst[lane * 33 + i], h, l);
+                            hi[i] = __float_as_uint(h);
+                            lo[i] = __float_as_uint(l);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2)
+                            split_f16x2(wst[lane * 33 + i], wst[lane * 33 + i + 1], hi[(pass * 16 + i / 2) & 31],
+                                        lo[(pass * 16 + i / 2) & 31]);
+                    }
+                    __syncwarp();
                 }
-                tmem_st32(lane_base + kColWHi + kc * kChunkK, hi);
-                tmem_st32(lane_base + kColWLo + kc * kChunkK, lo);
-                __syncwarp();
+                tmem_st32(lane_base + kColWHi + kc * 32, hi);
+                tmem_st32(lane_base + kColWLo + kc * 32, lo);
             }
             tmem_wait_st();
             tc_fence_before();
@@ -185,15 +321,11 @@ mlp_layer_tt_kernel(const TtArgs a) {
             const float *wp = a.W + (size_t)cg * a.wld + a.wxyz;
             wx = wp[0]; wy = wp[1]; wz = wp[2];
         }
-        const bool do_y = HAS_Y && cvalid;
+        const bool do_y = (!POOL || a.y != nullptr) && cvalid;
         const bool do_pool = POOL && cvalid;
         const uint64_t bias2 = pack2(bias, bias);
         const uint64_t wx2 = pack2(wx, wx), wy2 = pack2(wy, wy), wz2 = pack2(wz, wz);
         const int kshift = POOL ? (a.K == 32 ? 5 : a.K == 64 ? 6 : 7) : 0;  // K in {32, 64, 128}
-        // s_wst is dead once W is staged (all eight warps pass the named barrier below first):
-        // reused to combine the two row-halves (pool extrema for K = 128, final statistics)
-        float *s_comb = s_wst;  // [2 tile parities][2][128] floats
-        named_bar_sync(2, kEpiWarps * 32);
         double acc_s = 0.0, acc_q = 0.0;
         uint32_t tl = 0;
         for (long long tile = mi; tile < tiles_m; tile += gm, ++tl) {
@@ -203,30 +335,29 @@ mlp_layer_tt_kernel(const TtArgs a) {
             if (MODE == SRC_GATHER) mbar_wait(xyz_full + (tl & 3), (tl >> 2) & 1);
             mbar_wait(acc_full + buf, (tl >> 1) & 1);
             tc_fence_after();
-            // this warp's 64 accumulator columns -> registers, then hand the buffer straight back
-            uint32_t r[2][32];
-            tmem_ld32_nowait(lane_base + kColAcc + buf * kTile + half * 64, r[0]);
-            tmem_ld32_nowait(lane_base + kColAcc + buf * kTile + half * 64 + 32, r[1]);
-            tmem_wait_ld();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty + buf);
-
-            const float4 *xs = xyz_stage + (tl & 3) * kTile + half * 64;
-            float *yrow = do_y ? a.y + ((size_t)m0 + half * 64) * a.cout + cg : nullptr;
-            const int nr = nrows - half * 64;  // valid rows of this half (may be <= 0)
             uint64_t s2 = 0ull, q2 = 0ull;     // packed (even rows, odd rows) running sums
             float mx = -INFINITY, mn = INFINITY;
-            auto body = [&](auto full_tag) {
-                constexpr bool FULL = decltype(full_tag)::value;
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
+#pragma unroll 1
+            for (int blk = 0; blk < 4; ++blk) {      // 32 accumulator columns (= rows) at a time
+                uint32_t r[32];
+                tmem_ld32_nowait(lane_base + kColAcc + buf * kTile + blk * 32, r);
+                tmem_wait_ld();
+                if (blk == 3) {
+                    // accumulator fully read: hand the buffer back to the MMA issuer
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty + buf);
+                }
+                const uint32_t xs = smem_u32(smem) + SmemLayout::xyz + 16 * ((tl & 3) * kTile + blk * 32);
+                float *yrow = do_y ? a.y + ((size_t)m0 + blk * 32) * a.cout + cg : nullptr;
+                const int nr = nrows - blk * 32;  // valid rows of this block (may be <= 0)
+                auto body = [&](auto full_tag) {
+                    constexpr bool FULL = decltype(full_tag)::value;
 #pragma unroll
                     for (int i = 0; i < 32; i += 2) {
-                        const int rr = j * 32 + i;
-                        uint64_t v2 = add2(pack2u(r[j][i], r[j][i + 1]), bias2);
+                        uint64_t v2 = add2(pack2u(r[i], r[i + 1]), bias2);
                         if (has_xyz) {
-                            const float4 p0 = xs[rr], p1 = xs[rr + 1];
+                            const float4 p0 = lds128f(xs + 16 * i), p1 = lds128f(xs + 16 * (i + 1));
                             v2 = fma2(wx2, pack2(p0.x, p1.x), v2);
                             v2 = fma2(wy2, pack2(p0.y, p1.y), v2);
                             v2 = fma2(wz2, pack2(p0.z, p1.z), v2);
@@ -237,60 +368,46 @@ mlp_layer_tt_kernel(const TtArgs a) {
                             s2 = add2(s2, v2);
                             q2 = fma2(v2, v2, q2);
                             if (do_y) {
-                                yrow[(size_t)rr * a.cout] = va;
-                                yrow[(size_t)(rr + 1) * a.cout] = vb;
+                                yrow[(size_t)i * a.cout] = va;
+                                yrow[(size_t)(i + 1) * a.cout] = vb;
                             }
                             if (POOL) {
                                 mx = fmaxf(fmaxf(mx, va), vb);
                                 mn = fminf(fminf(mn, va), vb);
                             }
                         } else {
-                            const bool rva = rr < nr, rvb = rr + 1 < nr;
+                            const bool rva = i < nr, rvb = i + 1 < nr;
                             const uint64_t m2 = pack2(rva ? va : 0.f, rvb ? vb : 0.f);
                             s2 = add2(s2, m2);
                             q2 = fma2(m2, m2, q2);
-                            if (do_y && rva) yrow[(size_t)rr * a.cout] = va;
-                            if (do_y && rvb) yrow[(size_t)(rr + 1) * a.cout] = vb;
+                            if (do_y && rva) yrow[(size_t)i * a.cout] = va;
+                            if (do_y && rvb) yrow[(size_t)(i + 1) * a.cout] = vb;
                             if (POOL) {
                                 if (rva) { mx = fmaxf(mx, va); mn = fminf(mn, va); }
                                 if (rvb) { mx = fmaxf(mx, vb); mn = fminf(mn, vb); }
                             }
                         }
                     }
-                    if (POOL && kshift == 5) {  // K = 32: one group per 32-row block
-                        if (do_pool && (FULL || j * 32 < nr)) {
-                            const long long g = (m0 >> 5) + half * 2 + j;
-                            a.pool_max[g * a.cout + cg] = mx;
-                            a.pool_min[g * a.cout + cg] = mn;
-                        }
-                        mx = -INFINITY;
-                        mn = INFINITY;
+                };
+                if (a.dbg & 4) {
+                    s2 = pack2u(r[0], r[31]);
+                } else if (nr >= 32) body(std::true_type{});
+                else body(std::false_type{});
+                // pooled groups of K rows end at multiples of K (K in {32, 64, 128})
+                if (POOL && ((blk + 1) * 32) % a.K == 0 && kshift != 7) {
+                    if (do_pool && nr > 0) {
+                        const long long g = ((m0 + blk * 32) >> kshift);
+                        a.pool_max[g * a.cout + cg] = mx;
+                        a.pool_min[g * a.cout + cg] = mn;
                     }
-                }
-            };
-            if (a.dbg & 4) {
-                s2 = pack2u(r[0][0], r[1][31]);
-            } else if (nr >= 64) body(std::true_type{});
-            else body(std::false_type{});
-            if (POOL && kshift == 6) {  // K = 64: this half is exactly one group
-                if (do_pool && nr > 0) {
-                    const long long g = (m0 >> 6) + half;
-                    a.pool_max[g * a.cout + cg] = mx;
-                    a.pool_min[g * a.cout + cg] = mn;
+                    mx = -INFINITY;
+                    mn = INFINITY;
                 }
             }
-            if (POOL && kshift == 7) {  // K = 128: the group spans both halves -> combine
-                float *cb = s_comb + (tl & 1) * 256;
-                if (half == 1) {
-                    cb[c] = mx;
-                    cb[128 + c] = mn;
-                }
-                named_bar_sync(2, kEpiWarps * 32);
-                if (half == 0 && do_pool) {
-                    const long long g = m0 >> 7;
-                    a.pool_max[g * a.cout + cg] = fmaxf(mx, cb[c]);
-                    a.pool_min[g * a.cout + cg] = fminf(mn, cb[128 + c]);
-                }
+            if (POOL && kshift == 7 && do_pool) {  // K = 128: the tile is one group
+                const long long g = m0 >> 7;
+                a.pool_max[g * a.cout + cg] = mx;
+                a.pool_min[g * a.cout + cg] = mn;
             }
             float sa, sb, qa, qb;
             unpack2(s2, sa, sb);
@@ -298,91 +415,109 @@ mlp_layer_tt_kernel(const TtArgs a) {
             acc_s += (double)sa + (double)sb;
             acc_q += (double)qa + (double)qb;
         }
-        if (a.stats_partial != nullptr) {
-            // combine the two row-halves, one partial row per CTA (fixed order -> deterministic)
-            named_bar_sync(2, kEpiWarps * 32);  // every pool exchange through s_comb is finished
-            double *cd = reinterpret_cast<double *>(s_wst);  // [2][128] doubles
-            if (half == 1) {
-                cd[c] = acc_s;
-                cd[128 + c] = acc_q;
+        if (a.stats_partial != nullptr && cvalid) {
+            // one partial row per CTA (fixed order across launches -> deterministic)
+            a.stats_partial[((long long)mi * 2 + 0) * a.cout + cg] = acc_s;
+            a.stats_partial[((long long)mi * 2 + 1) * a.cout + cg] = acc_q;
+            // partial rows this launch does not own are zeroed (fixed row count per M)
+            for (long long rr = mi + gm; rr < a.partial_rows; rr += gm) {
+                a.stats_partial[(rr * 2 + 0) * a.cout + cg] = 0.0;
+                a.stats_partial[(rr * 2 + 1) * a.cout + cg] = 0.0;
             }
-            named_bar_sync(2, kEpiWarps * 32);
-            if (half == 0 && cvalid) {
-                a.stats_partial[((long long)mi * 2 + 0) * a.cout + cg] = acc_s + cd[c];
-                a.stats_partial[((long long)mi * 2 + 1) * a.cout + cg] = acc_q + cd[128 + c];
-                // partial rows this launch does not own are zeroed (fixed row count per M)
-                for (long long rr = mi + gm; rr < a.partial_rows; rr += gm) {
-                    a.stats_partial[(rr * 2 + 0) * a.cout + cg] = 0.0;
-                    a.stats_partial[(rr * 2 + 1) * a.cout + cg] = 0.0;
-                }
-                __threadfence();
-            }
+            __threadfence();
         }
     } else if (warp == kMmaWarp) {
         // ================================ MMA issuer =======================================
-        if (lane == 0) {
+        // The whole warp runs the (uniform) control flow; one elected lane issues the tcgen05 ops.
+        if (WMODE == 0) {
             mbar_wait(w_ready, 0);
             tc_fence_after();
-            constexpr uint32_t idesc = make_idesc_tf32_m128(kTile);
-            const uint32_t ring_base = smem_u32(smem + SmemLayout::ring);
-            uint32_t it = 0, tl = 0;
-            for (long long tile = mi; tile < tiles_m; tile += gm, ++tl) {
-                const uint32_t buf = tl & 1;
-                mbar_wait(acc_empty + buf, ((tl >> 1) & 1) ^ 1);
+        }
+        constexpr uint32_t idesc = make_idesc(P::kFmt);
+        const uint32_t ring_base = smem_u32(smem + SmemLayout::ring);
+        uint32_t it = 0, tl = 0;
+        for (long long tile = mi; tile < tiles_m; tile += gm, ++tl) {
+            const uint32_t buf = tl & 1;
+            mbar_wait(acc_empty + buf, ((tl >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + kColAcc + buf * kTile;
+            for (int c = 0; c < KC; ++c, ++it) {
+                const uint32_t s = it % kStages;
+                mbar_wait(x_full + s, (it / kStages) & 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + kColAcc + buf * kTile;
-                for (int c = 0; c < KC; ++c, ++it) {
-                    const uint32_t s = it % kStages;
-                    mbar_wait(x_full + s, (it / kStages) & 1);
-                    tc_fence_after();
-                    const int kreal = min(kChunkK, kpad - c * kChunkK);  // multiple of 8
-                    const uint32_t x_hi = ring_base + s * kStageBytes;
-                    const uint32_t x_lo = x_hi + kHalfBytes;
-                    const uint32_t w_hi = tmem_base + kColWHi + c * kChunkK;
-                    const uint32_t w_lo = tmem_base + kColWLo + c * kChunkK;
-                    for (int ks = 0; ks * 8 < kreal && !(a.dbg & 2); ++ks) {
-                        const uint64_t dxh = make_desc_sw128(x_hi + ks * 32);
-                        const uint64_t dxl = make_desc_sw128(x_lo + ks * 32);
-                        mma_tf32_ts(d_tmem, w_lo + ks * 8, dxh, idesc, (c | ks) != 0);  // small terms first
-                        mma_tf32_ts(d_tmem, w_hi + ks * 8, dxl, idesc, 1);
-                        mma_tf32_ts(d_tmem, w_hi + ks * 8, dxh, idesc, 1);
+                const int nks = (a.dbg & 2) ? 0 : min(P::kEPC, kpad - c * P::kEPC) / P::kMmaK;  // 1..4 K steps
+                const uint32_t x_hi = ring_base + s * kStageBytes;
+                // descriptors of K step 0; one K step = 32 bytes of the swizzle row = +2 in the
+                // (address >> 4) field, = 8 tensor-memory columns
+                const uint64_t dxh = make_desc_sw128(x_hi), dxl = make_desc_sw128(x_hi + kHalfBytes);
+                const uint64_t dwh = make_desc_sw128(x_hi + kXBytes), dwl = make_desc_sw128(x_hi + kXBytes + kHalfBytes);
+                const uint32_t w_hi = tmem_base + kColWHi + c * 32, w_lo = tmem_base + kColWLo + c * 32;
+                if (elect_one()) {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        if (ks < nks) {
+                            const uint32_t acc0 = (c | ks) != 0;
+                            // small terms first
+                            if (WMODE == 0) {
+                                if (PREC == PREC_TF32) {
+                                    mma_tf32_ts(d_tmem, w_lo + ks * 8, dxh + ks * 2, idesc, acc0);
+                                    mma_tf32_ts(d_tmem, w_hi + ks * 8, dxl + ks * 2, idesc, 1);
+                                    mma_tf32_ts(d_tmem, w_hi + ks * 8, dxh + ks * 2, idesc, 1);
+                                } else {
+                                    mma_f16_ts(d_tmem, w_lo + ks * 8, dxh + ks * 2, idesc, acc0);
+                                    mma_f16_ts(d_tmem, w_hi + ks * 8, dxl + ks * 2, idesc, 1);
+                                    mma_f16_ts(d_tmem, w_hi + ks * 8, dxh + ks * 2, idesc, 1);
+                                }
+                            } else {
+                                if (PREC == PREC_TF32) {
+                                    mma_tf32_ss(d_tmem, dwl + ks * 2, dxh + ks * 2, idesc, acc0);
+                                    mma_tf32_ss(d_tmem, dwh + ks * 2, dxl + ks * 2, idesc, 1);
+                                    mma_tf32_ss(d_tmem, dwh + ks * 2, dxh + ks * 2, idesc, 1);
+                                } else {
+                                    mma_f16_ss(d_tmem, dwl + ks * 2, dxh + ks * 2, idesc, acc0);
+                                    mma_f16_ss(d_tmem, dwh + ks * 2, dxl + ks * 2, idesc, 1);
+                                    mma_f16_ss(d_tmem, dwh + ks * 2, dxh + ks * 2, idesc, 1);
+                                }
+                            }
+                        }
                     }
-                    mma_commit(x_empty + s);  // chunk reusable once these MMAs have read it
+                    mma_commit(x_empty + s);                       // chunk reusable once these MMAs have read it
+                    if (c == KC - 1) mma_commit(acc_full + buf);   // accumulator complete
                 }
-                mma_commit(acc_full + buf);   // accumulator complete
+                __syncwarp();
             }
         }
-        __syncwarp();
     } else {
         // ================================ producers ========================================
-        const int ptid = tid - (kEpiWarps + 1) * 32;  // 0..255
+        const int ptid = tid - kEpiWarps * 32;  // 0..255
         const int u = ptid & 7;       // 16-byte unit inside the 128-byte chunk row
-        const int rb = ptid >> 3;     // rows rb + 32*j, j = 0..3
+        const int rb = ptid >> 3;     // rows rb + kRowStride*j, j = 0..kRPT-1
         const uint32_t swz = (uint32_t)((u ^ (rb & 7)) << 4);
         const bool has_act = (MODE == SRC_PLAIN) && a.in_scale != nullptr;
-        if (MODE == SRC_PLAIN && ptid < kMaxK) {
-            s_scale[ptid] = (has_act && ptid < a.cin) ? a.in_scale[ptid] : 0.f;
-            s_shift[ptid] = (has_act && ptid < a.cin) ? a.in_shift[ptid] : 0.f;
-        }
-        if (MODE == SRC_POINTMLP && ptid < kMaxK)
+        if (MODE == SRC_PLAIN)
+            for (int k = ptid; k < kMaxAct; k += kProdThreads) {
+                s_scale[k] = (has_act && k < a.cin) ? a.in_scale[k] : 0.f;
+                s_shift[k] = (has_act && k < a.cin) ? a.in_shift[k] : 0.f;
+            }
+        if (MODE == SRC_POINTMLP && ptid < kMaxFold)
             s_fold[ptid] = ptid < a.cin ? reinterpret_cast<const float4 *>(a.l0_fold)[ptid]
                                         : make_float4(0.f, 0.f, 0.f, 0.f);
         named_bar_sync(1, kProdThreads);
 
         // ---- per-row geometry pipeline (SRC_GATHER / SRC_POINTMLP)
-        long long src[4] = {0, 0, 0, 0};   // b*N + n of the current tile's rows
-        int grp[4] = {0, 0, 0, 0};
-        int idx_pf[4] = {0, 0, 0, 0};      // prefetched neighbour indices of a later tile
-        long long bN_pf[4] = {0, 0, 0, 0};
-        int grp_pf[4] = {0, 0, 0, 0};
-        float4 p_nx[4];                    // SRC_POINTMLP: centred points of the next tile
+        long long src[kRPT] = {};          // b*N + n of the rows of the tile being issued
+        int grp[kRPT] = {};
+        int idx_pf[kRPT] = {};             // prefetched neighbour indices of a later tile
+        long long bN_pf[kRPT] = {};
+        int grp_pf[kRPT] = {};
+        float4 p_nx[kRPT], p_cur[kRPT];    // SRC_POINTMLP: centred points of the next / current tile
 #pragma unroll
-        for (int j = 0; j < 4; ++j) p_nx[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < kRPT; ++j) p_nx[j] = p_cur[j] = make_float4(0.f, 0.f, 0.f, 0.f);
 
         auto fetch_idx = [&](long long tile) {  // -> idx_pf / bN_pf / grp_pf for `tile`
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                long long row = tile * kTile + rb + 32 * j;
+            for (int j = 0; j < kRPT; ++j) {
+                long long row = tile * kTile + rb + kRowStride * j;
                 row = row < a.M ? row : a.M - 1;
                 const RowGeom rg = row_geom(row, a.K, a.S, a.N);
                 bN_pf[j] = rg.bN;
@@ -392,7 +527,7 @@ mlp_layer_tt_kernel(const TtArgs a) {
         };
         auto fetch_points = [&]() {  // idx_pf (arrived) -> p_nx
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < kRPT; ++j) {
                 const int n = min(max(idx_pf[j], 0), a.N - 1);
                 const float *q = a.xyz + (bN_pf[j] + n) * 3;
                 float px = __ldg(q), py = __ldg(q + 1), pz = __ldg(q + 2);
@@ -406,114 +541,161 @@ mlp_layer_tt_kernel(const TtArgs a) {
             }
         };
 
-        auto load = [&](long long tile, int c, Chunk &ch) {
+        // ---- raw ring (SRC_PLAIN / SRC_GATHER): every thread lands ITS OWN 16-byte units of a chunk
+        //      with cp.async into thread-private slots (slot q of thread t at (q*256 + t)*16: conflict
+        //      free) and reads them back itself -- global latency is hidden by the depth of the ring,
+        //      not by registers or warps.
+        const uint32_t sm = smem_u32(smem);
+        auto raw_slot = [&](int rs, int q) -> uint32_t {
+            return sm + CF::raw + rs * CF::kRawStageBytes + (q * kProdThreads + ptid) * 16;
+        };
+        auto raw_xyz = [&](int rs, int q) -> uint32_t {  // SRC_GATHER: 6 floats per row (threads u < kRPT)
+            return sm + CF::raw + rs * CF::kRawStageBytes + kProdThreads * 16 * (kRPT * NV) +
+                   4 * (q * kTile + rb + kRowStride * (u & (kRPT - 1)));
+        };
+        auto issue = [&](long long tile, int c, int rs) {  // chunk (tile, c) -> raw stage rs
+            if (a.dbg & 16) return;                          // triage: no global loads
             const long long m0 = tile * kTile;
-            const int k0 = c * kChunkK + u * 4;
+            const int k0 = c * P::kEPC + u * P::kEPU;
             if (MODE == SRC_PLAIN) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    long long row = m0 + rb + 32 * j;
+                for (int j = 0; j < kRPT; ++j) {
+                    long long row = m0 + rb + kRowStride * j;
                     row = row < a.M ? row : a.M - 1;
-                    ch.v[j] = k0 < a.cin ? __ldg(reinterpret_cast<const float4 *>(a.x + row * a.cin + k0))
-                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const bool ok = k0 < a.cin;
+                    const float *p = ok ? a.x + row * a.cin + k0 : a.x;
+#pragma unroll
+                    for (int h = 0; h < NV; ++h) cp_async16(raw_slot(rs, j * NV + h), p + (ok ? 4 * h : 0), ok);
                 }
             } else if (MODE == SRC_GATHER) {
                 if (c == 0) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
+                    for (int j = 0; j < kRPT; ++j) {
                         src[j] = bN_pf[j] + min(max(idx_pf[j], 0), a.N - 1);
                         grp[j] = grp_pf[j];
                     }
                     fetch_idx(tile + gm < tiles_m ? tile + gm : tile);
-                    if (u < 4) {  // this thread also stages the centred xyz of row rb + 32*u
-                        const long long sj = u == 0 ? src[0] : u == 1 ? src[1] : u == 2 ? src[2] : src[3];
-                        const int gj = u == 0 ? grp[0] : u == 1 ? grp[1] : u == 2 ? grp[2] : grp[3];
+                    if (u < kRPT) {  // this thread also stages the centred xyz of row rb + 64*u
+                        long long sj = src[0];
+                        int gj = grp[0];
+#pragma unroll
+                        for (int j = 1; j < kRPT; ++j)
+                            if (u == j) { sj = src[j]; gj = grp[j]; }
                         const float *q = a.xyz + sj * 3;
-                        ch.e0 = __ldg(q); ch.e1 = __ldg(q + 1); ch.e2 = __ldg(q + 2);
-                        if (a.new_xyz != nullptr) {
-                            const float *cc = a.new_xyz + (long long)gj * 3;
-                            ch.e0 = __fsub_rn(ch.e0, __ldg(cc));
-                            ch.e1 = __fsub_rn(ch.e1, __ldg(cc + 1));
-                            ch.e2 = __fsub_rn(ch.e2, __ldg(cc + 2));
+                        const float *cc = a.new_xyz != nullptr ? a.new_xyz + (long long)gj * 3 : q;
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) {
+                            cp_async4(raw_xyz(rs, d), q + d);
+                            cp_async4(raw_xyz(rs, 3 + d), cc + d);
                         }
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    ch.v[j] = k0 < a.D ? __ldg(reinterpret_cast<const float4 *>(a.feats + src[j] * a.D + k0))
-                                       : make_float4(0.f, 0.f, 0.f, 0.f);
-            } else {  // SRC_POINTMLP: no per-chunk loads, only the per-tile point pipeline
+                for (int j = 0; j < kRPT; ++j) {
+                    const bool ok = k0 < a.D;
+                    const float *p = ok ? a.feats + src[j] * a.D + k0 : a.feats;
+#pragma unroll
+                    for (int h = 0; h < NV; ++h) cp_async16(raw_slot(rs, j * NV + h), p + (ok ? 4 * h : 0), ok);
+                }
+            }
+        };
+
+        uint32_t it = 0, ptl = 0;
+        const uint8_t *wimg = reinterpret_cast<const uint8_t *>(a.wimg);
+        auto process = [&](long long tile, int c, int rs) {
+            const uint32_t s = it % kStages;
+            const int k0 = c * P::kEPC + u * P::kEPU;
+            float o[kRPT][P::kEPU];
+            float e0 = 0.f, e1 = 0.f, e2 = 0.f;
+            if (MODE == SRC_PLAIN || MODE == SRC_GATHER) {
+                float4 v[kRPT][NV];
+#pragma unroll
+                for (int j = 0; j < kRPT; ++j)
+#pragma unroll
+                    for (int h = 0; h < NV; ++h)
+                        v[j][h] = (a.dbg & 16) ? make_float4(1.f, 2.f, 3.f, (float)c)
+                                               : lds128f(raw_slot(rs, j * NV + h));
+                if (MODE == SRC_GATHER && c == 0 && u < kRPT && !(a.dbg & 16)) {
+                    e0 = lds32f(raw_xyz(rs, 0)); e1 = lds32f(raw_xyz(rs, 1)); e2 = lds32f(raw_xyz(rs, 2));
+                    if (a.new_xyz != nullptr) {
+                        e0 = __fsub_rn(e0, lds32f(raw_xyz(rs, 3)));
+                        e1 = __fsub_rn(e1, lds32f(raw_xyz(rs, 4)));
+                        e2 = __fsub_rn(e2, lds32f(raw_xyz(rs, 5)));
+                    }
+                }
+#pragma unroll
+                for (int h = 0; h < NV; ++h) {
+                    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (has_act) {
+                        sc = lds128f(sm + SmemLayout::scale + 4 * ((k0 & (kMaxAct - 1)) + 4 * h));
+                        sh = lds128f(sm + SmemLayout::shift + 4 * ((k0 & (kMaxAct - 1)) + 4 * h));
+                    }
+#pragma unroll
+                    for (int j = 0; j < kRPT; ++j) {
+                        const float4 w = v[j][h];
+                        if (has_act) {
+                            o[j][4 * h + 0] = fmaxf(fmaf(w.x, sc.x, sh.x), 0.f);
+                            o[j][4 * h + 1] = fmaxf(fmaf(w.y, sc.y, sh.y), 0.f);
+                            o[j][4 * h + 2] = fmaxf(fmaf(w.z, sc.z, sh.z), 0.f);
+                            o[j][4 * h + 3] = fmaxf(fmaf(w.w, sc.w, sh.w), 0.f);
+                        } else {
+                            o[j][4 * h + 0] = w.x; o[j][4 * h + 1] = w.y;
+                            o[j][4 * h + 2] = w.z; o[j][4 * h + 3] = w.w;
+                        }
+                    }
+                }
+            } else {  // SRC_POINTMLP
                 if (c == 0) {
                     // p_nx holds this tile's points (issued one tile ago); refill it for the next
                     // tile from idx_pf (issued one tile ago), then prefetch idx two tiles ahead
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) ch.v[j] = p_nx[j];
+                    for (int j = 0; j < kRPT; ++j) p_cur[j] = p_nx[j];
                     fetch_points();
                     const long long t2 = tile + 2LL * gm;
                     fetch_idx(t2 < tiles_m ? t2 : tile);
                 }
-            }
-        };
-        // SRC_POINTMLP keeps the current tile's points here (chunks c >= 1 reuse them)
-        float4 p_cur[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) p_cur[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-
-        uint32_t it = 0, ptl = 0;
-        auto process = [&](int c, Chunk &ch) {
-            const uint32_t s = it % kStages;
-            const int k0 = c * kChunkK + u * 4;
-            float4 o[4];
-            if (MODE == SRC_PLAIN) {
-                if (has_act) {
-                    const float4 sc = *reinterpret_cast<const float4 *>(s_scale + k0);
-                    const float4 sh = *reinterpret_cast<const float4 *>(s_shift + k0);
+                for (int q = 0; q < P::kEPU; ++q) {
+                    const float4 f = lds128f(sm + SmemLayout::fold + 16 * ((k0 + q) & (kMaxFold - 1)));
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        o[j].x = fmaxf(fmaf(ch.v[j].x, sc.x, sh.x), 0.f);
-                        o[j].y = fmaxf(fmaf(ch.v[j].y, sc.y, sh.y), 0.f);
-                        o[j].z = fmaxf(fmaf(ch.v[j].z, sc.z, sh.z), 0.f);
-                        o[j].w = fmaxf(fmaf(ch.v[j].w, sc.w, sh.w), 0.f);
+                    for (int j = 0; j < kRPT; ++j) {
+                        const float4 p = p_cur[j];
+                        o[j][q] = fmaxf(fmaf(f.x, p.x, fmaf(f.y, p.y, fmaf(f.z, p.z, f.w))), 0.f);
                     }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) o[j] = ch.v[j];
-                }
-            } else if (MODE == SRC_GATHER) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) o[j] = ch.v[j];
-            } else {
-                if (c == 0) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) p_cur[j] = ch.v[j];
-                }
-                const float4 f0 = s_fold[k0], f1 = s_fold[k0 + 1], f2 = s_fold[k0 + 2], f3 = s_fold[k0 + 3];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float4 p = p_cur[j];
-                    o[j].x = fmaxf(fmaf(f0.x, p.x, fmaf(f0.y, p.y, fmaf(f0.z, p.z, f0.w))), 0.f);
-                    o[j].y = fmaxf(fmaf(f1.x, p.x, fmaf(f1.y, p.y, fmaf(f1.z, p.z, f1.w))), 0.f);
-                    o[j].z = fmaxf(fmaf(f2.x, p.x, fmaf(f2.y, p.y, fmaf(f2.z, p.z, f2.w))), 0.f);
-                    o[j].w = fmaxf(fmaf(f3.x, p.x, fmaf(f3.y, p.y, fmaf(f3.z, p.z, f3.w))), 0.f);
                 }
             }
             mbar_wait(x_empty + s, ((it / kStages) & 1) ^ 1);
+            const uint32_t stage = sm + SmemLayout::ring + s * kStageBytes;
+            if (WMODE == 1 && ptid == 0) {
+                // stream this chunk of W (hi + lo blocks, 32 KiB contiguous in the image)
+                mbar_expect_tx(x_full + s, kXBytes);
+                bulk_g2s(smem + SmemLayout::ring + s * kStageBytes + kXBytes,
+                         wimg + ((size_t)tile_n * KC + c) * kXBytes, kXBytes, x_full + s);
+            }
             if (MODE == SRC_GATHER && c == 0) {
-                if (u < 4) xyz_stage[(ptl & 3) * kTile + rb + 32 * u] = make_float4(ch.e0, ch.e1, ch.e2, 0.f);
+                if (u < kRPT)
+                    sts128f(sm + SmemLayout::xyz + 16 * ((ptl & 3) * kTile + rb + kRowStride * u), make_float4(e0, e1, e2, 0.f));
                 __syncwarp();
                 if (lane == 0) mbar_arrive(xyz_full + (ptl & 3));
             }
-            uint8_t *hi_base = smem + SmemLayout::ring + s * kStageBytes;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float4 hi, lo;
-                split_tf32(o[j].x, hi.x, lo.x);
-                split_tf32(o[j].y, hi.y, lo.y);
-                split_tf32(o[j].z, hi.z, lo.z);
-                split_tf32(o[j].w, hi.w, lo.w);
-                const uint32_t off = (uint32_t)(rb + 32 * j) * 128u + swz;
-                *reinterpret_cast<float4 *>(hi_base + off) = hi;
-                *reinterpret_cast<float4 *>(hi_base + kHalfBytes + off) = lo;
+            for (int j = 0; j < kRPT; ++j) {
+                uint4 hi, lo;
+                if (PREC == PREC_TF32) {
+                    float h[4], l[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) split_tf32(o[j][q], h[q], l[q]);
+                    hi = make_uint4(__float_as_uint(h[0]), __float_as_uint(h[1]), __float_as_uint(h[2]), __float_as_uint(h[3]));
+                    lo = make_uint4(__float_as_uint(l[0]), __float_as_uint(l[1]), __float_as_uint(l[2]), __float_as_uint(l[3]));
+                } else {
+                    split_f16x2(o[j][0], o[j][1], hi.x, lo.x);
+                    split_f16x2(o[j][2], o[j][3], hi.y, lo.y);
+                    split_f16x2(o[j][4 % P::kEPU], o[j][5 % P::kEPU], hi.z, lo.z);
+                    split_f16x2(o[j][6 % P::kEPU], o[j][7 % P::kEPU], hi.w, lo.w);
+                }
+                const uint32_t off = (uint32_t)(rb + kRowStride * j) * 128u + swz;
+                sts128(stage + off, hi);
+                sts128(stage + kHalfBytes + off, lo);
             }
             fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
             __syncwarp();
@@ -522,31 +704,17 @@ mlp_layer_tt_kernel(const TtArgs a) {
             if (c == KC - 1) ++ptl;
         };
 
-        const long long tile = mi;
-        const bool have = tile < tiles_m;
-        if (have && MODE != SRC_PLAIN) {
-            fetch_idx(tile);                       // idx of the first tile
-            if (MODE == SRC_POINTMLP) {
-                fetch_points();                    // -> p_nx = points of the first tile
-                fetch_idx(tile + gm < tiles_m ? tile + gm : tile);
-            }
-        }
-        // three chunks of global loads in flight per thread (registers ca / cb / cc rotate)
-        Chunk ca, cb, cc;
-        ca.e0 = ca.e1 = ca.e2 = cb.e0 = cb.e1 = cb.e2 = cc.e0 = cc.e1 = cc.e2 = 0.f;
         auto advance = [&](long long &t, int &ci) {
             if (++ci == KC) { ci = 0; t += gm; }
         };
-        long long t0 = tile, t1 = tile, t2;
-        int c0 = 0, c1 = 0, c2;
-        advance(t1, c1);
-        bool have0 = have, have1 = have && t1 < tiles_m;
+        const long long tile0 = mi;
         if (a.dbg & 1) {
             // triage: ring protocol only
-            for (long long t = tile; t < tiles_m; t += gm)
+            for (long long t = tile0; t < tiles_m; t += gm)
                 for (int cq = 0; cq < KC; ++cq) {
                     const uint32_t s = it % kStages;
                     mbar_wait(x_empty + s, ((it / kStages) & 1) ^ 1);
+                    if (WMODE == 1 && ptid == 0) mbar_arrive(x_full + s);
                     if (MODE == SRC_GATHER && cq == 0) { __syncwarp(); if (lane == 0) mbar_arrive(xyz_full + (ptl & 3)); }
                     fence_proxy_async();
                     __syncwarp();
@@ -554,27 +722,32 @@ mlp_layer_tt_kernel(const TtArgs a) {
                     ++it;
                     if (cq == KC - 1) ++ptl;
                 }
-            have0 = false;
-        }
-        if (have0) load(t0, c0, ca);
-        if (have1) load(t1, c1, cb);
-        while (have0) {
-            t2 = t1; c2 = c1; advance(t2, c2);
-            const bool have2 = have1 && t2 < tiles_m;
-            if (have2) load(t2, c2, cc);
-            process(c0, ca);
-            if (!have1) break;
-            long long t3 = t2; int c3 = c2; advance(t3, c3);
-            const bool have3 = have2 && t3 < tiles_m;
-            if (have3) load(t3, c3, ca);
-            process(c1, cb);
-            if (!have2) break;
-            long long t4 = t3; int c4 = c3; advance(t4, c4);
-            const bool have4 = have3 && t4 < tiles_m;
-            if (have4) load(t4, c4, cb);
-            process(c2, cc);
-            t0 = t3; c0 = c3; have0 = have3;
-            t1 = t4; c1 = c4; have1 = have4;
+        } else if (MODE == SRC_POINTMLP) {
+            if (tile0 < tiles_m) {
+                fetch_idx(tile0);                       // idx of the first tile
+                fetch_points();                         // -> p_nx = points of the first tile
+                fetch_idx(tile0 + gm < tiles_m ? tile0 + gm : tile0);
+            }
+            for (long long t = tile0; t < tiles_m; t += gm)
+                for (int cq = 0; cq < KC; ++cq) process(t, cq, 0);
+        } else {
+            constexpr int R = CF::kRawStages > 0 ? CF::kRawStages : 1;
+            if (MODE == SRC_GATHER && tile0 < tiles_m) fetch_idx(tile0);
+            long long ti = tile0, tp = tile0;  // issue cursor, process cursor
+            int ci = 0, cp = 0;
+            for (int n = 0; n < R - 1; ++n) {
+                if (ti < tiles_m) { issue(ti, ci, n); advance(ti, ci); }
+                cp_async_commit();
+            }
+            uint32_t i = 0;
+            while (tp < tiles_m) {
+                if (ti < tiles_m) { issue(ti, ci, (int)((i + R - 1) % R)); advance(ti, ci); }
+                cp_async_commit();              // (possibly empty) group: keeps the group count uniform
+                cp_async_wait<R - 1>();         // chunk i has landed (this thread's own copies)
+                process(tp, cp, (int)(i % R));
+                advance(tp, cp);
+                ++i;
+            }
         }
     }
 
@@ -593,60 +766,40 @@ mlp_layer_tt_kernel(const TtArgs a) {
         __syncthreads();
         if (*s_last != 0u) {
             __threadfence();
-            // 2*cout (channel, sum | sum^2) columns x gm partial rows: 256 columns at a time, the
-            // rows split over two thread slices (fixed order -> deterministic), combined in smem
-            double *red = reinterpret_cast<double *>(smem + SmemLayout::ring);  // [2][256]
-            const int col_l = tid & 255, sl = tid >> 8;  // threads >= 512 idle
-            for (int base = 0; base < 2 * a.cout; base += 256) {
+            // 2*cout (sum | sum^2, channel) columns x gm partial rows: 128 columns at a time, the
+            // rows split over three thread slices (fixed order -> deterministic), combined in smem
+            double *red = reinterpret_cast<double *>(smem + SmemLayout::ring);            // [3][128]
+            double *all = reinterpret_cast<double *>(smem + SmemLayout::ring + kXBytes);  // [2*cout]
+            const int col_l = tid & 127, sl = tid >> 7;  // slices 0..2; threads >= 384 idle
+            for (int base = 0; base < 2 * a.cout; base += 128) {
                 const int col = base + col_l;  // = which * cout + ch
-                double acc = 0.0;
-                if (sl < 2 && col < 2 * a.cout) {
-                    const int which = col / a.cout, ch = col - which * a.cout;
-                    const double *p = a.stats_partial + (long long)which * a.cout + ch;
+                if (sl < 3 && col < 2 * a.cout) {
+                    double acc = 0.0;
+                    const double *p = a.stats_partial + col;
 #pragma unroll 16
-                    for (int r = sl; r < gm; r += 2) acc += __ldcg(p + (long long)r * 2 * a.cout);
-                    red[sl * 256 + col_l] = acc;
+                    for (int r = sl; r < gm; r += 3) acc += __ldcg(p + (long long)r * 2 * a.cout);
+                    red[sl * 128 + col_l] = acc;
                 }
                 __syncthreads();
-                if (sl == 0 && col < 2 * a.cout) red[col_l] = red[col_l] + red[256 + col_l];
-                __syncthreads();
-                // channels whose sum AND sum^2 columns are both inside this 256-column window
-                // (cout >= 128: the two columns of a channel are cout apart -> handled below)
-                if (2 * a.cout <= 256) {
-                    if (tid < a.cout) {
-                        const int ch = tid;
-                        const double mean = red[ch] / a.count;
-                        double var = red[a.cout + ch] / a.count - mean * mean;  // biased (Paddle training BN)
-                        var = var > 0.0 ? var : 0.0;
-                        const double g = a.gamma ? (double)a.gamma[ch] : 1.0;
-                        const double b = a.beta ? (double)a.beta[ch] : 0.0;
-                        const double sc = g / sqrt(var + (double)a.eps);
-                        a.scale[ch] = (float)sc;
-                        a.shift[ch] = (float)(b - mean * sc);
-                        if (a.mean_out) a.mean_out[ch] = (float)mean;
-                        if (a.var_out) a.var_out[ch] = (float)var;
-                    }
-                } else {
-                    // park the reduced columns in the (dead) second ring stage: [2*cout] doubles
-                    double *all = reinterpret_cast<double *>(smem + SmemLayout::ring + kStageBytes);
-                    if (sl == 0 && col < 2 * a.cout) all[col] = red[col_l];
-                }
+                if (sl == 0 && col < 2 * a.cout) all[col] = (red[col_l] + red[128 + col_l]) + red[256 + col_l];
                 __syncthreads();
             }
-            if (2 * a.cout > 256) {
-                const double *all = reinterpret_cast<const double *>(smem + SmemLayout::ring + kStageBytes);
-                for (int ch = tid; ch < a.cout; ch += kThreads) {
-                    const double mean = all[ch] / a.count;
-                    double var = all[a.cout + ch] / a.count - mean * mean;
-                    var = var > 0.0 ? var : 0.0;
-                    const double g = a.gamma ? (double)a.gamma[ch] : 1.0;
-                    const double b = a.beta ? (double)a.beta[ch] : 0.0;
-                    const double sc = g / sqrt(var + (double)a.eps);
-                    a.scale[ch] = (float)sc;
-                    a.shift[ch] = (float)(b - mean * sc);
-                    if (a.mean_out) a.mean_out[ch] = (float)mean;
-                    if (a.var_out) a.var_out[ch] = (float)var;
+            for (int ch = tid; ch < a.cout; ch += kThreads) {
+                const double mean = all[ch] / a.count;
+                double var = all[a.cout + ch] / a.count - mean * mean;  // biased, as Paddle's training BN
+                var = var > 0.0 ? var : 0.0;
+                const double g = a.gamma ? (double)a.gamma[ch] : 1.0;
+                const double b = a.beta ? (double)a.beta[ch] : 0.0;
+                const double sc = g / sqrt(var + (double)a.eps);
+                float cs = 1.f;
+                if (a.out_colscale != nullptr) {
+                    cs = f16_colscale(g, b, a.count);
+                    a.out_colscale[ch] = cs;
                 }
+                a.scale[ch] = (float)sc / cs;
+                a.shift[ch] = (float)(b - mean * sc) / cs;
+                if (a.mean_out) a.mean_out[ch] = (float)mean;
+                if (a.var_out) a.var_out[ch] = (float)var;
             }
             if (tid == 0) *a.counter = 0u;  // self-cleaning for the next launch
         }
@@ -749,31 +902,64 @@ point_moments_kernel(const MomentArgs a) {
         const double sh = be - mean * sc;
         a.scale[c] = (float)sc;
         a.shift[c] = (float)sh;
+        double cs = 1.0;  // power of two keeping relu(bn(y0)) / cs below 2^15 (fp16 operands)
+        if (a.out_colscale != nullptr) {
+            const float csf = f16_colscale(g, be, (double)a.M);
+            a.out_colscale[c] = csf;
+            cs = (double)csf;
+        }
         reinterpret_cast<float4 *>(a.l0_fold)[c] =
-            make_float4((float)(sc * w0), (float)(sc * w1), (float)(sc * w2), (float)(sc * b0 + sh));
+            make_float4((float)(sc * w0 / cs), (float)(sc * w1 / cs), (float)(sc * w2 / cs),
+                        (float)((sc * b0 + sh) / cs));
     }
 }
 
 // ------------------------------------------------------------------------------------ host side
+static int tmem_k(int prec) { return prec == PREC_F16 ? Prec<PREC_F16>::kTmemK : Prec<PREC_TF32>::kTmemK; }
+static int epc(int prec) { return prec == PREC_F16 ? Prec<PREC_F16>::kEPC : Prec<PREC_TF32>::kEPC; }
+static int epu(int prec) { return prec == PREC_F16 ? Prec<PREC_F16>::kEPU : Prec<PREC_TF32>::kEPU; }
+
 bool eligible(const TtProblem &p) {
-    if (p.cout < 1 || p.cout > 4 * kTile) return false;
-    if (p.cin < 4 || p.cin > kMaxK || p.cin % 4 != 0) return false;
-    if (p.mode == SRC_GATHER && p.D != p.cin) return false;
+    if (p.prec != PREC_TF32 && p.prec != PREC_F16) return false;
+    if (p.cout < 1 || p.cout > 8 * kTile) return false;
+    if (p.cin < epu(p.prec) || p.cin % epu(p.prec) != 0) return false;
+    if (p.mode == SRC_POINTMLP) {
+        if (p.cin > kMaxFold) return false;
+    } else if (p.cin > kMaxAct) {
+        return false;
+    }
+    if (p.mode == SRC_GATHER && (p.D != p.cin || p.prec != PREC_TF32)) return false;
     if (p.pool && !(p.K == 32 || p.K == 64 || p.K == 128)) return false;
     return true;
 }
 
-template <int MODE, bool POOL, bool HAS_Y>
+size_t wimg_bytes(int prec, int cin, int cout) {
+    if (cin <= tmem_k(prec)) return 0;
+    return (size_t)ceil_div(cout, kTile) * ceil_div(cin, epc(prec)) * kXBytes;
+}
+
+template <int MODE, int PREC, int WMODE, bool POOL>
 static int launch_inst(const TtArgs &a, int grid, cudaStream_t st) {
-    auto k = mlp_layer_tt_kernel<MODE, POOL, HAS_Y>;
+    auto k = mlp_layer_tt_kernel<MODE, PREC, WMODE, POOL>;
     static bool configured = false;
     if (!configured) {
-        PAPC_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        PAPC_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)Cfg<MODE, PREC, WMODE>::bytes));
         configured = true;
     }
-    k<<<grid, kThreads, kSmemBytes, st>>>(a);
+    k<<<grid, kThreads, Cfg<MODE, PREC, WMODE>::bytes, st>>>(a);
     PAPC_LAUNCH_CHECK();
     return PAPC_OK;
+}
+
+template <int MODE, int PREC>
+static int launch_mp(const TtArgs &a, bool streamed, bool pool, int grid, cudaStream_t st) {
+    if (streamed) {
+        if (MODE == SRC_POINTMLP) return PAPC_EUNSUPPORTED;
+        constexpr int M1 = MODE == SRC_POINTMLP ? SRC_PLAIN : MODE;  // never instantiated for POINTMLP
+        return pool ? launch_inst<M1, PREC, 1, true>(a, grid, st) : launch_inst<M1, PREC, 1, false>(a, grid, st);
+    }
+    return pool ? launch_inst<MODE, PREC, 0, true>(a, grid, st) : launch_inst<MODE, PREC, 0, false>(a, grid, st);
 }
 
 int launch(const TtArgs &a_in, cudaStream_t st) {
@@ -783,26 +969,38 @@ int launch(const TtArgs &a_in, cudaStream_t st) {
         a.dbg = e ? atoi(e) : 0;
     }
     const bool pool = a.pool_max != nullptr;
+    if (!pool && a.y == nullptr) return PAPC_EINVAL;
+    const bool streamed = a.cin > tmem_k(a.prec);
     const int nt = ceil_div(a.cout, kTile);
+    if (streamed) {
+        if (a.wimg == nullptr) return PAPC_EWORKSPACE;
+        const int KC = ceil_div(a.cin, epc(a.prec));
+        long long blocks = ((long long)nt * KC * kTile * 8 + 255) / 256;
+        if (blocks > 4LL * kNumSMs) blocks = 4LL * kNumSMs;
+        if (a.prec == PREC_F16)
+            prep_wimg_kernel<PREC_F16><<<(unsigned)blocks, 256, 0, st>>>(
+                a.W, a.wld, a.wk0, a.cin, a.cout, a.w_colscale, KC, reinterpret_cast<uint8_t *>(a.wimg));
+        else
+            prep_wimg_kernel<PREC_TF32><<<(unsigned)blocks, 256, 0, st>>>(
+                a.W, a.wld, a.wk0, a.cin, a.cout, a.w_colscale, KC, reinterpret_cast<uint8_t *>(a.wimg));
+        PAPC_LAUNCH_CHECK();
+    }
     const long long tiles_m = ceil_div<long long>(a.M, kTile);
     long long gm = kNumSMs / nt;
     if (gm < 1) gm = 1;
     if (gm > tiles_m) gm = tiles_m;
     if (a.stats_partial != nullptr && gm > a.partial_rows) gm = a.partial_rows;
     const int grid = (int)(gm * nt);
-    const bool has_y = a.y != nullptr;
-#define PAPC_TT_CASE(MODE_)                                                        \
-    case MODE_:                                                                    \
-        if (pool && has_y) return launch_inst<MODE_, true, true>(a, grid, st);     \
-        if (pool) return launch_inst<MODE_, true, false>(a, grid, st);             \
-        if (has_y) return launch_inst<MODE_, false, true>(a, grid, st);            \
-        return launch_inst<MODE_, false, false>(a, grid, st);
     switch (a.mode) {
-        PAPC_TT_CASE(SRC_PLAIN)
-        PAPC_TT_CASE(SRC_GATHER)
-        PAPC_TT_CASE(SRC_POINTMLP)
+        case SRC_PLAIN:
+            return a.prec == PREC_F16 ? launch_mp<SRC_PLAIN, PREC_F16>(a, streamed, pool, grid, st)
+                                      : launch_mp<SRC_PLAIN, PREC_TF32>(a, streamed, pool, grid, st);
+        case SRC_GATHER:
+            return launch_mp<SRC_GATHER, PREC_TF32>(a, streamed, pool, grid, st);
+        case SRC_POINTMLP:
+            return a.prec == PREC_F16 ? launch_mp<SRC_POINTMLP, PREC_F16>(a, streamed, pool, grid, st)
+                                      : launch_mp<SRC_POINTMLP, PREC_TF32>(a, streamed, pool, grid, st);
     }
-#undef PAPC_TT_CASE
     return PAPC_EINVAL;
 }
 

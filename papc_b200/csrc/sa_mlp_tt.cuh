@@ -1,5 +1,5 @@
-// sa_mlp_tt.cuh -- interface of the transposed tcgen05 layer kernel (weights resident in tensor
-// memory) and of the point-moment kernel that lets a cin<=8 first layer be recomputed on the fly.
+// sa_mlp_tt.cuh -- interface of the transposed tcgen05 layer kernel and of the point-moment kernel
+// that lets a cin<=8 first layer be recomputed on the fly.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -11,8 +11,12 @@ enum { SRC_PLAIN = 0,     // x [M,cin] (+ optional relu(in_scale*x + in_shift))
        SRC_GATHER = 1,    // feats[b, idx] rows through the tensor core, centred xyz in the epilogue
        SRC_POINTMLP = 2 };// relu(bn(W0 * centred xyz + b0)) recomputed per row from the folded W0
 
+enum { PREC_TF32 = 0,     // 3xTF32: hi/lo TF32 split of both operands, K = 8 per MMA
+       PREC_F16 = 1 };    // 3xFP16: hi/lo fp16 split, K = 16 per MMA; needs |activation| < 2^15 --
+                          // used only where a bound is known (inputs that are relu(batch-norm(.)))
+
 struct TtArgs {
-    int mode;
+    int mode, prec;
     long long M;
     int K;          // rows per group (pooling)
     int cin;        // reduction length on the tensor core (PLAIN: columns of x, GATHER: D, POINTMLP: c0)
@@ -25,30 +29,45 @@ struct TtArgs {
     int N, S, D;
     const float *l0_fold;  // SRC_POINTMLP: [cin][4] = scale*w_x, scale*w_y, scale*w_z, scale*b + shift
     // weights of THIS layer: W[c*wld + wk0 + k] multiplies tensor column k; W[c*wld + wxyz + {0,1,2}]
-    // the centred xyz (SRC_GATHER, -1 = none)
+    // the centred xyz (SRC_GATHER, -1 = none).  w_colscale[k] (nullable): power-of-two factor folded
+    // into column k (the producer of the activations divided them by it).
     const float *W;
     int wld, wk0, wxyz;
+    const float *w_colscale;
+    void *wimg;                  // streamed-W mode: workspace for the pre-split, pre-swizzled image
     const float *bias;
     float *y;                    // [M,cout] pre-BN output (nullable)
     float *pool_max, *pool_min;  // [M/K,cout] (nullable)
     double *stats_partial;       // [partial_rows][2][cout] (nullable)
     long long partial_rows;
-    // fused BatchNorm finalisation by the last CTA to finish (counter nullable = off)
+    // fused BatchNorm finalisation by the last CTA to finish (counter nullable = off).
+    // out_colscale (nullable): per-channel power of two 2^e such that relu(bn(y)) / 2^e < 2^15 for
+    // every possible y (bound |gamma| sqrt(count) + |beta|); scale/shift are written divided by it.
     unsigned int *counter;
     const float *gamma, *beta;
     float eps;
     double count;
-    float *scale, *shift, *mean_out, *var_out;
+    float *scale, *shift, *mean_out, *var_out, *out_colscale;
     int dbg;  // PAPC_TT_DBG bit mask (performance triage only): 1 = producers skip loads+math,
               // 2 = no MMAs issued, 4 = epilogue skips its math / stores
 };
 
 struct TtProblem {
-    int mode, cin, cout, K, D;
+    int mode, prec, cin, cout, K, D;
     bool pool;
 };
 bool eligible(const TtProblem &p);
+// Bytes of the streamed-W image the launch needs in TtArgs::wimg (0 = W fits in tensor memory).
+size_t wimg_bytes(int prec, int cin, int cout);
 int launch(const TtArgs &a, cudaStream_t st);
+
+// 2^e >= bound / 2^15 (e >= 0): the exact power-of-two pre-scale that keeps fp16 operands finite
+__host__ __device__ inline float f16_colscale(double gamma, double beta, double count) {
+    const double bound = (gamma < 0 ? -gamma : gamma) * sqrt(count) + (beta < 0 ? -beta : beta);
+    float s = 1.f;
+    while ((double)s * 32768.0 < bound && s < 1e30f) s *= 2.f;
+    return s;
+}
 
 // Moments of the centred grouped points p = xyz[b, idx] - new_xyz over all M rows, then -- in the
 // last block -- BatchNorm statistics of y0 = W0 p + b0 derived analytically in fp64
@@ -67,6 +86,7 @@ struct MomentArgs {
     unsigned int *counter;
     float *scale, *shift, *mean_out, *var_out;  // [c0] (mean/var nullable)
     float *l0_fold;         // [c0][4]
+    float *out_colscale;    // [c0] (nullable): see TtArgs::out_colscale; folded into l0_fold
 };
 int moment_blocks(long long M);
 int launch_moments(const MomentArgs &a, cudaStream_t st);

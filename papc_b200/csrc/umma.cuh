@@ -136,6 +136,39 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
 __device__ __forceinline__ void tmem_wait_st() {
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
+// explicit shared-window accesses on 32-bit shared addresses (pointer arithmetic on the dynamic
+// shared buffer otherwise degrades to generic LD/ST with 64-bit address math)
+__device__ __forceinline__ void sts128(uint32_t saddr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void sts128f(uint32_t saddr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ float4 lds128f(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr)
+                 : "memory");
+    return v;
+}
+__device__ __forceinline__ float lds32f(uint32_t saddr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr) : "memory");
+    return v;
+}
+// one lane of a converged warp (elect.sync): the canonical way to issue tcgen05 ops from uniform code
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ float tf32_rna(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));

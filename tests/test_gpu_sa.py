@@ -209,6 +209,28 @@ def test_set_abstraction_layer(cfg, bn_mode):
     np.testing.assert_allclose(gp.cpu().numpy(), rp, **TOL)
 
 
+def test_fp16_split_column_scale_large_gamma():
+    """BatchNorm weights large enough that relu(bn(.)) exceeds the fp16 range: the exact
+    power-of-two column scale of the fp16-split layers must keep the result within tolerance."""
+    rng = np.random.default_rng(5)
+    B, N = 4, 512
+    xyz = synth.clouds(B, N, seed=8)
+    start = synth.fps_start(B, N, seed=9)
+    args = (128, 0.2, 32, 3, [64, 64, 128], False)
+    gpu, ref = layers.PointNetSetAbstraction(*args), layers_np.PointNetSetAbstraction(*args)
+    _set_params(gpu.mlp_convs, gpu.mlp_bns, ref.mlp_convs, ref.mlp_bns, synth.mlp_params(3, args[4], seed=5), rng)
+    for l in range(2):  # inputs of layers 1 and 2 reach ~ 5000 * sqrt(16384) = 6.4e5 >> 65504
+        g = (ref.mlp_bns[l].weight * 5000.0).astype(np.float32)
+        ref.mlp_bns[l].weight = g
+        gpu.mlp_bns[l].weight = _cu(g)
+    gpu.to(DEV)
+    gx, gp = gpu(_cu(xyz), None, start_idx=_cu(start))
+    rx, rp = ref(xyz, None, start_idx=start)
+    assert np.isfinite(gp.cpu().numpy()).all()
+    np.testing.assert_array_equal(gx.cpu().numpy(), rx)
+    np.testing.assert_allclose(gp.cpu().numpy(), rp, **TOL)
+
+
 def test_ssg_stack_c2_full_size_vs_oracle():
     """BASELINE config 2 at full size (B=32, N=1024, the three SSG SetAbstraction layers of
     PointNet2_SSG_Clas, classify/pointnet2/pointnet2.py:11-16) against the oracle."""

@@ -51,8 +51,9 @@ def run(M, cin, cout, K, pool, want_y, act=True, reps=5):
 
 cfgs = [("K64->128 pool", 64, 128, 32, True, False), ("K128->128 y", 128, 128, 64, False, True)]
 masks = [int(m) for m in (sys.argv[1].split(",") if len(sys.argv) > 1 else "0,7,5,6,3".split(","))]
+tiles = [int(t) for t in (sys.argv[2].split(",") if len(sys.argv) > 2 else "1,8,28".split(","))]
 for name, cin, cout, K, pool, want_y in cfgs:
-    for tiles_per_cta in (1, 8, 28):
+    for tiles_per_cta in tiles:
         M = 128 * 148 * tiles_per_cta
         row = []
         for m in masks:
