@@ -52,6 +52,18 @@ int papc_last_cuda_error(void);
  * diagnostics for bench.py's gpu_launches -- memsets are not counted). */
 uint64_t papc_launch_count(void);
 
+/* Launch profiler (diagnostics; this is how bench.py times "the dominant kernel" live).  While
+ * enabled on the calling host thread, every kernel launch of papc_fps_f32, papc_ball_query_f32 and
+ * the grouped-MLP entry points is bracketed by two CUDA events recorded on the launching stream.
+ * papc_prof_get(i) synchronises record i's end event and returns the kernel's name, its problem
+ * size, the algorithmic FLOPs / bytes of that launch and the elapsed milliseconds.  Records
+ * accumulate (at most 8192) until papc_prof_reset().  Not for use inside a CUDA-graph capture. */
+int papc_prof_enable(int on);
+int papc_prof_reset(void);
+int papc_prof_count(void);
+int papc_prof_get(int i, char *name, int name_cap, int64_t *M, int32_t *cin, int32_t *cout,
+                  double *flops, double *bytes, float *ms);
+
 /* ----------------------------------------------------------------------------------------
  * A1  square_distance(src, dst)                                    layers.py:26-40
  *     src [B,N,3], dst [B,M,3] -> out [B,N,M];  out = (-2*dot + |src|^2) + |dst|^2 with

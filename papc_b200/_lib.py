@@ -55,6 +55,11 @@ _SIGNATURES = {
     "papc_abi_version": (_I, []),
     "papc_last_cuda_error": (_I, []),
     "papc_launch_count": (C.c_uint64, []),
+    "papc_prof_enable": (_I, [_I]),
+    "papc_prof_reset": (_I, []),
+    "papc_prof_count": (_I, []),
+    "papc_prof_get": (_I, [_I, C.c_char_p, _I, C.POINTER(C.c_int64), C.POINTER(C.c_int32),
+                           C.POINTER(C.c_int32), C.POINTER(_D), C.POINTER(_D), C.POINTER(_F)]),
     "papc_square_distance_f32": (_I, [_vp, _vp, _I, _I, _I, _vp, _vp]),
     "papc_gather_f32": (_I, [_vp, _vp, _I, _I, _I, _I, _vp, _vp]),
     "papc_fps_workspace_bytes": (_SZ, [_I, _I]),
@@ -111,6 +116,21 @@ def check(status: int, what: str):
         if status == -3:
             msg += f" (cudaError {l.papc_last_cuda_error()})"
         raise PapcError(f"{what}: {msg}")
+
+
+def prof_records():
+    """All records of the launch profiler as dicts (synchronises their events)."""
+    l = lib()
+    out = []
+    name = C.create_string_buffer(64)
+    M, ci, co = C.c_int64(), C.c_int32(), C.c_int32()
+    fl, by, ms = C.c_double(), C.c_double(), C.c_float()
+    for i in range(l.papc_prof_count()):
+        check(l.papc_prof_get(i, name, 64, C.byref(M), C.byref(ci), C.byref(co), C.byref(fl), C.byref(by),
+                              C.byref(ms)), "prof_get")
+        out.append({"name": name.value.decode(), "M": M.value, "cin": ci.value, "cout": co.value,
+                    "flops": fl.value, "bytes": by.value, "ms": ms.value})
+    return out
 
 
 def ptr(t):

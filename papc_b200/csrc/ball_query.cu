@@ -260,6 +260,8 @@ extern "C" int papc_ball_query_f32(const float *xyz, const float *new_xyz, int B
     if (!xyz || !new_xyz || !out_idx) return PAPC_EINVAL;
     if (B > 65535) return PAPC_EUNSUPPORTED;
     dim3 grid(ceil_div(S, kBqWarps), B);
+    ProfScope prof(as_stream(stream), "ball_query", (long long)B * S, N, nsample, 0.0,
+                   12.0 * B * (N + S) + (idx_bits / 8.0) * B * S * nsample);
     if (idx_bits == 64)
         ball_query_kernel<int64_t><<<grid, kBqWarps * 32, 0, as_stream(stream)>>>(
             xyz, new_xyz, N, S, radius2, nsample, reinterpret_cast<int64_t *>(out_idx), empty_count);

@@ -12,6 +12,8 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 OUT_DIR = os.path.join(os.path.dirname(HERE), "lib")
 OUT = os.path.join(OUT_DIR, "libpapc_b200.so")
 SOURCES = ["capi.cu", "fps.cu", "ball_query.cu", "sa_mlp.cu", "sa_mlp_tc.cu", "sa_mlp_tt.cu", "pillars.cu"]
+# per-file flags.  fps.cu: the distance is pinned as separately rounded multiplies and adds.
+EXTRA = {"fps.cu": ["-fmad=false"]}
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", HERE]
@@ -37,7 +39,7 @@ def build(force=False, verbose=False, ptxas_info=False):
         obj = os.path.join(obj_dir, s.replace(".cu", ".o"))
         objs.append(obj)
         if force or _stale(obj, src):
-            cmd = [NVCC, *FLAGS, "-c", src, "-o", obj]
+            cmd = [NVCC, *FLAGS, *EXTRA.get(s, []), "-c", src, "-o", obj]
             if ptxas_info:
                 cmd += ["-Xptxas", "-v"]
             if verbose:

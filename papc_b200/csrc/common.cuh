@@ -31,6 +31,31 @@ inline int cuda_fail(cudaError_t e) {
 
 inline cudaStream_t as_stream(papc_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// ---- launch profiler (papc_prof_* in the C ABI): when enabled on the calling host thread, the
+// instrumented kernel launches are bracketed by CUDA events recorded on the launching stream.
+struct ProfRec {
+    char name[56];
+    long long M;
+    int cin, cout;
+    double flops, bytes;  // algorithmic work of the launch (0 = not stated)
+    cudaEvent_t e0, e1;
+};
+struct Prof {
+    bool on = false;
+    int n = 0, cap = 0;
+    ProfRec *rec = nullptr;
+};
+extern thread_local Prof g_prof;
+struct ProfScope {
+    ProfRec *r = nullptr;
+    cudaStream_t st;
+    ProfScope(cudaStream_t stream, const char *name, long long M, int cin, int cout, double flops,
+              double bytes);
+    ~ProfScope();
+    ProfScope(const ProfScope &) = delete;
+    ProfScope &operator=(const ProfScope &) = delete;
+};
+
 template <typename T>
 __host__ __device__ constexpr T ceil_div(T a, T b) {
     return (a + b - 1) / b;

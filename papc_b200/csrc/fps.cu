@@ -1,29 +1,87 @@
 // fps.cu -- farthest point sampling (reference: layers.py:65-95) for sm_100a.
 //
-// One persistent CTA per cloud runs all `npoint` dependent iterations: the cloud's xyz and the
-// running min-distance live in REGISTERS (PPT points per thread, blocked so that lower threads
-// own lower indices), a shared-memory AoS copy of xyz serves the winner-coordinate broadcast,
-// and the per-iteration argmax is a redux.sync (integer max on the fp32 bit pattern -- all
-// distances are >= 0) + ballot inside each warp, then one double-buffered shared-memory
-// exchange across warps: ONE __syncthreads per iteration.
+// One persistent CTA per cloud runs all `npoint` dependent iterations; the kernel is LATENCY bound
+// (npoint serial argmax steps over a 12 KB cloud), so everything is arranged to shorten the
+// per-iteration dependency chain:
+//   * the cloud's xyz and the running min-distance live in REGISTERS (PPT points per thread, blocked
+//     so that lower threads own lower indices), two points per packed f32x2 instruction;
+//   * the per-thread / per-warp argmax works on the fp32 bit pattern as a signed integer (all
+//     distances are >= 0): integer max in the thread, redux.sync in the warp, ballot for the lowest
+//     lane holding the maximum;
+//   * that lane publishes (distance bits, index) of its candidate, so after the ONE __syncthreads
+//     of the iteration every thread reads all warps' candidates (broadcast LDS.128, two candidates
+//     each) and reduces them itself in a fixed tree (lower warp wins ties == lowest index): no
+//     second redux / ballot / shuffle round;
+//   * the cloud is also kept in shared memory as float4 so the next centroid is ONE LDS.128.
 //
-// Bit-exactness vs the oracle: d = (dx*dx + dy*dy) + dz*dz with separately rounded ops
-// (__fmul_rn/__fadd_rn are never contracted), running = min(running, d) (== the reference's
-// masked assignment for non-NaN data), argmax = lowest index among maxima (paddle.argmax).
+// Bit-exactness vs the oracle: d = (dx*dx + dy*dy) + dz*dz with separately rounded ops (packed
+// subtractions and squares, scalar add.rn sums -- checked in SASS: no FFMA in the loop;
+// x - c == x + (-c) exactly), running = min(running, d)
+// (== the reference's masked assignment for non-NaN data), argmax = lowest index among maxima
+// (paddle.argmax).
 #include "common.cuh"
+
+#include <stdlib.h>
 
 namespace papc {
 
 constexpr int kFpsRegMaxN = 8192;
+
+__device__ __forceinline__ uint64_t f2pack(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2unpack(uint64_t v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2add(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// explicit shared-window accesses on 32-bit addresses computed once: generic accesses to __shared__
+// objects make ptxas re-derive the window base (S2R SR_CgaCtaId, ~30 cycles) inside the hot loop
+__device__ __forceinline__ uint32_t fps_smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ float4 fps_lds128f(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr)
+                 : "memory");
+    return v;
+}
+__device__ __forceinline__ int4 fps_lds128i(uint32_t saddr) {
+    int4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr)
+                 : "memory");
+    return v;
+}
+__device__ __forceinline__ int2 fps_lds64i(uint32_t saddr) {
+    int2 v;
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fps_sts64i(uint32_t saddr, int a, int b) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(saddr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ uint64_t f2mul(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
 
 template <int THREADS, int PPT>
 __global__ void __launch_bounds__(THREADS)
 fps_reg_kernel(const float *__restrict__ xyz, int N, int npoint,
                const int64_t *__restrict__ start_idx, float init_dist,
                int64_t *__restrict__ out_idx, float *__restrict__ out_new_xyz) {
-    extern __shared__ float s_xyz[];  // [N*3] AoS
+    static_assert(PPT % 2 == 0, "points are processed in packed pairs");
+    extern __shared__ float4 s_xyz4[];  // [N] (x, y, z, 0): one LDS.128 fetches a centroid
     constexpr int NW = THREADS / 32;
-    __shared__ unsigned long long s_red[2][32];
+    constexpr int PP = PPT / 2;
+    constexpr int NWP = NW > 1 ? NW : 2;
+    __shared__ __align__(16) int2 s_red[2][NWP];  // per warp: (distance bits, point index)
 
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
@@ -31,75 +89,133 @@ fps_reg_kernel(const float *__restrict__ xyz, int N, int npoint,
     const int warp = tid >> 5;
     const float *cloud = xyz + (size_t)b * N * 3;
 
-    for (int i = tid; i < N * 3; i += THREADS) s_xyz[i] = cloud[i];
+    for (int i = tid; i < N; i += THREADS)
+        s_xyz4[i] = make_float4(cloud[i * 3 + 0], cloud[i * 3 + 1], cloud[i * 3 + 2], 0.f);
     __syncthreads();
 
-    float px[PPT], py[PPT], pz[PPT], pd[PPT];
+    uint64_t px[PP], py[PP], pz[PP];
+    float pd[PPT];
 #pragma unroll
-    for (int p = 0; p < PPT; ++p) {
-        const int j = tid * PPT + p;
-        if (j < N) {
-            px[p] = s_xyz[j * 3 + 0];
-            py[p] = s_xyz[j * 3 + 1];
-            pz[p] = s_xyz[j * 3 + 2];
-            pd[p] = init_dist;
-        } else {
-            px[p] = py[p] = pz[p] = 0.0f;
-            pd[p] = -1.0f;  // negative bit pattern: never the (signed) maximum
+    for (int q = 0; q < PP; ++q) {
+        float4 v[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int j = tid * PPT + 2 * q + h;
+            if (j < N) {
+                v[h] = s_xyz4[j];
+                pd[2 * q + h] = init_dist;
+            } else {
+                v[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+                pd[2 * q + h] = -1.0f;  // negative bit pattern: never the (signed) maximum
+            }
         }
+        px[q] = f2pack(v[0].x, v[1].x);
+        py[q] = f2pack(v[0].y, v[1].y);
+        pz[q] = f2pack(v[0].z, v[1].z);
     }
 
     int far = (int)start_idx[b];
     far = min(max(far, 0), N - 1);
     int64_t *out = out_idx + (size_t)b * npoint;
+    float *oxyz = out_new_xyz != nullptr ? out_new_xyz + (size_t)b * npoint * 3 : nullptr;
+    unsigned lt_mask;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
+    // window addresses laundered through a volatile shared-memory round trip: ptxas otherwise
+    // rematerialises them (an S2UR of SR_CgaCtaId at the head of the dependency chain) in every
+    // iteration instead of keeping two registers
+    __shared__ uint32_t s_addr[2];
+    if (tid == 0) {
+        s_addr[0] = fps_smem_u32(s_xyz4);
+        s_addr[1] = fps_smem_u32(&s_red[0][0]);
+    }
+    __syncthreads();
+    uint32_t xyz_sa, red_sa;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(xyz_sa) : "r"(fps_smem_u32(&s_addr[0])) : "memory");
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(red_sa) : "r"(fps_smem_u32(&s_addr[1])) : "memory");
 
     for (int it = 0; it < npoint; ++it) {
-        const float cx = s_xyz[far * 3 + 0];
-        const float cy = s_xyz[far * 3 + 1];
-        const float cz = s_xyz[far * 3 + 2];
+        const float4 c = fps_lds128f(xyz_sa + 16u * (uint32_t)far);
+        const uint32_t red_it = red_sa + (uint32_t)(it & 1) * (NWP * 8);
         if (tid == 0) {
             out[it] = far;
-            if (out_new_xyz != nullptr) {
-                float *o = out_new_xyz + ((size_t)b * npoint + it) * 3;
-                o[0] = cx;
-                o[1] = cy;
-                o[2] = cz;
+            if (oxyz != nullptr) {
+                oxyz[it * 3 + 0] = c.x;
+                oxyz[it * 3 + 1] = c.y;
+                oxyz[it * 3 + 2] = c.z;
             }
         }
-        int best = -2147483647 - 1;
-        int besti = 0;
+        if (it == npoint - 1) break;  // the reference's last argmax is discarded (:93 after :80)
+        const uint64_t ncx = f2pack(-c.x, -c.x), ncy = f2pack(-c.y, -c.y), ncz = f2pack(-c.z, -c.z);
+        int bits[PPT];
 #pragma unroll
-        for (int p = 0; p < PPT; ++p) {
-            const float dx = __fsub_rn(px[p], cx);
-            const float dy = __fsub_rn(py[p], cy);
-            const float dz = __fsub_rn(pz[p], cz);
-            const float d = sq3(dx, dy, dz);
+        for (int q = 0; q < PP; ++q) {
+            const uint64_t dx = f2add(px[q], ncx);
+            const uint64_t dy = f2add(py[q], ncy);
+            const uint64_t dz = f2add(pz[q], ncz);
+            // squares packed, sums as scalar add.rn.f32: ptxas contracts mul.rn.f32x2 + add.rn.f32x2
+            // into FFMA2 (even under -fmad=false) but never touches an explicit scalar add.rn
+            float xx0, xx1, yy0, yy1, zz0, zz1;
+            f2unpack(f2mul(dx, dx), xx0, xx1);
+            f2unpack(f2mul(dy, dy), yy0, yy1);
+            f2unpack(f2mul(dz, dz), zz0, zz1);
+            const float d0 = __fadd_rn(__fadd_rn(xx0, yy0), zz0);
+            const float d1 = __fadd_rn(__fadd_rn(xx1, yy1), zz1);
             // tid*PPT+p >= N keeps pd = -1 (d >= 0 is never smaller)
-            pd[p] = (d < pd[p]) ? d : pd[p];
-            const int bits = __float_as_int(pd[p]);
-            if (bits > best) {  // strict: first maximum wins inside the thread
-                best = bits;
-                besti = tid * PPT + p;
-            }
+            pd[2 * q] = fminf(pd[2 * q], d0);
+            pd[2 * q + 1] = fminf(pd[2 * q + 1], d1);
+            bits[2 * q] = __float_as_int(pd[2 * q]);
+            bits[2 * q + 1] = __float_as_int(pd[2 * q + 1]);
         }
-        // warp argmax: integer max, then the lowest lane holding it (lanes own ascending indices)
+        // thread maximum as a balanced tree (short dependency chain)
+        int tmax[PPT];
+#pragma unroll
+        for (int p = 0; p < PPT; ++p) tmax[p] = bits[p];
+#pragma unroll
+        for (int step = 1; step < PPT; step <<= 1)
+#pragma unroll
+            for (int p = 0; p + step < PPT; p += 2 * step) tmax[p] = max(tmax[p], tmax[p + step]);
+        const int best = tmax[0];
         const int wmax = __reduce_max_sync(0xffffffffu, best);
-        const unsigned ball = __ballot_sync(0xffffffffu, best == wmax);
-        const int src = __ffs(ball) - 1;
-        const int widx = __shfl_sync(0xffffffffu, besti, src);
+        // first point of this thread holding its maximum (independent of the redux result)
+        unsigned eq = 0u;
+#pragma unroll
+        for (int p = 0; p < PPT; ++p) eq |= (bits[p] == best ? 1u : 0u) << p;
+        const int bi = __ffs(eq) - 1;
+        const bool mine = best == wmax;
+        const unsigned ball = __ballot_sync(0xffffffffu, mine);
         if (NW == 1) {
-            far = widx;
+            const int src = __ffs(ball) - 1;  // lowest lane == lowest index
+            far = __shfl_sync(0xffffffffu, tid * PPT + bi, src);
         } else {
-            if (lane == 0)
-                s_red[it & 1][warp] =
-                    ((unsigned long long)(unsigned)wmax << 32) | (unsigned)widx;
+            if (mine && (ball & lt_mask) == 0u)  // lowest lane holding the warp maximum
+                fps_sts64i(red_it + 8u * warp, wmax, tid * PPT + bi);
             __syncthreads();
-            unsigned long long k = s_red[it & 1][lane < NW ? lane : 0];
-            const int kmax = (int)(unsigned)(k >> 32);
-            const int m2 = __reduce_max_sync(0xffffffffu, kmax);
-            const unsigned ball2 = __ballot_sync(0xffffffffu, (kmax == m2) && (lane < NW));
-            const int src2 = __ffs(ball2) - 1;  // lowest warp == lowest index
-            far = (int)__shfl_sync(0xffffffffu, (unsigned)(k & 0xffffffffu), src2);
+            if (NW <= 8) {
+                // every thread reduces all warps' candidates itself: broadcast LDS.128 (two
+                // candidates each), fixed tree, the lower warp (= lower indices) wins ties
+                int kb[NWP], ki[NWP];
+#pragma unroll
+                for (int w = 0; w < NWP; w += 2) {
+                    const int4 e = fps_lds128i(red_it + 8u * w);
+                    kb[w] = e.x; ki[w] = e.y; kb[w + 1] = e.z; ki[w + 1] = e.w;
+                }
+#pragma unroll
+                for (int step = 1; step < NW; step <<= 1)
+#pragma unroll
+                    for (int w = 0; w + step < NW; w += 2 * step) {
+                        const bool tb = kb[w + step] > kb[w];
+                        kb[w] = tb ? kb[w + step] : kb[w];
+                        ki[w] = tb ? ki[w + step] : ki[w];
+                    }
+                far = ki[0];
+            } else {
+                // many warps: lane w holds warp w's candidate, second redux round + shuffle
+                const int2 e = fps_lds64i(red_it + 8u * (lane < NW ? lane : 0));
+                const int kb = lane < NW ? e.x : (-2147483647 - 1);
+                const int m2 = __reduce_max_sync(0xffffffffu, kb);
+                const int src = __ffs(__ballot_sync(0xffffffffu, kb == m2)) - 1;  // lowest warp
+                far = __shfl_sync(0xffffffffu, e.y, src);
+            }
         }
     }
 }
@@ -178,11 +294,13 @@ template <int THREADS, int PPT>
 static int launch_fps_reg(const float *xyz, int B, int N, int npoint, const int64_t *start,
                           float init_dist, int64_t *out_idx, float *out_new_xyz,
                           cudaStream_t st) {
-    const size_t smem = (size_t)N * 3 * sizeof(float);
+    const size_t smem = (size_t)N * sizeof(float4);
     auto k = fps_reg_kernel<THREADS, PPT>;
     if (smem > 48 * 1024)
         PAPC_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)smem));
+    ProfScope prof(st, "fps_reg", (long long)B * N, npoint, 0, 0.0,
+                   12.0 * B * N + 8.0 * B * npoint + (out_new_xyz ? 12.0 * B * npoint : 0.0));
     k<<<B, THREADS, smem, st>>>(xyz, N, npoint, start, init_dist, out_idx, out_new_xyz);
     PAPC_LAUNCH_CHECK();
     return PAPC_OK;
@@ -204,15 +322,19 @@ extern "C" int papc_fps_f32(const float *xyz, int B, int N, int npoint,
     if (B == 0 || npoint == 0) return PAPC_OK;
     if (!xyz || !start_idx || !out_idx) return PAPC_EINVAL;
     cudaStream_t st = as_stream(stream);
-    if (N <= 32) return launch_fps_reg<32, 1>(xyz, B, N, npoint, start_idx, init_dist, out_idx, out_new_xyz, st);
-    if (N <= 64) return launch_fps_reg<64, 1>(xyz, B, N, npoint, start_idx, init_dist, out_idx, out_new_xyz, st);
-    if (N <= 128) return launch_fps_reg<128, 1>(xyz, B, N, npoint, start_idx, init_dist, out_idx, out_new_xyz, st);
-    if (N <= 256) return launch_fps_reg<256, 1>(xyz, B, N, npoint, start_idx, init_dist, out_idx, out_new_xyz, st);
-    if (N <= 512) return launch_fps_reg<256, 2>(xyz, B, N, npoint, start_idx, init_dist, out_idx, out_new_xyz, st);
-    if (N <= 1024) return launch_fps_reg<256, 4>(xyz, B, N, npoint, start_idx, init_dist, out_idx, out_new_xyz, st);
-    if (N <= 2048) return launch_fps_reg<512, 4>(xyz, B, N, npoint, start_idx, init_dist, out_idx, out_new_xyz, st);
-    if (N <= 4096) return launch_fps_reg<1024, 4>(xyz, B, N, npoint, start_idx, init_dist, out_idx, out_new_xyz, st);
-    if (N <= kFpsRegMaxN) return launch_fps_reg<1024, 8>(xyz, B, N, npoint, start_idx, init_dist, out_idx, out_new_xyz, st);
+    // threads x points-per-thread; PAPC_FPS_WIDE=1 selects the wider (more warps, fewer points per
+    // thread) variant for the mid sizes -- A/B switch for tuning, same results either way
+    static const bool wide = [] { const char *e = getenv("PAPC_FPS_WIDE"); return e && e[0] == '1'; }();
+#define FPS_GO(T, P) return launch_fps_reg<T, P>(xyz, B, N, npoint, start_idx, init_dist, out_idx, out_new_xyz, st)
+    if (N <= 64) FPS_GO(32, 2);
+    if (N <= 128) FPS_GO(32, 4);
+    if (N <= 256) { if (wide) FPS_GO(128, 2); FPS_GO(64, 4); }
+    if (N <= 512) { if (wide) FPS_GO(256, 2); FPS_GO(128, 4); }
+    if (N <= 1024) { if (wide) FPS_GO(256, 4); FPS_GO(128, 8); }
+    if (N <= 2048) { if (wide) FPS_GO(512, 4); FPS_GO(256, 8); }
+    if (N <= 4096) { if (wide) FPS_GO(1024, 4); FPS_GO(512, 8); }
+    if (N <= kFpsRegMaxN) FPS_GO(1024, 8);
+#undef FPS_GO
     const size_t need = papc_fps_workspace_bytes(B, N);
     if (!workspace || workspace_bytes < need) return PAPC_EWORKSPACE;
     fps_global_kernel<1024><<<B, 1024, 0, st>>>(xyz, N, npoint, start_idx, init_dist, out_idx,

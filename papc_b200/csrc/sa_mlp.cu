@@ -546,6 +546,9 @@ static long long grid_rows(long long M) {
 
 static int launch_layer(const LayerArgs &a, bool gather, cudaStream_t st) {
     const long long tiles_m = grid_rows(a.M);
+    ProfScope prof(st, gather ? "mlp_simt<gather>" : "mlp_simt<plain>", a.M, a.cin, a.cout,
+                   2.0 * (double)a.M * a.cin * a.cout,
+                   4.0 * (double)a.M * a.cin + (a.y ? 4.0 * (double)a.M * a.cout : 0.0));
     if (a.cout <= 64) {
         const long long grid = tiles_m * ceil_div(a.cout, 64);
         if (grid > 0x7fffffffLL) return PAPC_EUNSUPPORTED;
@@ -833,6 +836,7 @@ extern "C" int papc_sa_pool_finish_f32(const float *pool_max, const float *pool_
     if (B == 0) return PAPC_OK;
     if (!pool_max || !pool_min || !scale || !shift || !out) return PAPC_EINVAL;
     cudaStream_t st = as_stream(stream);
+    ProfScope prof(st, "pool_finish", (long long)B * S, 0, cout, 0.0, 12.0 * B * S * cout);
     if (out_layout == PAPC_OUT_BSC || S == 1) {  // [B,C,1] and [B,1,C] are the same bytes
         const size_t total = (size_t)B * S * cout;
         size_t blocks = (total + 255) / 256;

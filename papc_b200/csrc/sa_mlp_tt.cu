@@ -39,6 +39,7 @@
 #include "umma.cuh"
 
 #include <cuda_fp16.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <type_traits>
@@ -51,7 +52,21 @@ using namespace umma;
 constexpr int kTile = 128;                    // rows per tile == UMMA N
 constexpr int kHalfBytes = kTile * 128;       // one [128 rows][128 B] SWIZZLE_128B block
 constexpr int kXBytes = 2 * kHalfBytes;       // X chunk: hi block + lo block
-constexpr int kEpiWarps = 4;                  // one per TMEM lane quadrant (13 warps: 128 regs/thread)
+#ifndef PAPC_TT_EPI_WARPS
+#define PAPC_TT_EPI_WARPS 8
+#endif
+// Epilogue warps: warp w reads TMEM lane quadrant w % 4; with 8 warps the two warps of a quadrant
+// (same SM sub-partition) split the 128 accumulator columns (= rows of the tile) in halves, so the
+// latency-bound tcgen05.ld -> math -> store chains of two warps interleave on one scheduler.
+constexpr int kEpiWarps = PAPC_TT_EPI_WARPS;
+constexpr int kEpiHalves = kEpiWarps / 4;
+constexpr int kBlkPerHalf = 4 / kEpiHalves;   // 32-column accumulator blocks per epilogue warp per tile
+static_assert(kEpiWarps == 4 || kEpiWarps == 8, "epilogue warps: one or two per TMEM lane quadrant");
+#ifdef PAPC_TT_TRIAGE
+#define TT_DBG(a, bit) ((a).dbg & (bit))
+#else
+#define TT_DBG(a, bit) 0
+#endif
 #ifndef PAPC_TT_PROD_WARPS
 #define PAPC_TT_PROD_WARPS 8
 #endif
@@ -60,7 +75,7 @@ constexpr int kRPT = 128 * 8 / (kProdWarps * 32);  // rows per producer thread p
 constexpr int kRowStride = kTile / kRPT;       // rows rb + kRowStride * j
 constexpr int kProdThreads = kProdWarps * 32;
 constexpr int kMmaWarp = kEpiWarps + kProdWarps;  // highest warp id: wins issue arbitration
-constexpr int kThreads = (kEpiWarps + 1 + kProdWarps) * 32;  // 672 -> 80 registers / thread
+constexpr int kThreads = (kEpiWarps + 1 + kProdWarps) * 32;  // 544 -> at most 120 registers / thread
 constexpr int kMaxAct = 512;                  // reduction length with per-column scale / shift in smem
 constexpr int kMaxFold = 128;                 // SRC_POINTMLP: channels of the folded first layer
 static_assert(kRPT == 2 || kRPT == 4, "producer row mapping");
@@ -117,6 +132,10 @@ struct SmemLayout {
     static constexpr uint32_t bars = wst + 4 * 32 * 33 * 4;
     static constexpr uint32_t nbars = 2 * 6 + 2 + 2 + 1 + 4;
     static constexpr uint32_t misc = bars + nbars * 8;               // tmem slot, last-CTA flag
+    // hand-over slots between the two epilogue warps of a quadrant; they alias the W staging area,
+    // which is dead once w_ready has completed (no accumulator exists before that)
+    static constexpr uint32_t xpool = wst;                           // [2][128] float2: K = 128 max/min
+    static constexpr uint32_t xstat = xpool + 2 * kTile * 8;         // [128] double2: statistic sums
     static constexpr uint32_t ring = (misc + 16 + 1023) / 1024 * 1024;  // operand ring (1024-aligned)
 };
 template <int MODE, int PREC, int WMODE>
@@ -256,7 +275,7 @@ mlp_layer_tt_kernel(const TtArgs a) {
             mbar_init(acc_full + b, 1);
             mbar_init(acc_empty + b, kEpiWarps);
         }
-        mbar_init(w_ready, kEpiWarps);
+        mbar_init(w_ready, 4);
         for (int b = 0; b < 4; ++b) mbar_init(xyz_full + b, kProdWarps);
         fence_mbar_init();
     }
@@ -268,14 +287,15 @@ mlp_layer_tt_kernel(const TtArgs a) {
 
     if (warp < kEpiWarps) {
         // ================================ epilogue =========================================
-        const int quad = warp;            // TMEM lane quadrant this warp may access
+        const int quad = warp & 3;        // TMEM lane quadrant this warp may access (warp id % 4)
+        const int half = warp >> 2;       // which accumulator column blocks (rows of the tile) it owns
         const int c = quad * 32 + lane;   // channel inside this CTA's 128-channel tile == TMEM lane
         const int cg = n0 + c;
         const bool cvalid = cg < a.cout;
         const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
-        // ---- stage 32 W rows per warp into tensor memory (hi / lo split): coalesced row loads,
+        // ---- stage 32 W rows per quadrant into tensor memory (hi / lo split): coalesced row loads,
         //      transposed through shared memory so that thread = channel owns its row
-        if (WMODE == 0) {
+        if (WMODE == 0 && half == 0) {
             float *wst = s_wst + quad * 32 * 33;
             for (int kc = 0; kc < KC; ++kc) {       // one 32-column TMEM chunk = kEPC elements
                 uint32_t hi[32], lo[32];
@@ -326,6 +346,8 @@ mlp_layer_tt_kernel(const TtArgs a) {
         const uint64_t bias2 = pack2(bias, bias);
         const uint64_t wx2 = pack2(wx, wx), wy2 = pack2(wy, wy), wz2 = pack2(wz, wz);
         const int kshift = POOL ? (a.K == 32 ? 5 : a.K == 64 ? 6 : 7) : 0;  // K in {32, 64, 128}
+        const size_t ystride = (size_t)a.cout;
+        float2 *s_xpool = reinterpret_cast<float2 *>(smem + SmemLayout::xpool);
         double acc_s = 0.0, acc_q = 0.0;
         uint32_t tl = 0;
         for (long long tile = mi; tile < tiles_m; tile += gm, ++tl) {
@@ -338,21 +360,23 @@ mlp_layer_tt_kernel(const TtArgs a) {
             uint64_t s2 = 0ull, q2 = 0ull;     // packed (even rows, odd rows) running sums
             float mx = -INFINITY, mn = INFINITY;
 #pragma unroll 1
-            for (int blk = 0; blk < 4; ++blk) {      // 32 accumulator columns (= rows) at a time
+            for (int bi = 0; bi < kBlkPerHalf; ++bi) {  // 32 accumulator columns (= rows) at a time
+                const int blk = half * kBlkPerHalf + bi;
                 uint32_t r[32];
                 tmem_ld32_nowait(lane_base + kColAcc + buf * kTile + blk * 32, r);
                 tmem_wait_ld();
-                if (blk == 3) {
-                    // accumulator fully read: hand the buffer back to the MMA issuer
+                if (bi == kBlkPerHalf - 1) {
+                    // this warp's share of the accumulator is in registers: hand the buffer back
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(acc_empty + buf);
                 }
                 const uint32_t xs = smem_u32(smem) + SmemLayout::xyz + 16 * ((tl & 3) * kTile + blk * 32);
-                float *yrow = do_y ? a.y + ((size_t)m0 + blk * 32) * a.cout + cg : nullptr;
+                float *yp = a.y + ((size_t)m0 + blk * 32) * ystride + cg;   // dereferenced only if do_y
                 const int nr = nrows - blk * 32;  // valid rows of this block (may be <= 0)
-                auto body = [&](auto full_tag) {
+                auto body = [&](auto full_tag, auto store_tag) {
                     constexpr bool FULL = decltype(full_tag)::value;
+                    constexpr bool STORE = decltype(store_tag)::value;
 #pragma unroll
                     for (int i = 0; i < 32; i += 2) {
                         uint64_t v2 = add2(pack2u(r[i], r[i + 1]), bias2);
@@ -367,9 +391,9 @@ mlp_layer_tt_kernel(const TtArgs a) {
                         if (FULL) {
                             s2 = add2(s2, v2);
                             q2 = fma2(v2, v2, q2);
-                            if (do_y) {
-                                yrow[(size_t)i * a.cout] = va;
-                                yrow[(size_t)(i + 1) * a.cout] = vb;
+                            if (STORE) {
+                                yp[0] = va;
+                                yp[ystride] = vb;
                             }
                             if (POOL) {
                                 mx = fmaxf(fmaxf(mx, va), vb);
@@ -380,19 +404,25 @@ mlp_layer_tt_kernel(const TtArgs a) {
                             const uint64_t m2 = pack2(rva ? va : 0.f, rvb ? vb : 0.f);
                             s2 = add2(s2, m2);
                             q2 = fma2(m2, m2, q2);
-                            if (do_y && rva) yrow[(size_t)i * a.cout] = va;
-                            if (do_y && rvb) yrow[(size_t)(i + 1) * a.cout] = vb;
+                            if (STORE && rva) yp[0] = va;
+                            if (STORE && rvb) yp[ystride] = vb;
                             if (POOL) {
                                 if (rva) { mx = fmaxf(mx, va); mn = fminf(mn, va); }
                                 if (rvb) { mx = fmaxf(mx, vb); mn = fminf(mn, vb); }
                             }
                         }
+                        if (STORE) yp += 2 * ystride;
                     }
                 };
-                if (a.dbg & 4) {
+                if (TT_DBG(a, 4)) {
                     s2 = pack2u(r[0], r[31]);
-                } else if (nr >= 32) body(std::true_type{});
-                else body(std::false_type{});
+                } else if (nr >= 32) {
+                    if (do_y) body(std::true_type{}, std::true_type{});
+                    else body(std::true_type{}, std::false_type{});
+                } else {
+                    if (do_y) body(std::false_type{}, std::true_type{});
+                    else body(std::false_type{}, std::false_type{});
+                }
                 // pooled groups of K rows end at multiples of K (K in {32, 64, 128})
                 if (POOL && ((blk + 1) * 32) % a.K == 0 && kshift != 7) {
                     if (do_pool && nr > 0) {
@@ -404,10 +434,23 @@ mlp_layer_tt_kernel(const TtArgs a) {
                     mn = INFINITY;
                 }
             }
-            if (POOL && kshift == 7 && do_pool) {  // K = 128: the tile is one group
-                const long long g = m0 >> 7;
-                a.pool_max[g * a.cout + cg] = mx;
-                a.pool_min[g * a.cout + cg] = mn;
+            if (POOL && kshift == 7) {  // K = 128: the tile is one group
+                if (kEpiHalves == 2) {
+                    // the upper half hands its extrema to the lower half (double buffered: the next
+                    // hand-over into this slot happens two named barriers later)
+                    if (half == 1) s_xpool[buf * kTile + c] = make_float2(mx, mn);
+                    named_bar_sync(2 + quad, 64);
+                    if (half == 0) {
+                        const float2 o = s_xpool[buf * kTile + c];
+                        mx = fmaxf(mx, o.x);
+                        mn = fminf(mn, o.y);
+                    }
+                }
+                if (do_pool && half == 0) {
+                    const long long g = m0 >> 7;
+                    a.pool_max[g * a.cout + cg] = mx;
+                    a.pool_min[g * a.cout + cg] = mn;
+                }
             }
             float sa, sb, qa, qb;
             unpack2(s2, sa, sb);
@@ -415,7 +458,17 @@ mlp_layer_tt_kernel(const TtArgs a) {
             acc_s += (double)sa + (double)sb;
             acc_q += (double)qa + (double)qb;
         }
-        if (a.stats_partial != nullptr && cvalid) {
+        if (kEpiHalves == 2) {  // fold the two halves' statistics (fixed order -> deterministic)
+            double2 *s_xstat = reinterpret_cast<double2 *>(smem + SmemLayout::xstat);
+            if (half == 1) s_xstat[c] = make_double2(acc_s, acc_q);
+            named_bar_sync(6 + quad, 64);
+            if (half == 0) {
+                const double2 o = s_xstat[c];
+                acc_s += o.x;
+                acc_q += o.y;
+            }
+        }
+        if (a.stats_partial != nullptr && cvalid && half == 0) {
             // one partial row per CTA (fixed order across launches -> deterministic)
             a.stats_partial[((long long)mi * 2 + 0) * a.cout + cg] = acc_s;
             a.stats_partial[((long long)mi * 2 + 1) * a.cout + cg] = acc_q;
@@ -445,7 +498,7 @@ mlp_layer_tt_kernel(const TtArgs a) {
                 const uint32_t s = it % kStages;
                 mbar_wait(x_full + s, (it / kStages) & 1);
                 tc_fence_after();
-                const int nks = (a.dbg & 2) ? 0 : min(P::kEPC, kpad - c * P::kEPC) / P::kMmaK;  // 1..4 K steps
+                const int nks = TT_DBG(a, 2) ? 0 : min(P::kEPC, kpad - c * P::kEPC) / P::kMmaK;  // 1..4 K steps
                 const uint32_t x_hi = ring_base + s * kStageBytes;
                 // descriptors of K step 0; one K step = 32 bytes of the swizzle row = +2 in the
                 // (address >> 4) field, = 8 tensor-memory columns
@@ -506,6 +559,7 @@ mlp_layer_tt_kernel(const TtArgs a) {
 
         // ---- per-row geometry pipeline (SRC_GATHER / SRC_POINTMLP)
         long long src[kRPT] = {};          // b*N + n of the rows of the tile being issued
+        long long srcD[kRPT] = {};         // ... times D: element offset of the feature row
         int grp[kRPT] = {};
         int idx_pf[kRPT] = {};             // prefetched neighbour indices of a later tile
         long long bN_pf[kRPT] = {};
@@ -554,24 +608,37 @@ mlp_layer_tt_kernel(const TtArgs a) {
                    4 * (q * kTile + rb + kRowStride * (u & (kRPT - 1)));
         };
         auto issue = [&](long long tile, int c, int rs) {  // chunk (tile, c) -> raw stage rs
-            if (a.dbg & 16) return;                          // triage: no global loads
+            if (TT_DBG(a, 16)) return;                          // triage: no global loads
             const long long m0 = tile * kTile;
             const int k0 = c * P::kEPC + u * P::kEPU;
             if (MODE == SRC_PLAIN) {
+                const bool ok = k0 < a.cin;
+                if (m0 + kTile <= a.M) {
+                    // full tile: one 64-bit multiply, the rows are a constant stride apart
+                    const float *p = ok ? a.x + ((m0 + rb) * a.cin + k0) : a.x;
+                    const long long rstep = ok ? (long long)kRowStride * a.cin : 0;
 #pragma unroll
-                for (int j = 0; j < kRPT; ++j) {
-                    long long row = m0 + rb + kRowStride * j;
-                    row = row < a.M ? row : a.M - 1;
-                    const bool ok = k0 < a.cin;
-                    const float *p = ok ? a.x + row * a.cin + k0 : a.x;
+                    for (int j = 0; j < kRPT; ++j) {
 #pragma unroll
-                    for (int h = 0; h < NV; ++h) cp_async16(raw_slot(rs, j * NV + h), p + (ok ? 4 * h : 0), ok);
+                        for (int h = 0; h < NV; ++h) cp_async16(raw_slot(rs, j * NV + h), p + (ok ? 4 * h : 0), ok);
+                        p += rstep;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < kRPT; ++j) {
+                        long long row = m0 + rb + kRowStride * j;
+                        row = row < a.M ? row : a.M - 1;
+                        const float *p = ok ? a.x + row * a.cin + k0 : a.x;
+#pragma unroll
+                        for (int h = 0; h < NV; ++h) cp_async16(raw_slot(rs, j * NV + h), p + (ok ? 4 * h : 0), ok);
+                    }
                 }
             } else if (MODE == SRC_GATHER) {
                 if (c == 0) {
 #pragma unroll
                     for (int j = 0; j < kRPT; ++j) {
                         src[j] = bN_pf[j] + min(max(idx_pf[j], 0), a.N - 1);
+                        srcD[j] = src[j] * a.D;
                         grp[j] = grp_pf[j];
                     }
                     fetch_idx(tile + gm < tiles_m ? tile + gm : tile);
@@ -593,7 +660,7 @@ mlp_layer_tt_kernel(const TtArgs a) {
 #pragma unroll
                 for (int j = 0; j < kRPT; ++j) {
                     const bool ok = k0 < a.D;
-                    const float *p = ok ? a.feats + src[j] * a.D + k0 : a.feats;
+                    const float *p = ok ? a.feats + (srcD[j] + k0) : a.feats;
 #pragma unroll
                     for (int h = 0; h < NV; ++h) cp_async16(raw_slot(rs, j * NV + h), p + (ok ? 4 * h : 0), ok);
                 }
@@ -613,9 +680,9 @@ mlp_layer_tt_kernel(const TtArgs a) {
                 for (int j = 0; j < kRPT; ++j)
 #pragma unroll
                     for (int h = 0; h < NV; ++h)
-                        v[j][h] = (a.dbg & 16) ? make_float4(1.f, 2.f, 3.f, (float)c)
+                        v[j][h] = TT_DBG(a, 16) ? make_float4(1.f, 2.f, 3.f, (float)c)
                                                : lds128f(raw_slot(rs, j * NV + h));
-                if (MODE == SRC_GATHER && c == 0 && u < kRPT && !(a.dbg & 16)) {
+                if (MODE == SRC_GATHER && c == 0 && u < kRPT && !TT_DBG(a, 16)) {
                     e0 = lds32f(raw_xyz(rs, 0)); e1 = lds32f(raw_xyz(rs, 1)); e2 = lds32f(raw_xyz(rs, 2));
                     if (a.new_xyz != nullptr) {
                         e0 = __fsub_rn(e0, lds32f(raw_xyz(rs, 3)));
@@ -708,7 +775,7 @@ mlp_layer_tt_kernel(const TtArgs a) {
             if (++ci == KC) { ci = 0; t += gm; }
         };
         const long long tile0 = mi;
-        if (a.dbg & 1) {
+        if (TT_DBG(a, 1)) {
             // triage: ring protocol only
             for (long long t = tile0; t < tiles_m; t += gm)
                 for (int cq = 0; cq < KC; ++cq) {
@@ -947,6 +1014,15 @@ static int launch_inst(const TtArgs &a, int grid, cudaStream_t st) {
                                            (int)Cfg<MODE, PREC, WMODE>::bytes));
         configured = true;
     }
+    char name[56];
+    snprintf(name, sizeof(name), "mlp_tt<%s,%s,%s%s>", MODE == SRC_PLAIN ? "plain" : MODE == SRC_GATHER ? "gather" : "pointmlp",
+             PREC == PREC_F16 ? "f16x3" : "tf32x3", WMODE ? "Wstream" : "Wtmem", POOL ? ",pool" : "");
+    // algorithmic bytes: the activation rows read (gathered rows count once per row read), the
+    // pre-BN output written (if any) and the pooled extrema
+    const double in_b = MODE == SRC_POINTMLP ? 16.0 * a.M : 4.0 * (double)a.M * a.cin;
+    const double out_b = (a.y ? 4.0 * (double)a.M * a.cout : 0.0) +
+                         (POOL ? 8.0 * (double)(a.M / (a.K > 0 ? a.K : 1)) * a.cout : 0.0);
+    ProfScope prof(st, name, a.M, a.cin, a.cout, 2.0 * (double)a.M * a.cin * a.cout, in_b + out_b);
     k<<<grid, kThreads, Cfg<MODE, PREC, WMODE>::bytes, st>>>(a);
     PAPC_LAUNCH_CHECK();
     return PAPC_OK;
@@ -1013,6 +1089,7 @@ int moment_blocks(long long M) {
 
 int launch_moments(const MomentArgs &a, cudaStream_t st) {
     const int blocks = a.running_mean != nullptr ? 1 : moment_blocks(a.M);
+    ProfScope prof(st, "point_moments", a.M, 3, a.c0, 0.0, 16.0 * (double)a.M);
     point_moments_kernel<<<blocks, kMomThreads, 0, st>>>(a);
     PAPC_LAUNCH_CHECK();
     return PAPC_OK;

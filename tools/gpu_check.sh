@@ -39,3 +39,15 @@ if [[ "$what" == *triage* ]]; then
   done
   cat gpurun_out/triage.log
 fi
+if [[ "$what" == *full* ]]; then
+  # one --set full capture of every grouped-MLP layer kernel of ONE warm step (the second pass)
+  timeout 1200 ncu --set full --clock-control none --import-source on \
+     -k regex:"mlp_layer_tt|fps_reg" -s ${NCU_SKIP:-10} -c ${NCU_COUNT:-10} -f -o gpurun_out/step_full python tools/prof_step.py 2 > gpurun_out/ncu_full.log 2>&1
+  echo "ncu full exit $?"; tail -3 gpurun_out/ncu_full.log | cut -c1-300
+fi
+if [[ "$what" == *prims* ]]; then
+  timeout 300 python tools/prof_prims.py > gpurun_out/prims.log 2>&1
+  echo "--- PAPC_FPS_WIDE=1" >> gpurun_out/prims.log
+  PAPC_FPS_WIDE=1 timeout 300 python tools/prof_prims.py >> gpurun_out/prims.log 2>&1
+  cat gpurun_out/prims.log
+fi
