@@ -26,6 +26,7 @@
 namespace papc {
 
 constexpr int kFpsRegMaxN = 8192;
+constexpr int kFpsOutCap = 4096;  // picks parked in shared memory between flushes to global
 
 __device__ __forceinline__ uint64_t f2pack(float lo, float hi) {
     uint64_t r;
@@ -78,6 +79,7 @@ fps_reg_kernel(const float *__restrict__ xyz, int N, int npoint,
                int64_t *__restrict__ out_idx, float *__restrict__ out_new_xyz) {
     static_assert(PPT % 2 == 0, "points are processed in packed pairs");
     extern __shared__ float4 s_xyz4[];  // [N] (x, y, z, 0): one LDS.128 fetches a centroid
+    int *s_out = reinterpret_cast<int *>(s_xyz4 + N);  // [min(npoint, kFpsOutCap)] picks awaiting the flush
     constexpr int NW = THREADS / 32;
     constexpr int PP = PPT / 2;
     constexpr int NWP = NW > 1 ? NW : 2;
@@ -116,35 +118,47 @@ fps_reg_kernel(const float *__restrict__ xyz, int N, int npoint,
 
     int far = (int)start_idx[b];
     far = min(max(far, 0), N - 1);
-    int64_t *out = out_idx + (size_t)b * npoint;
-    float *oxyz = out_new_xyz != nullptr ? out_new_xyz + (size_t)b * npoint * 3 : nullptr;
     unsigned lt_mask;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
     // window addresses laundered through a volatile shared-memory round trip: ptxas otherwise
     // rematerialises them (an S2UR of SR_CgaCtaId at the head of the dependency chain) in every
     // iteration instead of keeping two registers
-    __shared__ uint32_t s_addr[2];
+    __shared__ uint32_t s_addr[3];
     if (tid == 0) {
         s_addr[0] = fps_smem_u32(s_xyz4);
         s_addr[1] = fps_smem_u32(&s_red[0][0]);
+        s_addr[2] = fps_smem_u32(s_out);
     }
     __syncthreads();
-    uint32_t xyz_sa, red_sa;
+    uint32_t xyz_sa, red_sa, out_sa;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(out_sa) : "r"(fps_smem_u32(&s_addr[2])) : "memory");
     asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(xyz_sa) : "r"(fps_smem_u32(&s_addr[0])) : "memory");
     asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(red_sa) : "r"(fps_smem_u32(&s_addr[1])) : "memory");
+
+    int64_t *out = out_idx + (size_t)b * npoint;
+    float *oxyz = out_new_xyz != nullptr ? out_new_xyz + (size_t)b * npoint * 3 : nullptr;
+    auto flush = [&](int base, int n) {  // picks [base, base+n) -> global (all threads)
+        __syncthreads();
+        for (int i = tid; i < n; i += THREADS) out[base + i] = s_out[i];
+        if (oxyz != nullptr)
+            for (int i = tid; i < n * 3; i += THREADS) {
+                const int pt = i / 3, d = i - pt * 3;
+                const float4 v = s_xyz4[s_out[pt]];
+                oxyz[(size_t)base * 3 + i] = d == 0 ? v.x : (d == 1 ? v.y : v.z);
+            }
+        __syncthreads();
+    };
 
     for (int it = 0; it < npoint; ++it) {
         const float4 c = fps_lds128f(xyz_sa + 16u * (uint32_t)far);
         const uint32_t red_it = red_sa + (uint32_t)(it & 1) * (NWP * 8);
-        if (tid == 0) {
-            out[it] = far;
-            if (oxyz != nullptr) {
-                oxyz[it * 3 + 0] = c.x;
-                oxyz[it * 3 + 1] = c.y;
-                oxyz[it * 3 + 2] = c.z;
-            }
-        }
+        // the pick is parked in shared memory (one predicated STS): global stores with their 64-bit
+        // address arithmetic would sit on warp 0's path to the barrier in every iteration
+        if (tid == 0)
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(out_sa + 4u * (uint32_t)(it & (kFpsOutCap - 1))), "r"(far)
+                         : "memory");
         if (it == npoint - 1) break;  // the reference's last argmax is discarded (:93 after :80)
+        if ((it & (kFpsOutCap - 1)) == kFpsOutCap - 1) flush(it + 1 - kFpsOutCap, kFpsOutCap);  // rare
         const uint64_t ncx = f2pack(-c.x, -c.x), ncy = f2pack(-c.y, -c.y), ncz = f2pack(-c.z, -c.z);
         int bits[PPT];
 #pragma unroll
@@ -218,6 +232,7 @@ fps_reg_kernel(const float *__restrict__ xyz, int N, int npoint,
             }
         }
     }
+    flush((npoint - 1) & ~(kFpsOutCap - 1), ((npoint - 1) & (kFpsOutCap - 1)) + 1);
 }
 
 // Generic path for N > 8192: running distances in global memory (L2-resident), xyz read through
@@ -294,7 +309,7 @@ template <int THREADS, int PPT>
 static int launch_fps_reg(const float *xyz, int B, int N, int npoint, const int64_t *start,
                           float init_dist, int64_t *out_idx, float *out_new_xyz,
                           cudaStream_t st) {
-    const size_t smem = (size_t)N * sizeof(float4);
+    const size_t smem = (size_t)N * sizeof(float4) + (size_t)(npoint < kFpsOutCap ? npoint : kFpsOutCap) * sizeof(int);
     auto k = fps_reg_kernel<THREADS, PPT>;
     if (smem > 48 * 1024)
         PAPC_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,

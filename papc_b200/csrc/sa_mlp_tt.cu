@@ -128,14 +128,12 @@ struct SmemLayout {
     static constexpr uint32_t scale = xyz + 4 * kTile * 16;          // [512] float
     static constexpr uint32_t shift = scale + kMaxAct * 4;           // [512] float
     static constexpr uint32_t fold = shift + kMaxAct * 4;            // [128] float4 (SRC_POINTMLP)
-    static constexpr uint32_t wst = fold + kMaxFold * 16;            // [4 warps][32][33] float
-    static constexpr uint32_t bars = wst + 4 * 32 * 33 * 4;
+    // hand-over slots between the two epilogue warps of a quadrant
+    static constexpr uint32_t xpool = fold + kMaxFold * 16;          // [2][128] float2: K = 128 max/min
+    static constexpr uint32_t xstat = xpool + 2 * kTile * 8;         // [128] double2: statistic sums
+    static constexpr uint32_t bars = xstat + kTile * 16;
     static constexpr uint32_t nbars = 2 * 6 + 2 + 2 + 1 + 4;
     static constexpr uint32_t misc = bars + nbars * 8;               // tmem slot, last-CTA flag
-    // hand-over slots between the two epilogue warps of a quadrant; they alias the W staging area,
-    // which is dead once w_ready has completed (no accumulator exists before that)
-    static constexpr uint32_t xpool = wst;                           // [2][128] float2: K = 128 max/min
-    static constexpr uint32_t xstat = xpool + 2 * kTile * 8;         // [128] double2: statistic sums
     static constexpr uint32_t ring = (misc + 16 + 1023) / 1024 * 1024;  // operand ring (1024-aligned)
 };
 template <int MODE, int PREC, int WMODE>
@@ -243,7 +241,6 @@ mlp_layer_tt_kernel(const TtArgs a) {
     float *s_scale = reinterpret_cast<float *>(smem + SmemLayout::scale);
     float *s_shift = reinterpret_cast<float *>(smem + SmemLayout::shift);
     float4 *s_fold = reinterpret_cast<float4 *>(smem + SmemLayout::fold);
-    float *s_wst = reinterpret_cast<float *>(smem + SmemLayout::wst);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SmemLayout::bars);
     uint64_t *x_full = bars;
     uint64_t *x_empty = bars + 6;
@@ -275,7 +272,7 @@ mlp_layer_tt_kernel(const TtArgs a) {
             mbar_init(acc_full + b, 1);
             mbar_init(acc_empty + b, kEpiWarps);
         }
-        mbar_init(w_ready, 4);
+        mbar_init(w_ready, kEpiWarps);
         for (int b = 0; b < 4; ++b) mbar_init(xyz_full + b, kProdWarps);
         fence_mbar_init();
     }
@@ -293,38 +290,65 @@ mlp_layer_tt_kernel(const TtArgs a) {
         const int cg = n0 + c;
         const bool cvalid = cg < a.cout;
         const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
-        // ---- stage 32 W rows per quadrant into tensor memory (hi / lo split): coalesced row loads,
-        //      transposed through shared memory so that thread = channel owns its row
-        if (WMODE == 0 && half == 0) {
-            float *wst = s_wst + quad * 32 * 33;
-            for (int kc = 0; kc < KC; ++kc) {       // one 32-column TMEM chunk = kEPC elements
+        // ---- stage W into tensor memory (hi / lo split).  Thread = channel reads ITS OWN row
+        //      W[cg, kc*kEPC ...] straight into the registers tcgen05.st takes (16-byte loads when the
+        //      row is 16-byte aligned): every load of a chunk is independent, so the whole chunk is in
+        //      flight at once -- no shared-memory transposition, no per-row round trips.  The two
+        //      epilogue warps of a quadrant take alternate chunks.
+        if (WMODE == 0) {
+            const float *wrow = a.W + (size_t)(cvalid ? cg : 0) * a.wld + a.wk0;
+            const bool vec = ((a.wld | a.wk0) & 3) == 0 && (reinterpret_cast<uintptr_t>(a.W) & 15u) == 0 &&
+                             (a.w_colscale == nullptr || (reinterpret_cast<uintptr_t>(a.w_colscale) & 15u) == 0);
+            for (int kc = half; kc < KC; kc += kEpiHalves) {  // one 32-column TMEM chunk = kEPC elements
                 uint32_t hi[32], lo[32];
 #pragma unroll
                 for (int pass = 0; pass < P::kEPC / 32; ++pass) {
-                    const int k = kc * P::kEPC + pass * 32 + lane;
-                    const float cs = (a.w_colscale != nullptr && k < a.cin) ? __ldg(a.w_colscale + k) : 1.f;
+                    const int k0 = kc * P::kEPC + pass * 32;
+                    float v[32];
+                    if (vec && k0 + 32 <= a.cin) {
 #pragma unroll
-                    for (int rr = 0; rr < 32; ++rr) {
-                        const int row = n0 + quad * 32 + rr;
-                        wst[rr * 33 + lane] = (row < a.cout && k < a.cin)
-                                                  ? __ldg(a.W + (size_t)row * a.wld + a.wk0 + k) * cs : 0.f;
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 t = __ldg(reinterpret_cast<const float4 *>(wrow + k0) + q);
+                            v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+                        }
+                        if (a.w_colscale != nullptr) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const float4 t = __ldg(reinterpret_cast<const float4 *>(a.w_colscale + k0) + q);
+                                v[4 * q] *= t.x; v[4 * q + 1] *= t.y; v[4 * q + 2] *= t.z; v[4 * q + 3] *= t.w;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const int k = k0 + i;
+                            v[i] = k < a.cin ? __ldg(wrow + k) : 0.f;
+                        }
+                        if (a.w_colscale != nullptr) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                const int k = k0 + i;
+                                if (k < a.cin) v[i] *= __ldg(a.w_colscale + k);
+                            }
+                        }
                     }
-                    __syncwarp();
+                    if (!cvalid) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = 0.f;
+                    }
                     if (PREC == PREC_TF32) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
                             float h, l;
-                            split_tf32(wst[lane * 33 + i], h, l);
+                            split_tf32(v[i], h, l);
                             hi[i] = __float_as_uint(h);
                             lo[i] = __float_as_uint(l);
                         }
                     } else {
 #pragma unroll
                         for (int i = 0; i < 32; i += 2)
-                            split_f16x2(wst[lane * 33 + i], wst[lane * 33 + i + 1], hi[(pass * 16 + i / 2) & 31],
-                                        lo[(pass * 16 + i / 2) & 31]);
+                            split_f16x2(v[i], v[i + 1], hi[(pass * 16 + i / 2) & 31], lo[(pass * 16 + i / 2) & 31]);
                     }
-                    __syncwarp();
                 }
                 tmem_st32(lane_base + kColWHi + kc * 32, hi);
                 tmem_st32(lane_base + kColWLo + kc * 32, lo);
