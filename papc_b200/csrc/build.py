@@ -17,6 +17,7 @@ EXTRA = {"fps.cu": ["-fmad=false"]}
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", HERE]
+FLAGS += os.environ.get("PAPC_NVCC_EXTRA", "").split()  # tuning experiments, e.g. -DPAPC_TT_PROD_WARPS=16
 
 
 def _stale(obj, src):

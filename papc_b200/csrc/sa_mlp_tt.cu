@@ -64,8 +64,14 @@ constexpr int kBlkPerHalf = 4 / kEpiHalves;   // 32-column accumulator blocks pe
 static_assert(kEpiWarps == 4 || kEpiWarps == 8, "epilogue warps: one or two per TMEM lane quadrant");
 #ifdef PAPC_TT_TRIAGE
 #define TT_DBG(a, bit) ((a).dbg & (bit))
+// phase stamps of CTA 0 / 1 (slot = blockIdx) for the timeline printed by launch() under PAPC_TT_CLK=1
+#define TT_CLK(a, e)                                                                       \
+    do {                                                                                   \
+        if ((a).clk != nullptr && blockIdx.x < 2) (a).clk[blockIdx.x * 16 + (e)] = clock64(); \
+    } while (0)
 #else
 #define TT_DBG(a, bit) 0
+#define TT_CLK(a, e) do { } while (0)
 #endif
 #ifndef PAPC_TT_PROD_WARPS
 #define PAPC_TT_PROD_WARPS 8
@@ -169,15 +175,26 @@ struct RowGeom {
     int g;         // group index b*S + s
     int k;         // position inside the group
 };
-__device__ __forceinline__ RowGeom row_geom(long long row, int K, int S, int N) {
+__device__ __forceinline__ uint32_t fastdiv(uint32_t x, uint32_t mul, uint32_t shr) {
+    return mul == 0u ? x : (__umulhi(x, mul) >> shr);
+}
+template <typename A>
+__device__ __forceinline__ RowGeom row_geom(long long row, const A &a) {
     RowGeom r;
-    const long long gg = row / K;
-    r.k = (int)(row - gg * K);
-    r.g = (int)gg;
-    r.bN = (gg / S) * (long long)N;
+    if (a.fastgeom) {
+        const uint32_t rw = (uint32_t)row;
+        const uint32_t gg = fastdiv(rw, a.kmul, a.kshr);
+        r.k = (int)(rw - gg * (uint32_t)a.K);
+        r.g = (int)gg;
+        r.bN = (long long)fastdiv(gg, a.smul, a.sshr) * a.N;
+    } else {
+        const long long gg = row / a.K;
+        r.k = (int)(row - gg * a.K);
+        r.g = (int)gg;
+        r.bN = (gg / a.S) * (long long)a.N;
+    }
     return r;
 }
-
 
 // ------------------------------------------------------------------ streamed-W image (WMODE 1)
 // img: [nt][KC][hi | lo][128 rows][128 B] in the SWIZZLE_128B layout, so that a CTA stages the
@@ -254,6 +271,14 @@ mlp_layer_tt_kernel(const TtArgs a) {
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int lane = tid & 31;
+    if (tid == 0) TT_CLK(a, 0);
+#ifdef PAPC_TT_TRIAGE
+    unsigned long long gt0 = 0;
+    if (tid == 0 && a.clk != nullptr) {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0));
+        atomicMin(a.clk + 44, gt0);
+    }
+#endif
     const int nt = ceil_div(a.cout, kTile);
     const int tile_n = blockIdx.x % nt;
     const int mi = blockIdx.x / nt;
@@ -281,6 +306,7 @@ mlp_layer_tt_kernel(const TtArgs a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (tid == 0) TT_CLK(a, 1);
 
     if (warp < kEpiWarps) {
         // ================================ epilogue =========================================
@@ -358,6 +384,7 @@ mlp_layer_tt_kernel(const TtArgs a) {
             __syncwarp();
             if (lane == 0) mbar_arrive(w_ready);
         }
+        if (tid == 0) TT_CLK(a, 2);
         const float bias = (a.bias != nullptr && cvalid) ? a.bias[cg] : 0.f;
         float wx = 0.f, wy = 0.f, wz = 0.f;
         const bool has_xyz = (MODE == SRC_GATHER) && a.wxyz >= 0;
@@ -381,6 +408,8 @@ mlp_layer_tt_kernel(const TtArgs a) {
             if (MODE == SRC_GATHER) mbar_wait(xyz_full + (tl & 3), (tl >> 2) & 1);
             mbar_wait(acc_full + buf, (tl >> 1) & 1);
             tc_fence_after();
+            if (tid == 0 && tl == 0) TT_CLK(a, 5);
+            if (tid == 0 && tl == 1) TT_CLK(a, 11);
             uint64_t s2 = 0ull, q2 = 0ull;     // packed (even rows, odd rows) running sums
             float mx = -INFINITY, mn = INFINITY;
 #pragma unroll 1
@@ -482,6 +511,7 @@ mlp_layer_tt_kernel(const TtArgs a) {
             acc_s += (double)sa + (double)sb;
             acc_q += (double)qa + (double)qb;
         }
+        if (tid == 0) TT_CLK(a, 6);
         if (kEpiHalves == 2) {  // fold the two halves' statistics (fixed order -> deterministic)
             double2 *s_xstat = reinterpret_cast<double2 *>(smem + SmemLayout::xstat);
             if (half == 1) s_xstat[c] = make_double2(acc_s, acc_q);
@@ -560,6 +590,7 @@ mlp_layer_tt_kernel(const TtArgs a) {
                     }
                     mma_commit(x_empty + s);                       // chunk reusable once these MMAs have read it
                     if (c == KC - 1) mma_commit(acc_full + buf);   // accumulator complete
+                    if (it == 0) TT_CLK(a, 4);
                 }
                 __syncwarp();
             }
@@ -588,35 +619,47 @@ mlp_layer_tt_kernel(const TtArgs a) {
         int idx_pf[kRPT] = {};             // prefetched neighbour indices of a later tile
         long long bN_pf[kRPT] = {};
         int grp_pf[kRPT] = {};
-        float4 p_nx[kRPT], p_cur[kRPT];    // SRC_POINTMLP: centred points of the next / current tile
+        float4 p_cur[kRPT];                // SRC_POINTMLP: centred points of the current tile
 #pragma unroll
-        for (int j = 0; j < kRPT; ++j) p_nx[j] = p_cur[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < kRPT; ++j) p_cur[j] = make_float4(0.f, 0.f, 0.f, 0.f);
 
         auto fetch_idx = [&](long long tile) {  // -> idx_pf / bN_pf / grp_pf for `tile`
 #pragma unroll
             for (int j = 0; j < kRPT; ++j) {
                 long long row = tile * kTile + rb + kRowStride * j;
                 row = row < a.M ? row : a.M - 1;
-                const RowGeom rg = row_geom(row, a.K, a.S, a.N);
+                const RowGeom rg = row_geom(row, a);
                 bN_pf[j] = rg.bN;
                 grp_pf[j] = rg.g;
                 idx_pf[j] = a.idx != nullptr ? __ldg(a.idx + row) : rg.k;
             }
         };
-        auto fetch_points = [&]() {  // idx_pf (arrived) -> p_nx
-#pragma unroll
-            for (int j = 0; j < kRPT; ++j) {
-                const int n = min(max(idx_pf[j], 0), a.N - 1);
-                const float *q = a.xyz + (bN_pf[j] + n) * 3;
-                float px = __ldg(q), py = __ldg(q + 1), pz = __ldg(q + 2);
-                if (a.new_xyz != nullptr) {
-                    const float *cc = a.new_xyz + (long long)grp_pf[j] * 3;
-                    px = __fsub_rn(px, __ldg(cc));
-                    py = __fsub_rn(py, __ldg(cc + 1));
-                    pz = __fsub_rn(pz, __ldg(cc + 2));
-                }
-                p_nx[j] = make_float4(px, py, pz, 0.f);
+        // ---- SRC_POINTMLP: the tile's 128 centred points are fetched ONCE (producer thread r < 128
+        //      owns row r: index two tiles ahead, point one tile ahead, both in flight across a whole
+        //      tile) and handed to the 8 threads that expand that row through a double-buffered
+        //      shared-memory table -- instead of every thread gathering its rows' points itself.
+        int idx1 = 0, grp1 = 0;
+        long long bN1 = 0;
+        float4 pt1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto fetch_idx1 = [&](long long tile) {
+            long long row = tile * kTile + (ptid & (kTile - 1));
+            row = row < a.M ? row : a.M - 1;
+            const RowGeom rg = row_geom(row, a);
+            bN1 = rg.bN;
+            grp1 = rg.g;
+            idx1 = a.idx != nullptr ? __ldg(a.idx + row) : rg.k;
+        };
+        auto fetch_pt1 = [&]() {  // idx1 (arrived) -> pt1
+            const int n = min(max(idx1, 0), a.N - 1);
+            const float *q = a.xyz + (bN1 + n) * 3;
+            float px = __ldg(q), py = __ldg(q + 1), pz = __ldg(q + 2);
+            if (a.new_xyz != nullptr) {
+                const float *cc = a.new_xyz + (long long)grp1 * 3;
+                px = __fsub_rn(px, __ldg(cc));
+                py = __fsub_rn(py, __ldg(cc + 1));
+                pz = __fsub_rn(pz, __ldg(cc + 2));
             }
+            pt1 = make_float4(px, py, pz, 0.f);
         };
 
         // ---- raw ring (SRC_PLAIN / SRC_GATHER): every thread lands ITS OWN 16-byte units of a chunk
@@ -737,13 +780,18 @@ mlp_layer_tt_kernel(const TtArgs a) {
                 }
             } else {  // SRC_POINTMLP
                 if (c == 0) {
-                    // p_nx holds this tile's points (issued one tile ago); refill it for the next
-                    // tile from idx_pf (issued one tile ago), then prefetch idx two tiles ahead
+                    // pt1 holds this tile's point of row ptid (issued one tile ago): publish it, pick up
+                    // the rows this thread expands, then refill pt1 / idx1 for the next tiles
+                    const uint32_t tab = sm + SmemLayout::xyz + 16u * (uint32_t)((ptl & 1) * kTile);
+                    if (ptid < kTile) sts128f(tab + 16u * (uint32_t)ptid, pt1);
+                    named_bar_sync(1, kProdThreads);
 #pragma unroll
-                    for (int j = 0; j < kRPT; ++j) p_cur[j] = p_nx[j];
-                    fetch_points();
-                    const long long t2 = tile + 2LL * gm;
-                    fetch_idx(t2 < tiles_m ? t2 : tile);
+                    for (int j = 0; j < kRPT; ++j) p_cur[j] = lds128f(tab + 16u * (uint32_t)(rb + kRowStride * j));
+                    if (ptid < kTile) {
+                        fetch_pt1();
+                        const long long t2 = tile + 2LL * gm;
+                        fetch_idx1(t2 < tiles_m ? t2 : tile);
+                    }
                 }
 #pragma unroll
                 for (int q = 0; q < P::kEPU; ++q) {
@@ -791,6 +839,9 @@ mlp_layer_tt_kernel(const TtArgs a) {
             fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
             __syncwarp();
             if (lane == 0) mbar_arrive(x_full + s);
+            if (ptid == 0 && it == 0) TT_CLK(a, 3);
+            if (ptid == 0 && it == 1) TT_CLK(a, 12);
+            if (ptid == 0) TT_CLK(a, 10);
             ++it;
             if (c == KC - 1) ++ptl;
         };
@@ -814,10 +865,10 @@ mlp_layer_tt_kernel(const TtArgs a) {
                     if (cq == KC - 1) ++ptl;
                 }
         } else if (MODE == SRC_POINTMLP) {
-            if (tile0 < tiles_m) {
-                fetch_idx(tile0);                       // idx of the first tile
-                fetch_points();                         // -> p_nx = points of the first tile
-                fetch_idx(tile0 + gm < tiles_m ? tile0 + gm : tile0);
+            if (tile0 < tiles_m && ptid < kTile) {
+                fetch_idx1(tile0);                      // idx of the first tile
+                fetch_pt1();                            // -> pt1 = point of the first tile
+                fetch_idx1(tile0 + gm < tiles_m ? tile0 + gm : tile0);
             }
             for (long long t = tile0; t < tiles_m; t += gm)
                 for (int cq = 0; cq < KC; ++cq) process(t, cq, 0);
@@ -846,6 +897,7 @@ mlp_layer_tt_kernel(const TtArgs a) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (tid == 0) TT_CLK(a, 7);
     if (warp == kMmaWarp) tmem_dealloc<kTmemCols>(tmem_base);
 
     // ---- fused BatchNorm finalisation: the last CTA reduces the partial rows in fixed order
@@ -857,22 +909,45 @@ mlp_layer_tt_kernel(const TtArgs a) {
         __syncthreads();
         if (*s_last != 0u) {
             __threadfence();
-            // 2*cout (sum | sum^2, channel) columns x gm partial rows: 128 columns at a time, the
-            // rows split over three thread slices (fixed order -> deterministic), combined in smem
-            double *red = reinterpret_cast<double *>(smem + SmemLayout::ring);            // [3][128]
-            double *all = reinterpret_cast<double *>(smem + SmemLayout::ring + kXBytes);  // [2*cout]
-            const int col_l = tid & 127, sl = tid >> 7;  // slices 0..2; threads >= 384 idle
-            for (int base = 0; base < 2 * a.cout; base += 128) {
-                const int col = base + col_l;  // = which * cout + ch
-                if (sl < 3 && col < 2 * a.cout) {
-                    double acc = 0.0;
-                    const double *p = a.stats_partial + col;
-#pragma unroll 16
-                    for (int r = sl; r < gm; r += 3) acc += __ldcg(p + (long long)r * 2 * a.cout);
-                    red[sl * 128 + col_l] = acc;
+#ifdef PAPC_TT_TRIAGE
+            if (tid == 0 && a.clk != nullptr) a.clk[32 + 7] = clock64();
+#endif
+            // gm partial rows x 2*cout doubles (sum | sum^2 per channel), read as 16-byte column pairs:
+            // up to 512 pairs per pass, the rows split over S = 512 / pairs thread slices so that a
+            // thread's loads are all independent and few (fixed order -> deterministic); slices are
+            // combined through shared memory.  This is a serial tail of the kernel (one CTA works,
+            // the GPU waits), so it is arranged for the fewest dependent L2 round trips.
+            double2 *red = reinterpret_cast<double2 *>(smem + SmemLayout::ring);            // [512]
+            double *all = reinterpret_cast<double *>(smem + SmemLayout::ring + kXBytes);    // [2*cout]
+            const int npairs = a.cout;  // 2*cout doubles
+            const int P = npairs < 512 ? npairs : 512;
+            const int S = 512 / P;
+            const int pair_l = tid % P, sl = tid / P;
+            const double2 *part = reinterpret_cast<const double2 *>(a.stats_partial);
+            for (int base = 0; base < npairs; base += P) {
+                const int pr = base + pair_l;
+                if (sl < S && pr < npairs) {
+                    double ax = 0.0, ay = 0.0;
+                    const double2 *p = part + pr;
+#pragma unroll 8
+                    for (int r = sl; r < gm; r += S) {
+                        const double2 v = __ldcg(p + (long long)r * npairs);
+                        ax += v.x;
+                        ay += v.y;
+                    }
+                    red[sl * P + pair_l] = make_double2(ax, ay);
                 }
                 __syncthreads();
-                if (sl == 0 && col < 2 * a.cout) all[col] = (red[col_l] + red[128 + col_l]) + red[256 + col_l];
+                if (sl == 0 && pr < npairs) {
+                    double ax = 0.0, ay = 0.0;
+                    for (int q = 0; q < S; ++q) {
+                        const double2 v = red[q * P + pair_l];
+                        ax += v.x;
+                        ay += v.y;
+                    }
+                    all[2 * pr] = ax;
+                    all[2 * pr + 1] = ay;
+                }
                 __syncthreads();
             }
             for (int ch = tid; ch < a.cout; ch += kThreads) {
@@ -893,8 +968,21 @@ mlp_layer_tt_kernel(const TtArgs a) {
                 if (a.var_out) a.var_out[ch] = (float)var;
             }
             if (tid == 0) *a.counter = 0u;  // self-cleaning for the next launch
+#ifdef PAPC_TT_TRIAGE
+            if (tid == 0 && a.clk != nullptr) { a.clk[32 + 8] = clock64(); a.clk[32 + 9] = blockIdx.x; }
+#endif
         }
+        if (tid == 0) TT_CLK(a, 8);
     }
+#ifdef PAPC_TT_TRIAGE
+    if (tid == 0 && a.clk != nullptr) {
+        unsigned long long gt1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
+        atomicMax(a.clk + 45, gt1);
+        atomicMax(a.clk + 46, gt1 - gt0);
+        atomicAdd(a.clk + 47, gt1 - gt0);
+    }
+#endif
 }
 
 // ------------------------------------------------------------------------------ point moments
@@ -917,7 +1005,7 @@ point_moments_kernel(const MomentArgs a) {
         int n_in_acc = 0;
         for (long long row = (long long)blockIdx.x * kMomThreads + tid; row < a.M;
              row += (long long)gridDim.x * kMomThreads) {
-            const RowGeom rg = row_geom(row, a.K, a.S, a.N);
+            const RowGeom rg = row_geom(row, a);
             int n = a.idx != nullptr ? __ldg(a.idx + row) : rg.k;
             n = min(max(n, 0), a.N - 1);
             const float *q = a.xyz + (rg.bN + n) * 3;
@@ -1010,6 +1098,15 @@ static int tmem_k(int prec) { return prec == PREC_F16 ? Prec<PREC_F16>::kTmemK :
 static int epc(int prec) { return prec == PREC_F16 ? Prec<PREC_F16>::kEPC : Prec<PREC_TF32>::kEPC; }
 static int epu(int prec) { return prec == PREC_F16 ? Prec<PREC_F16>::kEPU : Prec<PREC_TF32>::kEPU; }
 
+void make_fastdiv(uint32_t d, uint32_t *mul, uint32_t *shr) {
+    if (d <= 1u) { *mul = 0u; *shr = 0u; return; }
+    uint32_t lg = 0;
+    while ((1ull << lg) < d) ++lg;  // ceil(log2(d))
+    const uint32_t p = 31u + lg;
+    *mul = (uint32_t)(((1ull << p) + d - 1ull) / d);
+    *shr = p - 32u;
+}
+
 bool eligible(const TtProblem &p) {
     if (p.prec != PREC_TF32 && p.prec != PREC_F16) return false;
     if (p.cout < 1 || p.cout > 8 * kTile) return false;
@@ -1068,8 +1165,21 @@ int launch(const TtArgs &a_in, cudaStream_t st) {
         const char *e = getenv("PAPC_TT_DBG");
         a.dbg = e ? atoi(e) : 0;
     }
+#ifdef PAPC_TT_TRIAGE
+    static unsigned long long *d_clk = nullptr;
+    const bool want_clk = getenv("PAPC_TT_CLK") != nullptr;
+    if (want_clk) {
+        if (d_clk == nullptr) cudaMalloc(&d_clk, 48 * sizeof(unsigned long long));
+        cudaMemsetAsync(d_clk, 0, 48 * sizeof(unsigned long long), st);
+        cudaMemsetAsync(d_clk + 44, 0xff, sizeof(unsigned long long), st);  // atomicMin target
+        a.clk = d_clk;
+    }
+#endif
     const bool pool = a.pool_max != nullptr;
     if (!pool && a.y == nullptr) return PAPC_EINVAL;
+    a.fastgeom = a.M < (1LL << 31) && a.K >= 1 && a.S >= 1;
+    make_fastdiv((uint32_t)(a.K >= 1 ? a.K : 1), &a.kmul, &a.kshr);
+    make_fastdiv((uint32_t)(a.S >= 1 ? a.S : 1), &a.smul, &a.sshr);
     const bool streamed = a.cin > tmem_k(a.prec);
     const int nt = ceil_div(a.cout, kTile);
     if (streamed) {
@@ -1091,17 +1201,37 @@ int launch(const TtArgs &a_in, cudaStream_t st) {
     if (gm > tiles_m) gm = tiles_m;
     if (a.stats_partial != nullptr && gm > a.partial_rows) gm = a.partial_rows;
     const int grid = (int)(gm * nt);
+    int rc = PAPC_EINVAL;
     switch (a.mode) {
         case SRC_PLAIN:
-            return a.prec == PREC_F16 ? launch_mp<SRC_PLAIN, PREC_F16>(a, streamed, pool, grid, st)
-                                      : launch_mp<SRC_PLAIN, PREC_TF32>(a, streamed, pool, grid, st);
+            rc = a.prec == PREC_F16 ? launch_mp<SRC_PLAIN, PREC_F16>(a, streamed, pool, grid, st)
+                                    : launch_mp<SRC_PLAIN, PREC_TF32>(a, streamed, pool, grid, st);
+            break;
         case SRC_GATHER:
-            return launch_mp<SRC_GATHER, PREC_TF32>(a, streamed, pool, grid, st);
+            rc = launch_mp<SRC_GATHER, PREC_TF32>(a, streamed, pool, grid, st);
+            break;
         case SRC_POINTMLP:
-            return a.prec == PREC_F16 ? launch_mp<SRC_POINTMLP, PREC_F16>(a, streamed, pool, grid, st)
-                                      : launch_mp<SRC_POINTMLP, PREC_TF32>(a, streamed, pool, grid, st);
+            rc = a.prec == PREC_F16 ? launch_mp<SRC_POINTMLP, PREC_F16>(a, streamed, pool, grid, st)
+                                    : launch_mp<SRC_POINTMLP, PREC_TF32>(a, streamed, pool, grid, st);
+            break;
     }
-    return PAPC_EINVAL;
+#ifdef PAPC_TT_TRIAGE
+    if (want_clk && rc == PAPC_OK) {
+        unsigned long long h[48];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, d_clk, sizeof(h), cudaMemcpyDeviceToHost);
+        auto us = [&](int slot, int e) { return h[slot * 16 + e] ? (double)(h[slot * 16 + e] - h[slot * 16]) / 1965.0 : -1.0; };
+        fprintf(stderr, "[tt clk] mode %d prec %d M %lld cin %d cout %d grid %d | CTA0 us: setup %.2f Wstaged %.2f "
+                "x_full0 %.2f x_full1 %.2f mma0 %.2f acc0 %.2f acc1 %.2f prod_end %.2f epi_end %.2f teardown %.2f "
+                "counted %.2f | last CTA %llu: start %.2f end %.2f (rel. CTA0 entry, same SM clock only if CTA 0)\n",
+                a.mode, a.prec, a.M, a.cin, a.cout, grid, us(0, 1), us(0, 2), us(0, 3), us(0, 12), us(0, 4), us(0, 5),
+                us(0, 11), us(0, 10), us(0, 6), us(0, 7), us(0, 8), h[32 + 9],
+                h[32 + 7] ? (double)(h[32 + 8] - h[32 + 7]) / 1965.0 : -1.0, 0.0);
+        fprintf(stderr, "[tt clk]   globaltimer: first entry -> last exit %.2f us, longest CTA %.2f us, mean CTA %.2f us\n",
+                (double)(h[45] - h[44]) / 1e3, (double)h[46] / 1e3, (double)h[47] / 1e3 / grid);
+    }
+#endif
+    return rc;
 }
 
 int moment_blocks(long long M) {
@@ -1111,7 +1241,11 @@ int moment_blocks(long long M) {
     return (int)b;
 }
 
-int launch_moments(const MomentArgs &a, cudaStream_t st) {
+int launch_moments(const MomentArgs &a_in, cudaStream_t st) {
+    MomentArgs a = a_in;
+    a.fastgeom = a.M < (1LL << 31) && a.K >= 1 && a.S >= 1;
+    make_fastdiv((uint32_t)(a.K >= 1 ? a.K : 1), &a.kmul, &a.kshr);
+    make_fastdiv((uint32_t)(a.S >= 1 ? a.S : 1), &a.smul, &a.sshr);
     const int blocks = a.running_mean != nullptr ? 1 : moment_blocks(a.M);
     ProfScope prof(st, "point_moments", a.M, 3, a.c0, 0.0, 16.0 * (double)a.M);
     point_moments_kernel<<<blocks, kMomThreads, 0, st>>>(a);

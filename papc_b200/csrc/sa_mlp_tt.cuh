@@ -48,8 +48,13 @@ struct TtArgs {
     float eps;
     double count;
     float *scale, *shift, *mean_out, *var_out, *out_colscale;
+    // row -> (group, position, cloud) without 64-bit divisions: magic-number division by K and S,
+    // filled in by launch(); valid while M < 2^31 (fastgeom = 0 falls back to long long division)
+    uint32_t kmul, kshr, smul, sshr;
+    int fastgeom;
     int dbg;  // PAPC_TT_DBG bit mask (performance triage only): 1 = producers skip loads+math,
               // 2 = no MMAs issued, 4 = epilogue skips its math / stores
+    unsigned long long *clk;  // triage builds: [3][16] per-phase clock64() stamps (CTA 0, CTA 1, last CTA)
 };
 
 struct TtProblem {
@@ -57,6 +62,8 @@ struct TtProblem {
     bool pool;
 };
 bool eligible(const TtProblem &p);
+// Division by a runtime constant d >= 1 for dividends < 2^31: q = d == 1 ? x : umulhi(x, mul) >> shr
+void make_fastdiv(uint32_t d, uint32_t *mul, uint32_t *shr);
 // Bytes of the streamed-W image the launch needs in TtArgs::wimg (0 = W fits in tensor memory).
 size_t wimg_bytes(int prec, int cin, int cout);
 int launch(const TtArgs &a, cudaStream_t st);
@@ -82,6 +89,8 @@ struct MomentArgs {
     const float *running_mean, *running_var;  // used instead of the batch moments when non-null
     float eps;
     int c0;
+    uint32_t kmul, kshr, smul, sshr;  // as TtArgs (filled in by launch_moments)
+    int fastgeom;
     double *partial;        // [blocks][9]
     unsigned int *counter;
     float *scale, *shift, *mean_out, *var_out;  // [c0] (mean/var nullable)
