@@ -608,6 +608,7 @@ struct FusedBn {
     const float *gamma, *beta;
     float eps;
     double count;
+    float sqrt_count;     // (float)sqrt(count), rounded up: argument of tt::f16_colscale_sq
     float *scale, *shift, *mean_out, *var_out;
     float *out_colscale;  // non-null: the NEXT layer runs the fp16 split (see tt::TtArgs)
 };
@@ -615,11 +616,16 @@ struct FusedBn {
 // Per-launch options of the transposed tcgen05 kernel.
 struct TtOpts {
     int prec;                 // tt::PREC_TF32 / tt::PREC_F16
-    const float *w_colscale;  // PREC_F16: column scale written by the producer layer's finalisation
+    // PREC_F16: the column scale is f16_colscale_sq(cs_gamma[k], cs_beta[k], cs_sqrt_count) of the
+    // layer that produced the activations (the same expression its finalisation divided by)
+    const float *cs_gamma, *cs_beta;
+    float cs_sqrt_count;
     const float *l0_fold;     // non-null: SRC_POINTMLP
     void *wimg;               // workspace for the streamed-W image
     size_t wimg_bytes;
     bool dry_run;             // only report eligibility
+    bool pdl;                 // the previous stream operation is one of this call's kernels: overlap
+                              // this launch's prologue with its tail (programmatic dependent launch)
 };
 
 // Tries the transposed tcgen05 kernel.  Returns 1 if launched (or, dry_run, launchable), 0 if the
@@ -633,7 +639,10 @@ static int try_tt(const LayerArgs &a, bool gather, int K, const FusedBn *bn, con
     t.bias = a.bias; t.y = a.y; t.pool_max = a.pool_max; t.pool_min = a.pool_min;
     t.stats_partial = a.stats_partial; t.partial_rows = grid_rows(a.M);
     t.W = a.W; t.wld = a.cin; t.wk0 = 0; t.wxyz = -1;
-    t.w_colscale = o.w_colscale;
+    t.w_colscale = nullptr;
+    t.cs_on = o.prec == tt::PREC_F16 ? 1 : 0;
+    t.cs_gamma = o.cs_gamma; t.cs_beta = o.cs_beta; t.cs_sqrt_count = o.cs_sqrt_count;
+    t.pdl = o.pdl ? 1 : 0;
     if (o.l0_fold != nullptr) {
         // `a` describes the SECOND layer (cin = first layer's cout); rows come from the points
         t.mode = tt::SRC_POINTMLP;
@@ -663,7 +672,7 @@ static int try_tt(const LayerArgs &a, bool gather, int K, const FusedBn *bn, con
     if (o.dry_run) return 1;
     if (bn != nullptr && a.stats_partial != nullptr) {
         t.counter = bn->counter; t.gamma = bn->gamma; t.beta = bn->beta; t.eps = bn->eps;
-        t.count = bn->count; t.scale = bn->scale; t.shift = bn->shift;
+        t.count = bn->count; t.sqrt_count = bn->sqrt_count; t.scale = bn->scale; t.shift = bn->shift;
         t.mean_out = bn->mean_out; t.var_out = bn->var_out; t.out_colscale = bn->out_colscale;
     }
     const int rc = tt::launch(t, st);
@@ -732,7 +741,7 @@ static int layer_forward(const papc_group_source *src, const float *x, const flo
     if (!(pool_max && M % K != 0)) {
         const bool sc_ok = a.in_scale == nullptr || (aligned16(a.in_scale) && aligned16(a.in_shift));
         if (sc_ok) {
-            TtOpts o{tt::PREC_TF32, nullptr, nullptr, workspace, workspace_bytes, false};
+            TtOpts o{tt::PREC_TF32, nullptr, nullptr, 0.f, nullptr, workspace, workspace_bytes, false, false};
             if (opts != nullptr) o = *opts;
             else if (!gather && a.in_scale != nullptr && cin % 8 == 0) {
                 // step-wise API: no bound on the activations is known, so TF32 -- unless the caller
@@ -979,10 +988,13 @@ extern "C" int papc_sa_mlp_f32(const papc_group_source *src, const papc_mlp *mlp
         a.pool_max = last ? pmax : nullptr; a.pool_min = last ? pmin : nullptr;
         a.stats_partial = partial;
         if (last && M % src->K != 0) return false;
-        const TtOpts o{tt::PREC_F16, colscale[0], nullptr, ws + p.wimg, p.wimg_bytes, true};
+        const TtOpts o{tt::PREC_F16, nullptr, nullptr, 0.f, nullptr, ws + p.wimg, p.wimg_bytes, true, false};
         return try_tt(a, false, src->K, nullptr, o, st) == 1;
     };
     bool this_f16 = false;  // precision of the layer about to run
+    // (float)sqrt(M) rounded up: the one value every f16_colscale_sq() user of this call receives
+    const float sqrt_m = nextafterf((float)sqrt((double)M), INFINITY);
+    bool prev_is_kernel = false;  // the last stream operation of this call is a kernel of ours (PDL)
     if (pointmlp_ok(src, mlp)) {
         // Layer 0 (3 -> c0) is never materialised: its BatchNorm statistics follow analytically
         // from the moments of the centred points, and layer 1's producer recomputes it per row.
@@ -994,7 +1006,7 @@ extern "C" int papc_sa_mlp_f32(const papc_group_source *src, const papc_mlp *mlp
         m.W0 = l0.weight; m.b0 = l0.bias; m.gamma = l0.gamma; m.beta = l0.beta;
         m.running_mean = batch ? nullptr : l0.running_mean;
         m.running_var = batch ? nullptr : l0.running_var;
-        m.eps = mlp->eps; m.c0 = l0.cout;
+        m.eps = mlp->eps; m.c0 = l0.cout; m.sqrt_M = sqrt_m;
         m.partial = reinterpret_cast<double *>(ws + p.mom_partial);
         m.counter = counters + PAPC_MAX_MLP_LAYERS;
         m.scale = scale; m.shift = shift; m.mean_out = l0.batch_mean; m.var_out = l0.batch_var;
@@ -1005,16 +1017,18 @@ extern "C" int papc_sa_mlp_f32(const papc_group_source *src, const papc_mlp *mlp
         l_first = 1;
         cin = l0.cout;
         folded = true;
+        prev_is_kernel = true;
     }
     for (int l = l_first; l < L; ++l) {
         const papc_mlp_layer &ly = mlp->layers[l];
         const bool last = (l == L - 1);
         float *y = last ? nullptr : ybuf[l & 1];
         const bool next_f16 = f16_ok(l + 1, ly.cout);
-        FusedBn bn{counters + l, ly.gamma, ly.beta, mlp->eps, (double)M,
+        FusedBn bn{counters + l, ly.gamma, ly.beta, mlp->eps, (double)M, sqrt_m,
                    scale, shift, ly.batch_mean, ly.batch_var, next_f16 ? colscale[l & 1] : nullptr};
-        TtOpts o{this_f16 ? tt::PREC_F16 : tt::PREC_TF32, this_f16 ? colscale[(l - 1) & 1] : nullptr,
-                 nullptr, ws + p.wimg, p.wimg_bytes, false};
+        TtOpts o{this_f16 ? tt::PREC_F16 : tt::PREC_TF32,
+                 this_f16 ? mlp->layers[l - 1].gamma : nullptr, this_f16 ? mlp->layers[l - 1].beta : nullptr,
+                 sqrt_m, nullptr, ws + p.wimg, p.wimg_bytes, false, prev_is_kernel};
         bool fused_done = false;
         if (folded && l == 1) {
             LayerArgs a{};
@@ -1059,6 +1073,7 @@ extern "C" int papc_sa_mlp_f32(const papc_group_source *src, const papc_mlp *mlp
         }
         xprev = y;
         cin = ly.cout;
+        prev_is_kernel = true;  // a layer kernel (or the scale / shift kernel after it)
     }
     return papc_sa_pool_finish_f32(pmax, pmin, scale, shift, src->B, src->S,
                                    mlp->layers[L - 1].cout, out, out_layout, stream);

@@ -137,7 +137,8 @@ struct SmemLayout {
     // hand-over slots between the two epilogue warps of a quadrant
     static constexpr uint32_t xpool = fold + kMaxFold * 16;          // [2][128] float2: K = 128 max/min
     static constexpr uint32_t xstat = xpool + 2 * kTile * 8;         // [128] double2: statistic sums
-    static constexpr uint32_t bars = xstat + kTile * 16;
+    static constexpr uint32_t cs = xstat + kTile * 16;               // [512] float: fp16 column scale of W
+    static constexpr uint32_t bars = cs + kMaxAct * 4;
     static constexpr uint32_t nbars = 2 * 6 + 2 + 2 + 1 + 4;
     static constexpr uint32_t misc = bars + nbars * 8;               // tmem slot, last-CTA flag
     static constexpr uint32_t ring = (misc + 16 + 1023) / 1024 * 1024;  // operand ring (1024-aligned)
@@ -202,7 +203,9 @@ __device__ __forceinline__ RowGeom row_geom(long long row, const A &a) {
 template <int PREC>
 __global__ void __launch_bounds__(256)
 prep_wimg_kernel(const float *__restrict__ W, int wld, int wk0, int cin, int cout,
-                 const float *__restrict__ colscale, int KC, uint8_t *__restrict__ img) {
+                 const float *__restrict__ colscale, int cs_on, const float *__restrict__ cs_gamma,
+                 const float *__restrict__ cs_beta, float cs_sqrt_count, int KC,
+                 uint8_t *__restrict__ img) {
     using P = Prec<PREC>;
     const int nt = ceil_div(cout, kTile);
     const long long total = (long long)nt * KC * kTile * 8;  // one 16-byte unit per thread step
@@ -220,7 +223,9 @@ prep_wimg_kernel(const float *__restrict__ W, int wld, int wk0, int cin, int cou
             float w = 0.f;
             if (row < cout && k < cin) {
                 w = W[(size_t)row * wld + wk0 + k];
-                if (colscale != nullptr) w *= colscale[k];
+                if (cs_on)
+                    w *= f16_colscale_sq(cs_gamma ? cs_gamma[k] : 1.f, cs_beta ? cs_beta[k] : 0.f, cs_sqrt_count);
+                else if (colscale != nullptr) w *= colscale[k];
             }
             v[q] = w;
         }
@@ -307,6 +312,13 @@ mlp_layer_tt_kernel(const TtArgs a) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (tid == 0) TT_CLK(a, 1);
+    // Programmatic dependent launch.  As the primary: let the next kernel's CTAs be scheduled on
+    // SMs as ours retire (they only run their prologue until we are completely done).  As the
+    // dependent (a.pdl): everything up to pdl_wait() reads launch arguments and the weights only.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    auto pdl_wait = [&]() {
+        if (a.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+    };
 
     if (warp < kEpiWarps) {
         // ================================ epilogue =========================================
@@ -322,6 +334,22 @@ mlp_layer_tt_kernel(const TtArgs a) {
         //      flight at once -- no shared-memory transposition, no per-row round trips.  The two
         //      epilogue warps of a quadrant take alternate chunks.
         if (WMODE == 0) {
+            float *s_cs = reinterpret_cast<float *>(smem + SmemLayout::cs);
+            const bool scaled = a.cs_on || a.w_colscale != nullptr;
+            if (scaled) {  // the column scale of every k once per CTA (256 threads), then 16-byte reads
+                for (int k = tid; k < kMaxAct; k += kEpiWarps * 32) {
+                    float c1 = 1.f;
+                    if (k < a.cin) {
+                        if (a.cs_on)
+                            c1 = f16_colscale_sq(a.cs_gamma ? __ldg(a.cs_gamma + k) : 1.f,
+                                                 a.cs_beta ? __ldg(a.cs_beta + k) : 0.f, a.cs_sqrt_count);
+                        else
+                            c1 = __ldg(a.w_colscale + k);
+                    }
+                    s_cs[k] = c1;
+                }
+                named_bar_sync(10, kEpiWarps * 32);
+            }
             const float *wrow = a.W + (size_t)(cvalid ? cg : 0) * a.wld + a.wk0;
             const bool vec = ((a.wld | a.wk0) & 3) == 0 && (reinterpret_cast<uintptr_t>(a.W) & 15u) == 0 &&
                              (a.w_colscale == nullptr || (reinterpret_cast<uintptr_t>(a.w_colscale) & 15u) == 0);
@@ -337,25 +365,18 @@ mlp_layer_tt_kernel(const TtArgs a) {
                             const float4 t = __ldg(reinterpret_cast<const float4 *>(wrow + k0) + q);
                             v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
                         }
-                        if (a.w_colscale != nullptr) {
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                const float4 t = __ldg(reinterpret_cast<const float4 *>(a.w_colscale + k0) + q);
-                                v[4 * q] *= t.x; v[4 * q + 1] *= t.y; v[4 * q + 2] *= t.z; v[4 * q + 3] *= t.w;
-                            }
-                        }
                     } else {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
                             const int k = k0 + i;
                             v[i] = k < a.cin ? __ldg(wrow + k) : 0.f;
                         }
-                        if (a.w_colscale != nullptr) {
+                    }
+                    if (scaled) {
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                const int k = k0 + i;
-                                if (k < a.cin) v[i] *= __ldg(a.w_colscale + k);
-                            }
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 t = *reinterpret_cast<const float4 *>(s_cs + ((k0 + 4 * q) & (kMaxAct - 1)));
+                            v[4 * q] *= t.x; v[4 * q + 1] *= t.y; v[4 * q + 2] *= t.z; v[4 * q + 3] *= t.w;
                         }
                     }
                     if (!cvalid) {
@@ -385,6 +406,7 @@ mlp_layer_tt_kernel(const TtArgs a) {
             if (lane == 0) mbar_arrive(w_ready);
         }
         if (tid == 0) TT_CLK(a, 2);
+        pdl_wait();
         const float bias = (a.bias != nullptr && cvalid) ? a.bias[cg] : 0.f;
         float wx = 0.f, wy = 0.f, wz = 0.f;
         const bool has_xyz = (MODE == SRC_GATHER) && a.wxyz >= 0;
@@ -536,6 +558,7 @@ mlp_layer_tt_kernel(const TtArgs a) {
     } else if (warp == kMmaWarp) {
         // ================================ MMA issuer =======================================
         // The whole warp runs the (uniform) control flow; one elected lane issues the tcgen05 ops.
+        pdl_wait();
         if (WMODE == 0) {
             mbar_wait(w_ready, 0);
             tc_fence_after();
@@ -602,6 +625,7 @@ mlp_layer_tt_kernel(const TtArgs a) {
         const int rb = ptid >> 3;     // rows rb + kRowStride*j, j = 0..kRPT-1
         const uint32_t swz = (uint32_t)((u ^ (rb & 7)) << 4);
         const bool has_act = (MODE == SRC_PLAIN) && a.in_scale != nullptr;
+        pdl_wait();
         if (MODE == SRC_PLAIN)
             for (int k = ptid; k < kMaxAct; k += kProdThreads) {
                 s_scale[k] = (has_act && k < a.cin) ? a.in_scale[k] : 0.f;
@@ -959,7 +983,7 @@ mlp_layer_tt_kernel(const TtArgs a) {
                 const double sc = g / sqrt(var + (double)a.eps);
                 float cs = 1.f;
                 if (a.out_colscale != nullptr) {
-                    cs = f16_colscale(g, b, a.count);
+                    cs = f16_colscale_sq(a.gamma ? a.gamma[ch] : 1.f, a.beta ? a.beta[ch] : 0.f, a.sqrt_count);
                     a.out_colscale[ch] = cs;
                 }
                 a.scale[ch] = (float)sc / cs;
@@ -1083,7 +1107,7 @@ point_moments_kernel(const MomentArgs a) {
         a.shift[c] = (float)sh;
         double cs = 1.0;  // power of two keeping relu(bn(y0)) / cs below 2^15 (fp16 operands)
         if (a.out_colscale != nullptr) {
-            const float csf = f16_colscale(g, be, (double)a.M);
+            const float csf = f16_colscale_sq(a.gamma ? a.gamma[c] : 1.f, a.beta ? a.beta[c] : 0.f, a.sqrt_M);
             a.out_colscale[c] = csf;
             cs = (double)csf;
         }
@@ -1144,6 +1168,21 @@ static int launch_inst(const TtArgs &a, int grid, cudaStream_t st) {
     const double out_b = (a.y ? 4.0 * (double)a.M * a.cout : 0.0) +
                          (POOL ? 8.0 * (double)(a.M / (a.K > 0 ? a.K : 1)) * a.cout : 0.0);
     ProfScope prof(st, name, a.M, a.cin, a.cout, 2.0 * (double)a.M * a.cin * a.cout, in_b + out_b);
+    if (a.pdl) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = Cfg<MODE, PREC, WMODE>::bytes;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        ++g_launch_count;
+        PAPC_CUDA_TRY(cudaLaunchKernelEx(&cfg, k, a));
+        return PAPC_OK;
+    }
     k<<<grid, kThreads, Cfg<MODE, PREC, WMODE>::bytes, st>>>(a);
     PAPC_LAUNCH_CHECK();
     return PAPC_OK;
@@ -1182,6 +1221,10 @@ int launch(const TtArgs &a_in, cudaStream_t st) {
     make_fastdiv((uint32_t)(a.S >= 1 ? a.S : 1), &a.smul, &a.sshr);
     const bool streamed = a.cin > tmem_k(a.prec);
     const int nt = ceil_div(a.cout, kTile);
+    {
+        const char *e = getenv("PAPC_TT_PDL");  // A/B switch: PAPC_TT_PDL=0 disables dependent launch
+        if (streamed || (e && e[0] == '0')) a.pdl = 0;  // (the W-image kernel sits in between)
+    }
     if (streamed) {
         if (a.wimg == nullptr) return PAPC_EWORKSPACE;
         const int KC = ceil_div(a.cin, epc(a.prec));
@@ -1189,10 +1232,12 @@ int launch(const TtArgs &a_in, cudaStream_t st) {
         if (blocks > 4LL * kNumSMs) blocks = 4LL * kNumSMs;
         if (a.prec == PREC_F16)
             prep_wimg_kernel<PREC_F16><<<(unsigned)blocks, 256, 0, st>>>(
-                a.W, a.wld, a.wk0, a.cin, a.cout, a.w_colscale, KC, reinterpret_cast<uint8_t *>(a.wimg));
+                a.W, a.wld, a.wk0, a.cin, a.cout, a.w_colscale, a.cs_on, a.cs_gamma, a.cs_beta, a.cs_sqrt_count, KC,
+                reinterpret_cast<uint8_t *>(a.wimg));
         else
             prep_wimg_kernel<PREC_TF32><<<(unsigned)blocks, 256, 0, st>>>(
-                a.W, a.wld, a.wk0, a.cin, a.cout, a.w_colscale, KC, reinterpret_cast<uint8_t *>(a.wimg));
+                a.W, a.wld, a.wk0, a.cin, a.cout, a.w_colscale, a.cs_on, a.cs_gamma, a.cs_beta, a.cs_sqrt_count, KC,
+                reinterpret_cast<uint8_t *>(a.wimg));
         PAPC_LAUNCH_CHECK();
     }
     const long long tiles_m = ceil_div<long long>(a.M, kTile);

@@ -34,6 +34,16 @@ struct TtArgs {
     const float *W;
     int wld, wk0, wxyz;
     const float *w_colscale;
+    // ... or, cs_on != 0, computed on the fly as f16_colscale_sq(cs_gamma[k], cs_beta[k], cs_sqrt_count)
+    // from the BatchNorm parameters of the layer that produced the activations (nullable = 1 / 0):
+    // nothing the weight staging reads then depends on the previous kernel.
+    int cs_on;
+    const float *cs_gamma, *cs_beta;
+    float cs_sqrt_count;
+    // programmatic dependent launch: this launch may start while the previous kernel on the stream
+    // drains (its prologue -- barrier init, tensor-memory allocation, weight staging -- touches nothing
+    // that kernel writes); griddepcontrol.wait precedes every dependent access
+    int pdl;
     void *wimg;                  // streamed-W mode: workspace for the pre-split, pre-swizzled image
     const float *bias;
     float *y;                    // [M,cout] pre-BN output (nullable)
@@ -47,6 +57,7 @@ struct TtArgs {
     const float *gamma, *beta;
     float eps;
     double count;
+    float sqrt_count;
     float *scale, *shift, *mean_out, *var_out, *out_colscale;
     // row -> (group, position, cloud) without 64-bit divisions: magic-number division by K and S,
     // filled in by launch(); valid while M < 2^31 (fastgeom = 0 falls back to long long division)
@@ -68,11 +79,16 @@ void make_fastdiv(uint32_t d, uint32_t *mul, uint32_t *shr);
 size_t wimg_bytes(int prec, int cin, int cout);
 int launch(const TtArgs &a, cudaStream_t st);
 
-// 2^e >= bound / 2^15 (e >= 0): the exact power-of-two pre-scale that keeps fp16 operands finite
-__host__ __device__ inline float f16_colscale(double gamma, double beta, double count) {
-    const double bound = (gamma < 0 ? -gamma : gamma) * sqrt(count) + (beta < 0 ? -beta : beta);
+// 2^e (e >= 0) with relu(bn(y)) / 2^e < 2^15 for every possible y: |bn(y)| <= |gamma| sqrt(count) +
+// |beta| (a sample is at most sqrt(count - 1) standard deviations from the batch mean).  Single
+// precision on purpose (fp64 is slow on this part and the staging code evaluates it per weight
+// column) with a 2 % margin for the rounding; every user -- the finalisation that divides scale /
+// shift, the weight staging and the streamed-W image -- calls this one function with the same
+// arguments, so producer and consumer always agree on the power of two.
+__host__ __device__ inline float f16_colscale_sq(float gamma, float beta, float sqrt_count) {
+    const float bound = (gamma < 0.f ? -gamma : gamma) * sqrt_count + (beta < 0.f ? -beta : beta);
     float s = 1.f;
-    while ((double)s * 32768.0 < bound && s < 1e30f) s *= 2.f;
+    while (s * 32000.f < bound && s < 1e30f) s *= 2.f;
     return s;
 }
 
@@ -89,6 +105,7 @@ struct MomentArgs {
     const float *running_mean, *running_var;  // used instead of the batch moments when non-null
     float eps;
     int c0;
+    float sqrt_M;
     uint32_t kmul, kshr, smul, sshr;  // as TtArgs (filled in by launch_moments)
     int fastgeom;
     double *partial;        // [blocks][9]
