@@ -100,8 +100,12 @@ __global__ void __launch_bounds__(kBqWarps * 32)
 ball_query_kernel(const float *__restrict__ xyz, const float *__restrict__ new_xyz, int N, int S,
                   float radius2, int K, IdxT *__restrict__ out_idx,
                   int32_t *__restrict__ empty_count) {
-    __shared__ __align__(128) float s_p[kBqChunk * 3];  // AoS xyz of the current chunk
-    __shared__ float s_n[kBqChunk];                     // |p|^2
+    // dynamic: chunk = min(N, kBqChunk) points -- [chunk*3] AoS xyz of the current chunk, then
+    // [chunk] |p|^2 (small clouds take a few KB, so the kernel co-resides with the MLP kernels)
+    extern __shared__ __align__(128) float s_dyn[];
+    const int chunk = N < kBqChunk ? ((N + 3) & ~3) : kBqChunk;
+    float *s_p = s_dyn;
+    float *s_n = s_dyn + chunk * 3;
     __shared__ __align__(8) uint64_t s_bar;
 
     const int b = blockIdx.y;
@@ -131,8 +135,8 @@ ball_query_kernel(const float *__restrict__ xyz, const float *__restrict__ new_x
     int cnt = 0;      // in-radius points found so far (may exceed K)
     int first = -1;   // lowest in-radius index
     uint32_t phase = 0;
-    for (int base = 0; base < N; base += kBqChunk) {
-        const int n = min(kBqChunk, N - base);
+    for (int base = 0; base < N; base += chunk) {
+        const int n = min(chunk, N - base);
         const float *gsrc = cloud + (size_t)base * 3;
         const uint32_t bytes = (uint32_t)n * 12u;
         // TMA bulk copy needs 16-byte aligned source and size; otherwise plain coalesced loads.
@@ -262,11 +266,13 @@ extern "C" int papc_ball_query_f32(const float *xyz, const float *new_xyz, int B
     dim3 grid(ceil_div(S, kBqWarps), B);
     ProfScope prof(as_stream(stream), "ball_query", (long long)B * S, N, nsample, 0.0,
                    12.0 * B * (N + S) + (idx_bits / 8.0) * B * S * nsample);
+    const int chunk = N < kBqChunk ? ((N + 3) & ~3) : kBqChunk;
+    const size_t smem = (size_t)chunk * 4 * sizeof(float);
     if (idx_bits == 64)
-        ball_query_kernel<int64_t><<<grid, kBqWarps * 32, 0, as_stream(stream)>>>(
+        ball_query_kernel<int64_t><<<grid, kBqWarps * 32, smem, as_stream(stream)>>>(
             xyz, new_xyz, N, S, radius2, nsample, reinterpret_cast<int64_t *>(out_idx), empty_count);
     else
-        ball_query_kernel<int32_t><<<grid, kBqWarps * 32, 0, as_stream(stream)>>>(
+        ball_query_kernel<int32_t><<<grid, kBqWarps * 32, smem, as_stream(stream)>>>(
             xyz, new_xyz, N, S, radius2, nsample, reinterpret_cast<int32_t *>(out_idx), empty_count);
     PAPC_LAUNCH_CHECK();
     return PAPC_OK;

@@ -72,7 +72,9 @@ __device__ __forceinline__ uint64_t f2mul(uint64_t a, uint64_t b) {
     return r;
 }
 
-template <int THREADS, int PPT>
+// DBG (timing experiments only, results are wrong): 1 = no cross-warp exchange, 2 = no warp redux /
+// ballot either, 4 = no centroid LDS dependency
+template <int THREADS, int PPT, int DBG = 0>
 __global__ void __launch_bounds__(THREADS)
 fps_reg_kernel(const float *__restrict__ xyz, int N, int npoint,
                const int64_t *__restrict__ start_idx, float init_dist,
@@ -150,7 +152,7 @@ fps_reg_kernel(const float *__restrict__ xyz, int N, int npoint,
     };
 
     for (int it = 0; it < npoint; ++it) {
-        const float4 c = fps_lds128f(xyz_sa + 16u * (uint32_t)far);
+        const float4 c = fps_lds128f(xyz_sa + 16u * (uint32_t)((DBG & 4) ? (it & 1023) : far));
         const uint32_t red_it = red_sa + (uint32_t)(it & 1) * (NWP * 8);
         // the pick is parked in shared memory (one predicated STS): global stores with their 64-bit
         // address arithmetic would sit on warp 0's path to the barrier in every iteration
@@ -189,15 +191,17 @@ fps_reg_kernel(const float *__restrict__ xyz, int N, int npoint,
 #pragma unroll
             for (int p = 0; p + step < PPT; p += 2 * step) tmax[p] = max(tmax[p], tmax[p + step]);
         const int best = tmax[0];
-        const int wmax = __reduce_max_sync(0xffffffffu, best);
+        const int wmax = (DBG & 2) ? best : __reduce_max_sync(0xffffffffu, best);
         // first point of this thread holding its maximum (independent of the redux result)
         unsigned eq = 0u;
 #pragma unroll
         for (int p = 0; p < PPT; ++p) eq |= (bits[p] == best ? 1u : 0u) << p;
         const int bi = __ffs(eq) - 1;
         const bool mine = best == wmax;
-        const unsigned ball = __ballot_sync(0xffffffffu, mine);
-        if (NW == 1) {
+        const unsigned ball = (DBG & 2) ? 1u : __ballot_sync(0xffffffffu, mine);
+        if (DBG & 1) {
+            far = (tid * PPT + bi + it) & 1023;
+        } else if (NW == 1) {
             const int src = __ffs(ball) - 1;  // lowest lane == lowest index
             far = __shfl_sync(0xffffffffu, tid * PPT + bi, src);
         } else {
@@ -305,12 +309,12 @@ fps_global_kernel(const float *__restrict__ xyz, int N, int npoint,
     }
 }
 
-template <int THREADS, int PPT>
+template <int THREADS, int PPT, int DBG = 0>
 static int launch_fps_reg(const float *xyz, int B, int N, int npoint, const int64_t *start,
                           float init_dist, int64_t *out_idx, float *out_new_xyz,
                           cudaStream_t st) {
     const size_t smem = (size_t)N * sizeof(float4) + (size_t)(npoint < kFpsOutCap ? npoint : kFpsOutCap) * sizeof(int);
-    auto k = fps_reg_kernel<THREADS, PPT>;
+    auto k = fps_reg_kernel<THREADS, PPT, DBG>;
     if (smem > 48 * 1024)
         PAPC_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)smem));
@@ -339,13 +343,19 @@ extern "C" int papc_fps_f32(const float *xyz, int B, int N, int npoint,
     cudaStream_t st = as_stream(stream);
     // threads x points-per-thread; PAPC_FPS_WIDE=1 selects the wider (more warps, fewer points per
     // thread) variant for the mid sizes -- A/B switch for tuning, same results either way
-    static const bool wide = [] { const char *e = getenv("PAPC_FPS_WIDE"); return e && e[0] == '1'; }();
+    static const int shape = [] { const char *e = getenv("PAPC_FPS_WIDE"); return e ? atoi(e) : 0; }();
+    const bool wide = shape == 1;
 #define FPS_GO(T, P) return launch_fps_reg<T, P>(xyz, B, N, npoint, start_idx, init_dist, out_idx, out_new_xyz, st)
     if (N <= 64) FPS_GO(32, 2);
     if (N <= 128) FPS_GO(32, 4);
     if (N <= 256) { if (wide) FPS_GO(128, 2); FPS_GO(64, 4); }
-    if (N <= 512) { if (wide) FPS_GO(256, 2); FPS_GO(128, 4); }
-    if (N <= 1024) { if (wide) FPS_GO(256, 4); FPS_GO(128, 8); }
+    if (N <= 512) { if (wide) FPS_GO(256, 2); if (shape == 2) FPS_GO(64, 8); if (shape == 3) FPS_GO(32, 16); FPS_GO(128, 4); }
+    if (N <= 1024) {
+        static const int dbg = [] { const char *e = getenv("PAPC_FPS_DBG"); return e ? atoi(e) : 0; }();
+#define FPS_DBG(D) if (dbg == D) return launch_fps_reg<128, 8, D>(xyz, B, N, npoint, start_idx, init_dist, out_idx, out_new_xyz, st)
+        FPS_DBG(1); FPS_DBG(2); FPS_DBG(3); FPS_DBG(4); FPS_DBG(7);
+#undef FPS_DBG
+        if (wide) FPS_GO(256, 4); if (shape == 2) FPS_GO(64, 16); if (shape == 3) FPS_GO(32, 32); FPS_GO(128, 8); }
     if (N <= 2048) { if (wide) FPS_GO(512, 4); FPS_GO(256, 8); }
     if (N <= 4096) { if (wide) FPS_GO(1024, 4); FPS_GO(512, 8); }
     if (N <= kFpsRegMaxN) FPS_GO(1024, 8);

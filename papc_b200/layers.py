@@ -20,6 +20,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 
 import torch
 import torch.distributed as dist
@@ -165,6 +166,60 @@ def sample_and_group_all(xyz, points):
 
 
 # ---------------------------------------------------------------------------------------------
+# Sampling overlap.  farthest_point_sample / query_ball_point of a SetAbstraction layer read only the
+# xyz coordinates, i.e. for every layer but the first the *sampled centroids* of the previous layer
+# -- available long before that layer's MLP has finished.  Each layer therefore tags the xyz tensor
+# it returns with the CUDA event recorded right after its own FPS, and a layer whose input carries
+# such a tag runs its FPS + ball query on a high-priority side stream that waits for that event
+# only; the main stream joins before the MLP.  The sampling kernels are small (one CTA per cloud, a
+# few KB of shared memory) and co-reside with the previous layer's MLP kernels.  Transparent to the
+# caller (same call sequence, same results); PAPC_OVERLAP_SAMPLING=0 switches it off.
+OVERLAP_SAMPLING = os.environ.get("PAPC_OVERLAP_SAMPLING", "1") != "0"
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    key = torch.device(device).index
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device, priority=-1)
+    return _SIDE_STREAMS[key]
+
+
+def _sample(xyz, ready, npoint, start_idx, queries):
+    """FPS + one ball query per (radius, nsample) in ``queries`` -> (new_xyz, [idx int32...], event
+    recorded right after the FPS).  Runs on the side stream when ``ready`` (the producer's event) is set.
+
+    Buffers allocated under the side stream come from that stream's pool of the caching allocator and
+    are consumed on the main stream.  No ``record_stream`` is needed (and it is expensive: deferred
+    frees): a freed block can only be handed to a LATER side-stream allocation, whose kernels wait for
+    a later layer's ``ready`` event, and that event is recorded on the main stream after every
+    main-stream consumer of the block was enqueued."""
+    dev = xyz.device
+    main = torch.cuda.current_stream(dev)
+    if ready is not None and OVERLAP_SAMPLING:
+        side = _side_stream(dev)
+        side.wait_event(ready)
+        with torch.cuda.stream(side):
+            _, new_xyz = farthest_point_sample_idx(xyz, npoint, start_idx, return_xyz=True)
+            ev = torch.cuda.Event()
+            ev.record(side)
+            idxs = [_ball_query(r, k, xyz, new_xyz, torch.int32) for r, k in queries]
+            done = torch.cuda.Event()
+            done.record(side)
+        main.wait_event(done)
+        return new_xyz, idxs, ev
+    _, new_xyz = farthest_point_sample_idx(xyz, npoint, start_idx, return_xyz=True)
+    ev = torch.cuda.Event()
+    ev.record(main)
+    idxs = [_ball_query(r, k, xyz, new_xyz, torch.int32) for r, k in queries]
+    return new_xyz, idxs, ev
+
+
+def _tag_ready(t, ev):
+    t._papc_ready = ev
+    return t
+
+
 class Conv2D:
     """Parameter holder mirroring ``paddle.nn.Conv2D(cin, cout, 1)``: weight [cout,cin,1,1], bias
     [cout].  Default init as Paddle: Normal(0, sqrt(2/fan_in)) weight, zero bias."""
@@ -378,6 +433,7 @@ class PointNetSetAbstraction(_SAMixin):
     def forward(self, xyz, points, start_idx=None):
         """xyz [B,3,N], points [B,D,N] | None -> (new_xyz [B,3,S], new_points [B,D',S])."""
         L.require_cuda(xyz, points)
+        ready = getattr(xyz, "_papc_ready", None)
         xyz = L.f32c(xyz.transpose(1, 2))                                  # :203
         feats = L.f32c(points.transpose(1, 2)) if points is not None else None  # :205
         B, N, Cc = xyz.shape
@@ -394,13 +450,17 @@ class PointNetSetAbstraction(_SAMixin):
             keep = (xyz, feats)
         else:                                                              # :213
             S = self.npoint
-            _, new_xyz = farthest_point_sample_idx(xyz, S, start_idx, return_xyz=True)
-            idx = _ball_query(self.radius, self.nsample, xyz, new_xyz, torch.int32)
+            if self.nsample > N:
+                raise ValueError(f"query_ball_point: nsample ({self.nsample}) > N ({N})")
+            new_xyz, (idx,), ev = _sample(xyz, ready, S, start_idx, [(self.radius, self.nsample)])
             src = _make_src(xyz, new_xyz, feats, idx, B, N, S, self.nsample, L.XYZ_FIRST)
             keep = (xyz, feats, new_xyz, idx)
         out = _MlpRunner(self.mlp_convs, self.mlp_bns).run(                # :214-219
             src, keep, 3 + D, B, S, self.bn_mode, dev, self.update_running_stats, self.sync_bn_group)
-        return new_xyz.transpose(1, 2), out.transpose(1, 2)               # :220-221
+        out_xyz = new_xyz.transpose(1, 2)
+        if not self.group_all:
+            _tag_ready(out_xyz, ev)
+        return out_xyz, out.transpose(1, 2)                                # :220-221
 
 
 class PointNetSetAbstractionMsg(_SAMixin):
@@ -429,6 +489,7 @@ class PointNetSetAbstractionMsg(_SAMixin):
 
     def forward(self, xyz, points, start_idx=None):
         L.require_cuda(xyz, points)
+        ready = getattr(xyz, "_papc_ready", None)
         xyz = L.f32c(xyz.transpose(1, 2))
         feats = L.f32c(points.transpose(1, 2)) if points is not None else None
         B, N, Cc = xyz.shape
@@ -437,14 +498,17 @@ class PointNetSetAbstractionMsg(_SAMixin):
             raise ValueError(f"in_channel={self.in_channel} but points has {D} channels")
         dev = xyz.device
         S = self.npoint
-        _, new_xyz = farthest_point_sample_idx(xyz, S, start_idx, return_xyz=True)   # :258
+        if max(self.nsample_list) > N:
+            raise ValueError(f"query_ball_point: nsample ({max(self.nsample_list)}) > N ({N})")
+        new_xyz, idxs, ev = _sample(xyz, ready, S, start_idx,                        # :258, :262
+                                    list(zip(self.radius_list, self.nsample_list)))
         outs = []
         for i, radius in enumerate(self.radius_list):
             K = self.nsample_list[i]
-            idx = _ball_query(radius, K, xyz, new_xyz, torch.int32)                  # :262
+            idx = idxs[i]
             src = _make_src(xyz, new_xyz, feats, idx, B, N, S, K, L.FEATS_FIRST)     # :263-267
             outs.append(_MlpRunner(self.conv_blocks[i], self.bn_blocks[i]).run(     # :271-276
                 src, (xyz, feats, new_xyz, idx), 3 + D, B, S, self.bn_mode, dev,
                 self.update_running_stats, self.sync_bn_group))
         new_points_concat = torch.cat(outs, dim=2)                                   # :280 (channels-last)
-        return new_xyz.transpose(1, 2), new_points_concat.transpose(1, 2)
+        return _tag_ready(new_xyz.transpose(1, 2), ev), new_points_concat.transpose(1, 2)

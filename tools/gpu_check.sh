@@ -51,3 +51,6 @@ if [[ "$what" == *prims* ]]; then
   PAPC_FPS_WIDE=1 timeout 300 python tools/prof_prims.py >> gpurun_out/prims.log 2>&1
   cat gpurun_out/prims.log
 fi
+if [[ "$what" == *fpsshape* ]]; then
+  for w in 0 2 3; do echo "--- PAPC_FPS_WIDE=$w"; PAPC_FPS_WIDE=$w timeout 300 python tools/prof_prims.py 2>&1 | grep -v 2048; done | tee gpurun_out/fps_shapes.log
+fi
