@@ -147,6 +147,11 @@ def time_cpu_baseline(steps, warmup, batch):
         torch.set_num_threads(cores)
     except Exception:
         pass
+    try:  # torchrun exports OMP_NUM_THREADS=1: give NumPy's BLAS all the host cores back
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=cores)
+    except Exception:
+        pass
     xyz = synth.clouds(batch, N_POINTS, seed=0)
     starts = [synth.fps_start(batch, N_POINTS, seed=1), np.zeros(batch, np.int64), None]
     params = [synth.mlp_params(c[3], c[4], seed=2 + i) for i, c in enumerate(SA_CFG)]

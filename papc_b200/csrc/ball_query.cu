@@ -3,7 +3,8 @@
 //
 // query_ball_point never materialises the reference's [B,S,N] distance matrix nor sorts it:
 // "the nsample lowest in-radius indices, ascending" is an in-order scan with a warp ballot +
-// prefix popcount compaction.  One warp per query point; all warps of a CTA share one cloud
+// prefix popcount compaction.  One warp per query point (kBqQPW queries in turn);
+// all warps of a CTA share one cloud
 // whose xyz block is staged into shared memory by a TMA bulk copy (cp.async.bulk, completion
 // on an mbarrier) -- chunked, so any N works with a fixed 28 KB of shared memory.
 #include "common.cuh"
@@ -93,6 +94,7 @@ gather_rows_kernel(const float *__restrict__ points, const int64_t *__restrict__
 
 // ------------------------------------------------------------------ query_ball_point
 constexpr int kBqWarps = 8;
+constexpr int kBqQPW = 1;       // queries per warp (4 measured slower: fewer, longer warps; scanning, not staging, is the cost)
 constexpr int kBqChunk = 2048;  // points per shared-memory stage: 24 KB xyz + 8 KB |p|^2
 
 template <typename IdxT>
@@ -112,19 +114,25 @@ ball_query_kernel(const float *__restrict__ xyz, const float *__restrict__ new_x
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int s = blockIdx.x * kBqWarps + warp;
-    const bool active = s < S;
+    const int s0 = (blockIdx.x * kBqWarps + warp) * kBqQPW;  // this warp's queries s0 .. s0+QPW-1
     const float *cloud = xyz + (size_t)b * N * 3;
 
-    float qx = 0.f, qy = 0.f, qz = 0.f, qn = 0.f;
-    if (active) {
-        const float *q = new_xyz + ((size_t)b * S + s) * 3;
-        qx = q[0];
-        qy = q[1];
-        qz = q[2];
-        qn = sq3(qx, qy, qz);
+    float qx[kBqQPW], qy[kBqQPW], qz[kBqQPW], qn[kBqQPW];
+    int cnt[kBqQPW];    // in-radius points found so far (may exceed K)
+    int first[kBqQPW];  // lowest in-radius index
+#pragma unroll
+    for (int i = 0; i < kBqQPW; ++i) {
+        qx[i] = qy[i] = qz[i] = qn[i] = 0.f;
+        cnt[i] = 0;
+        first[i] = -1;
+        if (s0 + i < S) {
+            const float *q = new_xyz + ((size_t)b * S + s0 + i) * 3;
+            qx[i] = q[0];
+            qy[i] = q[1];
+            qz[i] = q[2];
+            qn[i] = sq3(qx[i], qy[i], qz[i]);
+        }
     }
-    IdxT *out = out_idx + ((size_t)b * S + (active ? s : 0)) * K;
 
     if (tid == 0) {
         mbar_init(&s_bar, 1);
@@ -132,8 +140,6 @@ ball_query_kernel(const float *__restrict__ xyz, const float *__restrict__ new_x
     }
     __syncthreads();
 
-    int cnt = 0;      // in-radius points found so far (may exceed K)
-    int first = -1;   // lowest in-radius index
     uint32_t phase = 0;
     for (int base = 0; base < N; base += chunk) {
         const int n = min(chunk, N - base);
@@ -156,31 +162,37 @@ ball_query_kernel(const float *__restrict__ xyz, const float *__restrict__ new_x
             s_n[j] = sq3(s_p[j * 3 + 0], s_p[j * 3 + 1], s_p[j * 3 + 2]);
         __syncthreads();
 
-        if (active && cnt < K) {
+#pragma unroll
+        for (int i = 0; i < kBqQPW; ++i) {
+            if (s0 + i >= S || cnt[i] >= K) continue;
+            IdxT *out = out_idx + ((size_t)b * S + s0 + i) * K;
             for (int j0 = 0; j0 < n; j0 += 32) {
                 const int j = j0 + lane;
                 bool in = false;
                 if (j < n) {
-                    const float d = sqdist_expanded(qx, qy, qz, qn, s_p[j * 3 + 0], s_p[j * 3 + 1],
+                    const float d = sqdist_expanded(qx[i], qy[i], qz[i], qn[i], s_p[j * 3 + 0], s_p[j * 3 + 1],
                                                     s_p[j * 3 + 2], s_n[j]);
                     in = !(d > radius2);  // layers.py:112 masks "> r^2" OUT
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, in);
                 if (m) {
-                    if (first < 0) first = base + j0 + __ffs(m) - 1;
-                    const int pos = cnt + __popc(m & ((1u << lane) - 1u));
+                    if (first[i] < 0) first[i] = base + j0 + __ffs(m) - 1;
+                    const int pos = cnt[i] + __popc(m & ((1u << lane) - 1u));
                     if (in && pos < K) out[pos] = (IdxT)(base + j);
-                    cnt += __popc(m);
-                    if (cnt >= K) break;
+                    cnt[i] += __popc(m);
+                    if (cnt[i] >= K) break;
                 }
             }
         }
         __syncthreads();  // everyone done with s_p / s_n before the next stage overwrites it
     }
-    if (active) {
-        const IdxT pad = (IdxT)(cnt > 0 ? first : N);  // empty ball: N, as the sort leaves it
-        for (int k = min(cnt, K) + lane; k < K; k += 32) out[k] = pad;
-        if (cnt == 0 && lane == 0 && empty_count != nullptr) atomicAdd(empty_count, 1);
+#pragma unroll
+    for (int i = 0; i < kBqQPW; ++i) {
+        if (s0 + i >= S) continue;
+        IdxT *out = out_idx + ((size_t)b * S + s0 + i) * K;
+        const IdxT pad = (IdxT)(cnt[i] > 0 ? first[i] : N);  // empty ball: N, as the sort leaves it
+        for (int k = min(cnt[i], K) + lane; k < K; k += 32) out[k] = pad;
+        if (cnt[i] == 0 && lane == 0 && empty_count != nullptr) atomicAdd(empty_count, 1);
     }
 }
 
@@ -263,7 +275,7 @@ extern "C" int papc_ball_query_f32(const float *xyz, const float *new_xyz, int B
     if (B == 0 || S == 0) return PAPC_OK;
     if (!xyz || !new_xyz || !out_idx) return PAPC_EINVAL;
     if (B > 65535) return PAPC_EUNSUPPORTED;
-    dim3 grid(ceil_div(S, kBqWarps), B);
+    dim3 grid(ceil_div(S, kBqWarps * kBqQPW), B);
     ProfScope prof(as_stream(stream), "ball_query", (long long)B * S, N, nsample, 0.0,
                    12.0 * B * (N + S) + (idx_bits / 8.0) * B * S * nsample);
     const int chunk = N < kBqChunk ? ((N + 3) & ~3) : kBqChunk;

@@ -69,9 +69,16 @@ static_assert(kEpiWarps == 4 || kEpiWarps == 8, "epilogue warps: one or two per 
     do {                                                                                   \
         if ((a).clk != nullptr && blockIdx.x < 2) (a).clk[blockIdx.x * 16 + (e)] = clock64(); \
     } while (0)
+// per-tile stamps of CTA 0 (local tiles 8..23): [48 + (tl-8)*8 + e]
+#define TT_TCLK(a, tl, e)                                                                           \
+    do {                                                                                            \
+        if ((a).clk != nullptr && blockIdx.x == 0 && (tl) >= 8u && (tl) < 24u)                      \
+            (a).clk[48 + ((tl) - 8u) * 8 + (e)] = clock64();                                        \
+    } while (0)
 #else
 #define TT_DBG(a, bit) 0
 #define TT_CLK(a, e) do { } while (0)
+#define TT_TCLK(a, tl, e) do { } while (0)
 #endif
 #ifndef PAPC_TT_PROD_WARPS
 #define PAPC_TT_PROD_WARPS 8
@@ -432,6 +439,7 @@ mlp_layer_tt_kernel(const TtArgs a) {
             tc_fence_after();
             if (tid == 0 && tl == 0) TT_CLK(a, 5);
             if (tid == 0 && tl == 1) TT_CLK(a, 11);
+            if (tid == 0) TT_TCLK(a, tl, 4);   // epilogue: accumulator ready
             uint64_t s2 = 0ull, q2 = 0ull;     // packed (even rows, odd rows) running sums
             float mx = -INFINITY, mn = INFINITY;
 #pragma unroll 1
@@ -445,6 +453,7 @@ mlp_layer_tt_kernel(const TtArgs a) {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(acc_empty + buf);
+                    if (tid == 0) TT_TCLK(a, tl, 5);   // epilogue: buffer handed back
                 }
                 const uint32_t xs = smem_u32(smem) + SmemLayout::xyz + 16 * ((tl & 3) * kTile + blk * 32);
                 float *yp = a.y + ((size_t)m0 + blk * 32) * ystride + cg;   // dereferenced only if do_y
@@ -499,7 +508,8 @@ mlp_layer_tt_kernel(const TtArgs a) {
                     else body(std::false_type{}, std::false_type{});
                 }
                 // pooled groups of K rows end at multiples of K (K in {32, 64, 128})
-                if (POOL && ((blk + 1) * 32) % a.K == 0 && kshift != 7) {
+                // (K is 32 / 64 / 128 here: a mask, not a runtime integer division per block)
+                if (POOL && kshift != 7 && ((((blk + 1) * 32) & (a.K - 1)) == 0)) {
                     if (do_pool && nr > 0) {
                         const long long g = ((m0 + blk * 32) >> kshift);
                         a.pool_max[g * a.cout + cg] = mx;
@@ -527,11 +537,14 @@ mlp_layer_tt_kernel(const TtArgs a) {
                     a.pool_min[g * a.cout + cg] = mn;
                 }
             }
+            if (tid == 0) TT_TCLK(a, tl, 6);   // epilogue: tile done
             float sa, sb, qa, qb;
             unpack2(s2, sa, sb);
             unpack2(q2, qa, qb);
-            acc_s += (double)sa + (double)sb;
-            acc_q += (double)qa + (double)qb;
+            // one fp64 add per quantity and tile (the fp64 pipe is narrow; sa + sb in fp32 costs one
+            // rounding at 2^-24 relative, far inside the statistic's own fp32 accumulation error)
+            acc_s += (double)(sa + sb);
+            acc_q += (double)(qa + qb);
         }
         if (tid == 0) TT_CLK(a, 6);
         if (kEpiHalves == 2) {  // fold the two halves' statistics (fixed order -> deterministic)
@@ -570,6 +583,7 @@ mlp_layer_tt_kernel(const TtArgs a) {
             const uint32_t buf = tl & 1;
             mbar_wait(acc_empty + buf, ((tl >> 1) & 1) ^ 1);
             tc_fence_after();
+            if (lane == 0) TT_TCLK(a, tl, 2);   // MMA: accumulator buffer free
             const uint32_t d_tmem = tmem_base + kColAcc + buf * kTile;
             for (int c = 0; c < KC; ++c, ++it) {
                 const uint32_t s = it % kStages;
@@ -614,8 +628,13 @@ mlp_layer_tt_kernel(const TtArgs a) {
                     mma_commit(x_empty + s);                       // chunk reusable once these MMAs have read it
                     if (c == KC - 1) mma_commit(acc_full + buf);   // accumulator complete
                     if (it == 0) TT_CLK(a, 4);
+                    if (c == KC - 1) TT_TCLK(a, tl, 3);   // MMA: last chunk issued + committed
                 }
                 __syncwarp();
+            }
+            if (TT_DBG(a, 64)) {  // triage: the issuer itself waits for the tile's MMAs to complete
+                mbar_wait(acc_full + buf, (tl >> 1) & 1);
+                if (lane == 0) TT_TCLK(a, tl, 7);
             }
         }
     } else {
@@ -827,6 +846,7 @@ mlp_layer_tt_kernel(const TtArgs a) {
                     }
                 }
             }
+            if (ptid == 0 && c == 0) TT_TCLK(a, ptl, 0);   // producer: first chunk of the tile computed
             mbar_wait(x_empty + s, ((it / kStages) & 1) ^ 1);
             const uint32_t stage = sm + SmemLayout::ring + s * kStageBytes;
             if (WMODE == 1 && ptid == 0) {
@@ -863,6 +883,7 @@ mlp_layer_tt_kernel(const TtArgs a) {
             fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
             __syncwarp();
             if (lane == 0) mbar_arrive(x_full + s);
+            if (ptid == 0 && c == KC - 1) TT_TCLK(a, ptl, 1);  // producer: last chunk of the tile published
             if (ptid == 0 && it == 0) TT_CLK(a, 3);
             if (ptid == 0 && it == 1) TT_CLK(a, 12);
             if (ptid == 0) TT_CLK(a, 10);
@@ -974,13 +995,21 @@ mlp_layer_tt_kernel(const TtArgs a) {
                 }
                 __syncthreads();
             }
+            // fp64 division and square root are long software sequences on a slow pipe and this is the
+            // kernel's serial tail: reciprocal of the count from the host, 1/sqrt by two Newton steps
+            // from the fp32 estimate (full double accuracy)
+            const double inv_count = a.inv_count;
             for (int ch = tid; ch < a.cout; ch += kThreads) {
-                const double mean = all[ch] / a.count;
-                double var = all[a.cout + ch] / a.count - mean * mean;  // biased, as Paddle's training BN
+                const double mean = all[ch] * inv_count;
+                double var = all[a.cout + ch] * inv_count - mean * mean;  // biased, as Paddle's training BN
                 var = var > 0.0 ? var : 0.0;
                 const double g = a.gamma ? (double)a.gamma[ch] : 1.0;
                 const double b = a.beta ? (double)a.beta[ch] : 0.0;
-                const double sc = g / sqrt(var + (double)a.eps);
+                const double ve = var + (double)a.eps;
+                double rs = (double)rsqrtf((float)ve);
+                rs = rs * (1.5 - 0.5 * ve * rs * rs);
+                rs = rs * (1.5 - 0.5 * ve * rs * rs);
+                const double sc = g * rs;
                 float cs = 1.f;
                 if (a.out_colscale != nullptr) {
                     cs = f16_colscale_sq(a.gamma ? a.gamma[ch] : 1.f, a.beta ? a.beta[ch] : 0.f, a.sqrt_count);
@@ -1026,27 +1055,48 @@ point_moments_kernel(const MomentArgs a) {
         double dacc[9];
 #pragma unroll
         for (int i = 0; i < 9; ++i) dacc[i] = 0.0;
-        int n_in_acc = 0;
-        for (long long row = (long long)blockIdx.x * kMomThreads + tid; row < a.M;
-             row += (long long)gridDim.x * kMomThreads) {
-            const RowGeom rg = row_geom(row, a);
-            int n = a.idx != nullptr ? __ldg(a.idx + row) : rg.k;
-            n = min(max(n, 0), a.N - 1);
-            const float *q = a.xyz + (rg.bN + n) * 3;
-            float px = __ldg(q), py = __ldg(q + 1), pz = __ldg(q + 2);
-            if (a.new_xyz != nullptr) {
-                const float *cc = a.new_xyz + (long long)rg.g * 3;
-                px = __fsub_rn(px, __ldg(cc));
-                py = __fsub_rn(py, __ldg(cc + 1));
-                pz = __fsub_rn(pz, __ldg(cc + 2));
+        // four rows per trip, their dependent load chains (index -> point, centroid) issued together;
+        // the fp32 run length stays bounded (flush to fp64 every 4 trips = 16 rows)
+        constexpr int R = 4;
+        const long long stride = (long long)gridDim.x * kMomThreads;
+        int trips = 0;
+        for (long long row0 = (long long)blockIdx.x * kMomThreads + tid; row0 < a.M; row0 += R * stride) {
+            int n[R];
+            RowGeom rg[R];
+            bool ok[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const long long row = row0 + r * stride;
+                ok[r] = row < a.M;
+                rg[r] = row_geom(ok[r] ? row : 0, a);
+                n[r] = (a.idx != nullptr && ok[r]) ? __ldg(a.idx + row) : rg[r].k;
             }
-            acc[0] += px; acc[1] += py; acc[2] += pz;
-            acc[3] = fmaf(px, px, acc[3]); acc[4] = fmaf(px, py, acc[4]); acc[5] = fmaf(px, pz, acc[5]);
-            acc[6] = fmaf(py, py, acc[6]); acc[7] = fmaf(py, pz, acc[7]); acc[8] = fmaf(pz, pz, acc[8]);
-            if (++n_in_acc == 16) {  // bound the fp32 run length
+            float px[R], py[R], pz[R], cx[R], cy[R], cz[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int nn = min(max(n[r], 0), a.N - 1);
+                const float *q = a.xyz + (rg[r].bN + nn) * 3;
+                px[r] = __ldg(q); py[r] = __ldg(q + 1); pz[r] = __ldg(q + 2);
+                cx[r] = cy[r] = cz[r] = 0.f;
+                if (a.new_xyz != nullptr) {
+                    const float *cc = a.new_xyz + (long long)rg[r].g * 3;
+                    cx[r] = __ldg(cc); cy[r] = __ldg(cc + 1); cz[r] = __ldg(cc + 2);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (!ok[r]) continue;
+                const float x = a.new_xyz != nullptr ? __fsub_rn(px[r], cx[r]) : px[r];
+                const float y = a.new_xyz != nullptr ? __fsub_rn(py[r], cy[r]) : py[r];
+                const float z = a.new_xyz != nullptr ? __fsub_rn(pz[r], cz[r]) : pz[r];
+                acc[0] += x; acc[1] += y; acc[2] += z;
+                acc[3] = fmaf(x, x, acc[3]); acc[4] = fmaf(x, y, acc[4]); acc[5] = fmaf(x, z, acc[5]);
+                acc[6] = fmaf(y, y, acc[6]); acc[7] = fmaf(y, z, acc[7]); acc[8] = fmaf(z, z, acc[8]);
+            }
+            if (++trips == 4) {
 #pragma unroll
                 for (int i = 0; i < 9; ++i) { dacc[i] += (double)acc[i]; acc[i] = 0.f; }
-                n_in_acc = 0;
+                trips = 0;
             }
         }
 #pragma unroll
@@ -1208,8 +1258,8 @@ int launch(const TtArgs &a_in, cudaStream_t st) {
     static unsigned long long *d_clk = nullptr;
     const bool want_clk = getenv("PAPC_TT_CLK") != nullptr;
     if (want_clk) {
-        if (d_clk == nullptr) cudaMalloc(&d_clk, 48 * sizeof(unsigned long long));
-        cudaMemsetAsync(d_clk, 0, 48 * sizeof(unsigned long long), st);
+        if (d_clk == nullptr) cudaMalloc(&d_clk, 176 * sizeof(unsigned long long));
+        cudaMemsetAsync(d_clk, 0, 176 * sizeof(unsigned long long), st);
         cudaMemsetAsync(d_clk + 44, 0xff, sizeof(unsigned long long), st);  // atomicMin target
         a.clk = d_clk;
     }
@@ -1219,6 +1269,7 @@ int launch(const TtArgs &a_in, cudaStream_t st) {
     a.fastgeom = a.M < (1LL << 31) && a.K >= 1 && a.S >= 1;
     make_fastdiv((uint32_t)(a.K >= 1 ? a.K : 1), &a.kmul, &a.kshr);
     make_fastdiv((uint32_t)(a.S >= 1 ? a.S : 1), &a.smul, &a.sshr);
+    a.inv_count = a.count > 0.0 ? 1.0 / a.count : 0.0;
     const bool streamed = a.cin > tmem_k(a.prec);
     const int nt = ceil_div(a.cout, kTile);
     {
@@ -1262,7 +1313,7 @@ int launch(const TtArgs &a_in, cudaStream_t st) {
     }
 #ifdef PAPC_TT_TRIAGE
     if (want_clk && rc == PAPC_OK) {
-        unsigned long long h[48];
+        unsigned long long h[176];
         cudaStreamSynchronize(st);
         cudaMemcpy(h, d_clk, sizeof(h), cudaMemcpyDeviceToHost);
         auto us = [&](int slot, int e) { return h[slot * 16 + e] ? (double)(h[slot * 16 + e] - h[slot * 16]) / 1965.0 : -1.0; };
@@ -1272,6 +1323,16 @@ int launch(const TtArgs &a_in, cudaStream_t st) {
                 a.mode, a.prec, a.M, a.cin, a.cout, grid, us(0, 1), us(0, 2), us(0, 3), us(0, 12), us(0, 4), us(0, 5),
                 us(0, 11), us(0, 10), us(0, 6), us(0, 7), us(0, 8), h[32 + 9],
                 h[32 + 7] ? (double)(h[32 + 8] - h[32 + 7]) / 1965.0 : -1.0, 0.0);
+        if (getenv("PAPC_TT_TILECLK") != nullptr) {
+            fprintf(stderr, "[tt tile] us rel. CTA0 entry: prod_ready prod_pub | mma_accfree mma_commit | epi_accfull epi_release epi_done\n");
+            for (int t = 0; t < 16; ++t) {
+                const unsigned long long *q = h + 48 + t * 8;
+                if (q[3] == 0) continue;
+                auto u = [&](int e) { return q[e] ? (double)(q[e] - h[0]) / 1965.0 : -1.0; };
+                fprintf(stderr, "[tt tile] %2d: %7.2f %7.2f | %7.2f %7.2f (done %7.2f) | %7.2f %7.2f %7.2f\n", t + 8, u(0), u(1), u(2),
+                        u(3), u(7), u(4), u(5), u(6));
+            }
+        }
         fprintf(stderr, "[tt clk]   globaltimer: first entry -> last exit %.2f us, longest CTA %.2f us, mean CTA %.2f us\n",
                 (double)(h[45] - h[44]) / 1e3, (double)h[46] / 1e3, (double)h[47] / 1e3 / grid);
     }
@@ -1280,7 +1341,7 @@ int launch(const TtArgs &a_in, cudaStream_t st) {
 }
 
 int moment_blocks(long long M) {
-    long long b = ceil_div<long long>(M, 2048);
+    long long b = ceil_div<long long>(M, 1024);
     if (b < 1) b = 1;
     if (b > 2LL * kNumSMs) b = 2LL * kNumSMs;
     return (int)b;

@@ -57,6 +57,7 @@ struct TtArgs {
     const float *gamma, *beta;
     float eps;
     double count;
+    double inv_count;  // 1 / count (filled in by launch())
     float sqrt_count;
     float *scale, *shift, *mean_out, *var_out, *out_colscale;
     // row -> (group, position, cloud) without 64-bit divisions: magic-number division by K and S,
