@@ -304,24 +304,51 @@ def run_ours(args):
     hbm_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     flops_cloud, _ = flops_per_cloud()
     step_ms = total_ms / args.steps
-    dom = max(kernels, key=lambda k: k["ms_per_step"])
-    traffic = lookup_traffic(dom)
-    if dom["flops"] > 0:
-        ach = dom["flops"] / (dom["ms"] / 1e3) / 1e12
+    # the dominant KERNEL = the kernel function with the largest share of the step, all its launches
+    # together (mlp_layer_tt_kernel runs 8 times per step on different layer shapes)
+    fams = {}
+    for k in kernels:
+        f = fams.setdefault(k["name"].split("<")[0], {"ms": 0.0, "launches": 0.0, "flops": 0.0, "bytes": 0.0,
+                                                      "traffic": 0.0, "traffic_ok": True, "members": []})
+        f["ms"] += k["ms_per_step"]
+        f["launches"] += k["per_step"]
+        f["flops"] += k["flops"] * k["per_step"]
+        f["bytes"] += k["bytes"] * k["per_step"]
+        t = lookup_traffic(k)
+        if t is None:
+            f["traffic_ok"] = False
+        else:
+            f["traffic"] += t * k["per_step"]
+        f["members"].append(k)
+    fam_name, fam = max(fams.items(), key=lambda kv: kv[1]["ms"])
+    dom = max(fam["members"], key=lambda k: k["ms_per_step"])
+    avg_ms = fam["ms"] / fam["launches"]
+    traffic = fam["traffic"] / fam["launches"] if fam["traffic_ok"] else None
+    sass = {"mlp_tt": "papc::tt::mlp_layer_tt_kernel (tcgen05 grouped-MLP layer: producers -> UMMA -> fused BN-stat / "
+                      "max-pool epilogue)", "fps_reg": "papc::fps_reg_kernel", "ball_query": "papc::ball_query_kernel"}
+    if fam["flops"] > 0:
+        ach = fam["flops"] / (fam["ms"] / 1e3) / 1e12
         roofline = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
                     "frac": ach / peak_tf, "traffic": traffic, "peak_source": peak_src,
-                    "note": "achieved = algorithmic 2*M*cin*cout per launch / live CUDA-event time; the fp32-parity "
-                            "operand split issues 3 tensor-core products per algorithmic product, so frac <= 1/3"}
+                    "note": "achieved = algorithmic 2*M*cin*cout of the kernel's launches / their live CUDA-event time "
+                            "(average launch); the fp32-parity operand split issues 3 tensor-core products per "
+                            "algorithmic product, so frac <= 1/3 of the measured bf16 peak"}
     else:
-        ach = dom["bytes"] / (dom["ms"] / 1e3) / 1e9
+        ach = fam["bytes"] / (fam["ms"] / 1e3) / 1e9
         roofline = {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
                     "traffic": traffic, "peak_source": hbm_src}
     roofline.update({
-        "kernel": dom["name"], "shape": {"M": dom["M"], "cin": dom["cin"], "cout": dom["cout"]},
-        "avg_launch_ms": dom["ms"], "launches_per_step": dom["per_step"],
-        "share_of_step": dom["ms_per_step"] / step_ms,
-        "algorithmic_flops_per_launch": dom["flops"], "algorithmic_bytes_per_launch": dom["bytes"],
-        "hbm_gbs_algorithmic": dom["bytes"] / (dom["ms"] / 1e3) / 1e9, "hbm_peak_gbs": hbm,
+        "kernel": sass.get(fam_name, fam_name), "avg_launch_ms": avg_ms, "launches_per_step": fam["launches"],
+        "share_of_step": fam["ms"] / step_ms,
+        "algorithmic_flops_per_launch": fam["flops"] / fam["launches"],
+        "algorithmic_bytes_per_launch": fam["bytes"] / fam["launches"],
+        "hbm_gbs_algorithmic": fam["bytes"] / (fam["ms"] / 1e3) / 1e9, "hbm_peak_gbs": hbm,
+        "largest_launch": {"name": dom["name"], "M": dom["M"], "cin": dom["cin"], "cout": dom["cout"],
+                           "avg_ms": dom["ms"], "tflops": dom["flops"] / (dom["ms"] / 1e3) / 1e12 if dom["flops"] else None,
+                           "traffic": lookup_traffic(dom)},
+        "fps": next(({"avg_ms": k["ms"], "ns_per_iteration": k["ms"] * 1e6 / max(k["cin"], 1),
+                      "note": "latency bound: npoint dependent argmax steps per cloud, one CTA per cloud"}
+                     for k in sorted(kernels, key=lambda k: -k["ms"]) if k["name"] == "fps_reg"), None),
         "kernels": [{"name": k["name"], "M": k["M"], "cin": k["cin"], "cout": k["cout"],
                      "launches_per_step": k["per_step"], "avg_ms": round(k["ms"], 5),
                      "share_of_step": round(k["ms_per_step"] / step_ms, 4),

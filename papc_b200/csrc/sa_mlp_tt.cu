@@ -926,13 +926,17 @@ mlp_layer_tt_kernel(const TtArgs a) {
                 if (ti < tiles_m) { issue(ti, ci, n); advance(ti, ci); }
                 cp_async_commit();
             }
+            // The next chunk's copies are issued AFTER this chunk has been processed: process() ends in
+            // fence.proxy.async (a CTA-scope membar underneath), which waits for the thread's outstanding
+            // cp.async traffic -- with freshly issued copies in flight every fence would cost a full
+            // global-memory round trip.  Issued here they have a whole chunk period to land.
             uint32_t i = 0;
             while (tp < tiles_m) {
-                if (ti < tiles_m) { issue(ti, ci, (int)((i + R - 1) % R)); advance(ti, ci); }
-                cp_async_commit();              // (possibly empty) group: keeps the group count uniform
-                cp_async_wait<R - 1>();         // chunk i has landed (this thread's own copies)
+                cp_async_wait<(R >= 2 ? R - 2 : 0)>();  // chunk i has landed (this thread's own copies)
                 process(tp, cp, (int)(i % R));
                 advance(tp, cp);
+                if (ti < tiles_m) { issue(ti, ci, (int)((i + R - 1) % R)); advance(ti, ci); }
+                cp_async_commit();              // (possibly empty) group: keeps the group count uniform
                 ++i;
             }
         }

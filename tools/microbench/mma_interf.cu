@@ -17,6 +17,7 @@ __host__ __device__ constexpr uint32_t idesc_of(int fmt, int n) {
 }
 
 __global__ void __launch_bounds__(544, 1) k(int reps, int mode, const float *g, long long *out, float *sink) {
+    long long ld_cyc = 0, ld_n = 0;
     extern __shared__ uint8_t raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
     __shared__ uint64_t bar;
@@ -69,9 +70,13 @@ __global__ void __launch_bounds__(544, 1) k(int reps, int mode, const float *g, 
             }
             if ((mode & 4) && warp < 8) {
                 uint32_t r[32];
+                const long long c0 = clock64();
                 tmem_ld32_nowait(tb + ((uint32_t)((warp & 3) * 32) << 16) + 384 + (it & 1) * 32, r);
                 tmem_wait_ld();
                 acc += __uint_as_float(r[0]) + __uint_as_float(r[31]);
+                ld_cyc += clock64() - c0;
+                ++ld_n;
+                for (int q = 0; q < 100; ++q) acc = fmaf(acc, 1.0001f, 0.5f);  // ~0.2 us between loads
             }
             if ((mode & 8)) {
 #pragma unroll
@@ -80,6 +85,7 @@ __global__ void __launch_bounds__(544, 1) k(int reps, int mode, const float *g, 
             ++it;
         }
         if (acc == 12345.f) sink[tid] = acc;
+        if (blockIdx.x == 0 && tid == 0 && ld_n > 0) { out[1] = ld_cyc; out[2] = ld_n; }
     }
     tc_fence_before(); __syncthreads(); tc_fence_after();
     if (warp == 16) tmem_dealloc<512>(tb);
@@ -87,19 +93,21 @@ __global__ void __launch_bounds__(544, 1) k(int reps, int mode, const float *g, 
 
 int main() {
     long long *d_out; float *sink, *g;
-    cudaMalloc(&d_out, 8); cudaMalloc(&sink, 4096); cudaMalloc(&g, (size_t)148 * 65536 * 16);
+    cudaMalloc(&d_out, 24); cudaMemset(d_out, 0, 24); cudaMalloc(&sink, 4096); cudaMalloc(&g, (size_t)148 * 65536 * 16);
     cudaMemset(g, 0, (size_t)148 * 65536 * 16);
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000);
-    const int modes[] = {0, 1, 2, 3, 4, 8, 16, 19, 32 + 2, 35, 7, 23, 31, 63};
+    const int modes[] = {4, 4 + 1, 4 + 2, 4 + 2 + 32, 4 + 16, 4 + 1 + 2 + 16, 4 + 1 + 2 + 16 + 32, 4 + 8};
     for (int m : modes) {
         const int reps = 12 * 512;
         k<<<148, 544, 200000>>>(reps, m, g, d_out, sink);
         k<<<148, 544, 200000>>>(reps, m, g, d_out, sink);
         cudaError_t e = cudaDeviceSynchronize();
-        long long h = 0;
-        cudaMemcpy(&h, d_out, 8, cudaMemcpyDeviceToHost);
-        printf("mode %2d (%s%s%s%s%s%s): %8.1f cycles/MMA  (%s)\n", m, m & 1 ? "LDS " : "", m & 2 ? "STS " : "", m & 32 ? "fence " : "",
-               m & 16 ? "cp.async " : "", m & 4 ? "tmem.ld " : "", m & 8 ? "FFMA " : "", (double)h / reps, cudaGetErrorString(e));
+        long long h[3] = {0, 0, 0};
+        cudaMemcpy(h, d_out, 24, cudaMemcpyDeviceToHost);
+        printf("mode %2d (%s%s%s%s%s%s): %8.1f cycles/MMA   tmem ld+wait %7.1f cycles (%lld)  (%s)\n", m, m & 1 ? "LDS " : "",
+               m & 2 ? "STS " : "", m & 32 ? "fence " : "", m & 16 ? "cp.async " : "", m & 4 ? "tmem.ld " : "", m & 8 ? "FFMA " : "",
+               (double)h[0] / reps, h[2] ? (double)h[1] / h[2] : 0.0, h[2], cudaGetErrorString(e));
+        cudaMemset(d_out, 0, 24);
     }
     return 0;
 }
