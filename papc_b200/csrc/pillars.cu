@@ -106,59 +106,85 @@ vox_cell_kernel(const float *__restrict__ points, int N, int F, const VoxGeom g,
     pt_cell[i] = cell;
 }
 
+// Exclusive prefix of one value per thread over a 1024-thread CTA (32 warps): returns the prefix,
+// *total receives the CTA sum.  Two __syncthreads; s_warp is a 32-int scratch.
+__device__ __forceinline__ int block_excl_scan_1024(int v, int *s_warp, int *total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    __syncthreads();  // previous use of s_warp is over
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    const int wsum = s_warp[lane];
+    int wincl = wsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, wincl, o);
+        if (lane >= o) wincl += t;
+    }
+    *total = __shfl_sync(0xffffffffu, wincl, 31);
+    const int warp_excl = __shfl_sync(0xffffffffu, wincl - wsum, warp);
+    return warp_excl + incl - v;
+}
+
+constexpr int kScanEPT = 16;  // consecutive elements per thread and pass: all their loads in flight at once
+
 // Single CTA: in-order exclusive scan of the opener flags; writes voxel ids of openers, the
-// coordinates of the first max_voxels voxels, the break position and the opener total.
+// coordinates of the first max_voxels voxels, the break position and the opener total.  Each thread
+// owns kScanEPT CONSECUTIVE points per pass (two batches of independent loads, a register prefix, one
+// block scan of the thread totals), so 20 000 points are two passes instead of twenty dependent
+// load -> scan -> barrier rounds.
 __global__ void __launch_bounds__(1024)
 vox_scan_kernel(const int32_t *__restrict__ pt_cell, const int32_t *__restrict__ cell_first, int N,
                 const VoxGeom g, int max_voxels, int32_t *__restrict__ pt_vid,
                 int32_t *__restrict__ coors, int32_t *__restrict__ meta) {
     __shared__ int s_warp[32];
-    __shared__ int s_carry;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_carry = 0;
-    __syncthreads();
-    for (int base = 0; base < N; base += 1024) {
-        const int i = base + tid;
-        int cell = -1, flag = 0;
-        if (i < N) {
-            cell = pt_cell[i];
-            flag = (cell >= 0 && cell_first[cell] == i) ? 1 : 0;
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, flag);
-        const int in_warp = __popc(m & ((1u << lane) - 1u));
-        if (lane == 0) s_warp[warp] = __popc(m);
-        __syncthreads();
-        int wsum = s_warp[lane];  // 32 warps
-        int wexcl = wsum;
+    const int tid = threadIdx.x;
+    int carry = 0;
+    for (int base = 0; base < N; base += 1024 * kScanEPT) {
+        const int i0 = base + tid * kScanEPT;
+        int cell[kScanEPT], first[kScanEPT];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, wexcl, o);
-            if (lane >= o) wexcl += t;
+        for (int e = 0; e < kScanEPT; ++e) cell[e] = (i0 + e < N) ? pt_cell[i0 + e] : -1;
+#pragma unroll
+        for (int e = 0; e < kScanEPT; ++e) first[e] = cell[e] >= 0 ? cell_first[cell[e]] : -1;
+        int local = 0;
+        unsigned flags = 0u;
+#pragma unroll
+        for (int e = 0; e < kScanEPT; ++e) {
+            const bool f = cell[e] >= 0 && first[e] == i0 + e;
+            flags |= (f ? 1u : 0u) << e;
+            local += f ? 1 : 0;
         }
-        const int block_total = __shfl_sync(0xffffffffu, wexcl, 31);
-        const int my_warp_excl = __shfl_sync(0xffffffffu, wexcl - wsum, warp);
-        const int carry = s_carry;
-        const int vid = carry + my_warp_excl + in_warp;
-        if (i < N) {
-            pt_vid[i] = vid;
-            if (flag) {
-                if (vid < max_voxels) {
-                    const int c2 = cell % g.shape[2];
-                    const int c1 = (cell / g.shape[2]) % g.shape[1];
-                    const int c0 = cell / (g.shape[2] * g.shape[1]);
-                    coors[vid * 3 + 0] = c0;
-                    coors[vid * 3 + 1] = c1;
-                    coors[vid * 3 + 2] = c2;
-                } else if (vid == max_voxels) {
-                    meta[0] = i;  // the reference breaks here (pc_ops.py:44-45)
+        int total;
+        int vid = carry + block_excl_scan_1024(local, s_warp, &total);
+#pragma unroll
+        for (int e = 0; e < kScanEPT; ++e) {
+            const int i = i0 + e;
+            if (i < N) {
+                pt_vid[i] = vid;
+                if ((flags >> e) & 1u) {
+                    if (vid < max_voxels) {
+                        const int c2 = cell[e] % g.shape[2];
+                        const int c1 = (cell[e] / g.shape[2]) % g.shape[1];
+                        const int c0 = cell[e] / (g.shape[2] * g.shape[1]);
+                        coors[vid * 3 + 0] = c0;
+                        coors[vid * 3 + 1] = c1;
+                        coors[vid * 3 + 2] = c2;
+                    } else if (vid == max_voxels) {
+                        meta[0] = i;  // the reference breaks here (pc_ops.py:44-45)
+                    }
+                    ++vid;
                 }
             }
         }
-        __syncthreads();
-        if (tid == 0) s_carry = carry + block_total;
-        __syncthreads();
+        carry += total;
     }
-    if (tid == 0) meta[1] = s_carry;
+    if (tid == 0) meta[1] = carry;
 }
 
 __global__ void __launch_bounds__(256)
@@ -177,54 +203,43 @@ vox_count_kernel(int32_t *__restrict__ pt_cell, const int32_t *__restrict__ cell
 }
 
 // Single CTA: exclusive scan of cnt over the voxels -> bucket offsets; final num_points and the
-// zero rows of coors / num_points beyond voxel_num.
+// zero rows of coors / num_points beyond voxel_num.  Same consecutive-elements-per-thread scheme.
 __global__ void __launch_bounds__(1024)
 vox_offsets_kernel(const int32_t *__restrict__ cnt, const int32_t *__restrict__ meta,
                    int max_voxels, int max_points, int32_t *__restrict__ off,
                    int32_t *__restrict__ num_points, int32_t *__restrict__ coors,
                    int32_t *__restrict__ voxel_num_out) {
     __shared__ int s_warp[32];
-    __shared__ int s_carry;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const int vnum = min(meta[1], max_voxels);
-    if (tid == 0) {
-        s_carry = 0;
-        *voxel_num_out = vnum;
-    }
-    __syncthreads();
-    for (int base = 0; base < max_voxels; base += 1024) {
-        const int v = base + tid;
-        const int c = (v < vnum) ? cnt[v] : 0;
-        int incl = c;
+    if (tid == 0) *voxel_num_out = vnum;
+    int carry = 0;
+    for (int base = 0; base < max_voxels; base += 1024 * kScanEPT) {
+        const int v0 = base + tid * kScanEPT;
+        int c[kScanEPT];
+        int local = 0;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
+        for (int e = 0; e < kScanEPT; ++e) {
+            c[e] = (v0 + e < vnum) ? cnt[v0 + e] : 0;
+            local += c[e];
         }
-        if (lane == 31) s_warp[warp] = incl;
-        __syncthreads();
-        int wsum = s_warp[lane];
-        int wincl = wsum;
+        int total;
+        int run = carry + block_excl_scan_1024(local, s_warp, &total);
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, wincl, o);
-            if (lane >= o) wincl += t;
-        }
-        const int block_total = __shfl_sync(0xffffffffu, wincl, 31);
-        const int warp_excl = __shfl_sync(0xffffffffu, wincl - wsum, warp);
-        const int carry = s_carry;
-        if (v < max_voxels) {
-            off[v] = carry + warp_excl + incl - c;
-            num_points[v] = min(c, max_points);
-            if (v >= vnum) {
-                coors[v * 3 + 0] = 0;
-                coors[v * 3 + 1] = 0;
-                coors[v * 3 + 2] = 0;
+        for (int e = 0; e < kScanEPT; ++e) {
+            const int v = v0 + e;
+            if (v < max_voxels) {
+                off[v] = run;
+                num_points[v] = min(c[e], max_points);
+                if (v >= vnum) {
+                    coors[v * 3 + 0] = 0;
+                    coors[v * 3 + 1] = 0;
+                    coors[v * 3 + 2] = 0;
+                }
             }
+            run += c[e];
         }
-        __syncthreads();
-        if (tid == 0) s_carry = carry + block_total;
-        __syncthreads();
+        carry += total;
     }
 }
 
@@ -435,23 +450,47 @@ pfn_main_kernel(const float *__restrict__ features, const int32_t *__restrict__ 
     }
 }
 
-// Single CTA: fixed-order reduction of the block partials -> scale / shift (+ mean / var).
-__global__ void __launch_bounds__(256)
+// Single CTA: fixed-order reduction of the block partials -> scale / shift (+ mean / var).  The
+// 2*cout columns are split over all 1024 threads (slices of the block rows, independent loads),
+// the slices are combined through shared memory in a fixed order -> deterministic.
+constexpr int kPfnBnThreads = 1024;
+__global__ void __launch_bounds__(kPfnBnThreads)
 pfn_bn_kernel(const double *__restrict__ partial, int nblocks, int P, int T,
               const int32_t *__restrict__ num_valid, const float *__restrict__ gamma,
               const float *__restrict__ beta, const float *__restrict__ rm,
               const float *__restrict__ rv, int bn_mode, float eps, int cout,
               float *__restrict__ scale, float *__restrict__ shift, float *__restrict__ mean_out,
               float *__restrict__ var_out) {
+    __shared__ double s_red[kPfnBnThreads];
+    __shared__ double s_sum[2 * 512];  // S | Q per channel (cout <= 512)
+    const int tid = threadIdx.x;
     const int Pv = num_valid ? min(*num_valid, P) : P;
-    for (int c = threadIdx.x; c < cout; c += blockDim.x) {
+    if (bn_mode == PAPC_BN_BATCH) {
+        const int C2 = 2 * cout;
+        for (int cbase = 0; cbase < C2; cbase += kPfnBnThreads) {
+            const int ncol = min(C2 - cbase, kPfnBnThreads);
+            int slices = kPfnBnThreads / ncol;          // >= 1
+            const int col = tid % ncol, sl = tid / ncol;
+            double acc = 0.0;
+            if (sl < slices) {
+                const double *p = partial + cbase + col;
+#pragma unroll 8
+                for (int b = sl; b < nblocks; b += slices) acc += p[(size_t)b * C2];
+            }
+            s_red[tid] = acc;
+            __syncthreads();
+            if (tid < ncol) {
+                double t = 0.0;
+                for (int q = 0; q < slices; ++q) t += s_red[q * ncol + tid];
+                s_sum[cbase + tid] = t;
+            }
+            __syncthreads();
+        }
+    }
+    for (int c = tid; c < cout; c += kPfnBnThreads) {
         double sc = 1.0, sh = 0.0;
         if (bn_mode == PAPC_BN_BATCH) {
-            double S = 0.0, Q = 0.0;
-            for (int b = 0; b < nblocks; ++b) {
-                S += partial[(size_t)b * 2 * cout + c];
-                Q += partial[(size_t)b * 2 * cout + cout + c];
-            }
+            const double S = s_sum[c], Q = s_sum[cout + c];
             const double count = (double)Pv * (double)T;
             const double mean = count > 0 ? S / count : 0.0;
             double var = count > 0 ? Q / count - mean * mean : 0.0;
@@ -695,7 +734,7 @@ extern "C" int papc_pfn_f32(const float *features, const int32_t *num_voxels, co
     else PAPC_PFN_LAUNCH(8);
 #undef PAPC_PFN_LAUNCH
     PAPC_LAUNCH_CHECK();
-    pfn_bn_kernel<<<1, 256, 0, st>>>(partial, w.nblocks, P, T, num_valid, gamma, beta, running_mean,
+    pfn_bn_kernel<<<1, kPfnBnThreads, 0, st>>>(partial, w.nblocks, P, T, num_valid, gamma, beta, running_mean,
                                      running_var, bn_mode, eps, cout, scale, shift, batch_mean,
                                      batch_var);
     PAPC_LAUNCH_CHECK();

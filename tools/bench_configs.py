@@ -1,7 +1,7 @@
 """Forward times of the other BASELINE.json configurations (parity-test cases, not bench lines):
   C3  PointNet++ MSG segment SetAbstraction stack, B=16 x 2048 points (3-radius ball query)
   C4  PointPillars pillar encode: voxelise -> PillarFeatureNet -> scatter, 20k-point KITTI-shaped frames
-CUDA events, median of 10 after 3 warm-up passes.  usage: python tools/bench_configs.py"""
+CUDA events around 30 back-to-back passes after 5 warm-up passes.  usage: python tools/bench_configs.py"""
 import json
 import os
 import sys
@@ -17,19 +17,19 @@ dev = torch.device("cuda:0")
 torch.cuda.set_device(dev)
 
 
-def timeit(fn, reps=10, warm=3):
+def timeit(fn, reps=30, warm=5):
+    """ms per call, reps calls queued back to back between two events (keeps the GPU busy, so the SM
+    clock does not fall back to idle between the small pillar kernels)."""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
-    ts = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     for _ in range(reps):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
         fn()
-        e1.record()
-        torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
-    return float(np.median(ts))
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
 
 
 out = {}

@@ -54,3 +54,11 @@ fi
 if [[ "$what" == *fpsshape* ]]; then
   for w in 0 2 3; do echo "--- PAPC_FPS_WIDE=$w"; PAPC_FPS_WIDE=$w timeout 300 python tools/prof_prims.py 2>&1 | grep -v 2048; done | tee gpurun_out/fps_shapes.log
 fi
+if [[ "$what" == *pillarncu* ]]; then
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"vox_|pfn_|scatter_" -s 13 -c 13 -f \
+     -o gpurun_out/pillars_full python tools/prof_pillars.py > gpurun_out/ncu_pillars.log 2>&1
+  echo "ncu pillars exit $?"; tail -2 gpurun_out/ncu_pillars.log | cut -c1-200
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:"ball_query" -s 2 -c 2 -f \
+     -o gpurun_out/bq_full python tools/prof_step.py 2 > gpurun_out/ncu_bq.log 2>&1
+  echo "ncu bq exit $?"
+fi
