@@ -883,6 +883,7 @@ mlp_layer_tt_kernel(const TtArgs a) {
             fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
             __syncwarp();
             if (lane == 0) mbar_arrive(x_full + s);
+            if (TT_DBG(a, 32)) __nanosleep(1500);  // triage: producers step aside after every chunk
             if (ptid == 0 && c == KC - 1) TT_TCLK(a, ptl, 1);  // producer: last chunk of the tile published
             if (ptid == 0 && it == 0) TT_CLK(a, 3);
             if (ptid == 0 && it == 1) TT_CLK(a, 12);
@@ -978,12 +979,28 @@ mlp_layer_tt_kernel(const TtArgs a) {
                 if (sl < S && pr < npairs) {
                     double ax = 0.0, ay = 0.0;
                     const double2 *p = part + pr;
+                    // all loads of a thread are independent: issue them 16 at a time (each batch is one
+                    // L2 round trip of this serial tail), two accumulator pairs to halve the add chain
+                    double bx = 0.0, by = 0.0;
+                    int r = sl;
+                    for (; r + 15 * S < gm; r += 16 * S) {
+                        double2 v[16];
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) v[q] = __ldcg(p + (long long)(r + q * S) * npairs);
+#pragma unroll
+                        for (int q = 0; q < 16; q += 2) {
+                            ax += v[q].x; ay += v[q].y;
+                            bx += v[q + 1].x; by += v[q + 1].y;
+                        }
+                    }
 #pragma unroll 8
-                    for (int r = sl; r < gm; r += S) {
+                    for (; r < gm; r += S) {
                         const double2 v = __ldcg(p + (long long)r * npairs);
                         ax += v.x;
                         ay += v.y;
                     }
+                    ax += bx;
+                    ay += by;
                     red[sl * P + pair_l] = make_double2(ax, ay);
                 }
                 __syncthreads();
@@ -999,6 +1016,9 @@ mlp_layer_tt_kernel(const TtArgs a) {
                 }
                 __syncthreads();
             }
+#ifdef PAPC_TT_TRIAGE
+            if (tid == 0 && a.clk != nullptr) a.clk[32 + 10] = clock64();
+#endif
             // fp64 division and square root are long software sequences on a slow pipe and this is the
             // kernel's serial tail: reciprocal of the count from the host, 1/sqrt by two Newton steps
             // from the fp32 estimate (full double accuracy)
@@ -1026,6 +1046,7 @@ mlp_layer_tt_kernel(const TtArgs a) {
             }
             if (tid == 0) *a.counter = 0u;  // self-cleaning for the next launch
 #ifdef PAPC_TT_TRIAGE
+            __syncthreads();
             if (tid == 0 && a.clk != nullptr) { a.clk[32 + 8] = clock64(); a.clk[32 + 9] = blockIdx.x; }
 #endif
         }
@@ -1323,10 +1344,11 @@ int launch(const TtArgs &a_in, cudaStream_t st) {
         auto us = [&](int slot, int e) { return h[slot * 16 + e] ? (double)(h[slot * 16 + e] - h[slot * 16]) / 1965.0 : -1.0; };
         fprintf(stderr, "[tt clk] mode %d prec %d M %lld cin %d cout %d grid %d | CTA0 us: setup %.2f Wstaged %.2f "
                 "x_full0 %.2f x_full1 %.2f mma0 %.2f acc0 %.2f acc1 %.2f prod_end %.2f epi_end %.2f teardown %.2f "
-                "counted %.2f | last CTA %llu: start %.2f end %.2f (rel. CTA0 entry, same SM clock only if CTA 0)\n",
+                "counted %.2f | last CTA %llu: finalisation %.2f us (reduction part %.2f)\n",
                 a.mode, a.prec, a.M, a.cin, a.cout, grid, us(0, 1), us(0, 2), us(0, 3), us(0, 12), us(0, 4), us(0, 5),
                 us(0, 11), us(0, 10), us(0, 6), us(0, 7), us(0, 8), h[32 + 9],
-                h[32 + 7] ? (double)(h[32 + 8] - h[32 + 7]) / 1965.0 : -1.0, 0.0);
+                h[32 + 7] ? (double)(h[32 + 8] - h[32 + 7]) / 1965.0 : -1.0,
+                h[32 + 10] ? (double)(h[32 + 10] - h[32 + 7]) / 1965.0 : -1.0);
         if (getenv("PAPC_TT_TILECLK") != nullptr) {
             fprintf(stderr, "[tt tile] us rel. CTA0 entry: prod_ready prod_pub | mma_accfree mma_commit | epi_accfull epi_release epi_done\n");
             for (int t = 0; t < 16; ++t) {
