@@ -210,6 +210,27 @@ int papc_sa_pool_finish_f32(const float *pool_max, const float *pool_min, const 
                             float *out, int out_layout, papc_stream_t stream);
 
 /* ----------------------------------------------------------------------------------------
+ * N1  PointNetFeaturePropagation (the first "next" row)          layers.py:284-335
+ *
+ *   papc_fp_interpolate_f32: lines :306-329.  xyz1 [B,N,3], xyz2 [B,S,3], points1 [B,N,D1] (nullable,
+ *     D1 = 0), points2 [B,S,D2], all channels-last -> out [B*N, ld_out] rows
+ *     [points1 | interpolated | zero padding], ld_out >= D1 + D2.  S == 1 tiles points2 (:314).
+ *     Otherwise the three smallest square_distance values of each point weight -- through
+ *     1/(d + 1e-8), normalised -- the features of sampled points 0, 1, 2: the reference takes the
+ *     argsort of the already SORTED distances (:317-318), i.e. the identity, and that quirk is
+ *     reproduced.
+ *   papc_pointwise_mlp_f32: lines :332-335, (Conv1D k=1 + BatchNorm1D + ReLU) x L over the M rows
+ *     of x [M, ld_x] (ld_x >= mlp->cin, padding columns must be zero) -> out [M, cout_last].
+ *     bn_mode / eps / per-layer pointers as in papc_mlp.
+ */
+int papc_fp_interpolate_f32(const float *xyz1, const float *xyz2, const float *points1,
+                            const float *points2, int B, int N, int S, int D1, int D2, int ld_out,
+                            float *out, papc_stream_t stream);
+size_t papc_pointwise_mlp_workspace_bytes(int64_t M, int32_t ld_x, const papc_mlp *mlp);
+int papc_pointwise_mlp_f32(const float *x, int64_t M, int32_t ld_x, const papc_mlp *mlp, float *out,
+                           void *workspace, size_t workspace_bytes, papc_stream_t stream);
+
+/* ----------------------------------------------------------------------------------------
  * A9  points_to_voxel(points, voxel_size, coors_range, max_points, reverse_index, max_voxels)
  *                                                                   pc_ops.py:106-166
  *     points [N,F] (F >= 3) -> voxels [max_voxels,max_points,F] (zero padded; every element is

@@ -298,3 +298,65 @@ def grouped_mlp(new_points, weights, biases, gammas, betas, eps=1e-5, bn_mode="b
         if bn_mode == "batch":
             stats.append((bn.last_mean, bn.last_var))
     return np.max(x, 2), stats
+
+
+# ----------------------------------------------------------------------------------
+class PointNetFeaturePropagation:
+    """layers.py:284-335, statement by statement.
+
+    Conv1D(k=1) / BatchNorm1D are restated with the 2-D holders above on a [B,C,N,1] view (a
+    1x1 convolution and a per-channel normalisation over (B, N) are the same arithmetic).
+
+    Reference quirk kept on purpose: ``dists`` is SORTED first (:316) and ``idx`` is the argsort
+    of the already sorted array (:317), i.e. the identity permutation -- so the three *smallest
+    distances* weight the features of sampled points 0, 1, 2, not of the three nearest ones.
+    (``np.argsort(kind='stable')`` makes the identity exact under ties; with ties Paddle may swap
+    equal entries, which leaves the weighted sum unchanged unless the tie straddles positions 2|3.)
+    """
+
+    def __init__(self, in_channel, mlp, rng=None):
+        self.mlp_convs = []
+        self.mlp_bns = []
+        last_channel = in_channel
+        for out_channel in mlp:
+            self.mlp_convs.append(Conv2D1x1(last_channel, out_channel, rng))   # nn.Conv1D(.., 1)  :292
+            self.mlp_bns.append(BatchNorm2D(out_channel))                      # nn.BatchNorm1D    :293
+            last_channel = out_channel
+        self.acc = np.float64
+
+    def interpolate(self, xyz1, xyz2, points1, points2):
+        """:306-329 -> new_points [B, N, D1+D2] (channels-last, before the transpose at :331)."""
+        xyz1 = xyz1.transpose(0, 2, 1)                                   # :306
+        xyz2 = xyz2.transpose(0, 2, 1)                                   # :307
+        points2 = points2.transpose(0, 2, 1)                             # :309
+        B, N, C = xyz1.shape
+        _, S, _ = xyz2.shape
+        if S == 1:
+            interpolated_points = np.tile(points2, [1, N, 1])            # :314
+        else:
+            dists = square_distance(xyz1, xyz2)                          # :316
+            dists = np.sort(dists, axis=-1)                              # :317
+            idx = np.argsort(dists, axis=-1, kind="stable")              # :318 (of the SORTED array)
+            dists, idx = dists[:, :, :3], idx[:, :, :3]                  # :319
+            dist_recip = F32(1.0) / (dists + F32(1e-8))                  # :321
+            norm = np.sum(dist_recip, axis=2, keepdims=True)             # :322
+            weight = dist_recip / norm                                   # :323
+            k3 = idx.shape[2]
+            interpolated_points = np.sum(index_points(points2, idx) * weight.reshape(B, N, k3, 1), axis=2)  # :324
+        if points1 is not None:
+            points1 = points1.transpose(0, 2, 1)                         # :327
+            new_points = np.concatenate([points1, interpolated_points], axis=-1)  # :328
+        else:
+            new_points = interpolated_points
+        return new_points.astype(F32)
+
+    def forward(self, xyz1, xyz2, points1, points2):
+        new_points = self.interpolate(xyz1, xyz2, points1, points2)
+        new_points = new_points.transpose(0, 2, 1)                       # :332  [B,C,N]
+        x = new_points[:, :, :, None]
+        for i, conv in enumerate(self.mlp_convs):
+            bn = self.mlp_bns[i]
+            x = relu(bn(conv(x, self.acc), self.acc))                    # :335
+        return x[:, :, :, 0]
+
+    __call__ = forward

@@ -78,6 +78,9 @@ _SIGNATURES = {
     "papc_bn_running_scale_shift_f32": (_I, [_vp, _vp, _vp, _vp, _F, C.c_int32, _vp, _vp, _vp]),
     "papc_sa_pool_finish_f32": (_I, [_vp, _vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp, _I,
                                       _vp]),
+    "papc_fp_interpolate_f32": (_I, [_vp, _vp, _vp, _vp, _I, _I, _I, _I, _I, _I, _vp, _vp]),
+    "papc_pointwise_mlp_workspace_bytes": (_SZ, [_I64, C.c_int32, C.POINTER(Mlp)]),
+    "papc_pointwise_mlp_f32": (_I, [_vp, _I64, C.c_int32, C.POINTER(Mlp), _vp, _vp, _SZ, _vp]),
     "papc_voxelize_workspace_bytes": (_SZ, [_I, C.POINTER(_F), C.POINTER(_F), _I]),
     "papc_voxelize_f32": (_I, [_vp, _I, _I, C.POINTER(_F), C.POINTER(_F), _I, _I, _I, _vp, _vp, _vp,
                                 _vp, _vp, _SZ, _vp]),

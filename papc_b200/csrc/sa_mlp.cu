@@ -663,7 +663,8 @@ static int try_tt(const LayerArgs &a, bool gather, int K, const FusedBn *bn, con
         t.cin = a.cin;
         t.x = a.x; t.in_scale = a.in_scale; t.in_shift = a.in_shift;
     }
-    const tt::TtProblem prob{t.mode, t.prec, t.cin, t.cout, K, t.D, a.pool_max != nullptr};
+    tt::TtProblem prob{t.mode, t.prec, t.cin, t.cout, K, t.D, a.pool_max != nullptr};
+    prob.no_act = t.mode == tt::SRC_PLAIN && t.in_scale == nullptr && t.prec == tt::PREC_TF32;
     if (!tt::eligible(prob)) return 0;
     if (!a.pool_max && !a.y) return 0;
     const size_t wneed = tt::wimg_bytes(t.prec, t.cin, t.cout);
@@ -1077,4 +1078,164 @@ extern "C" int papc_sa_mlp_f32(const papc_group_source *src, const papc_mlp *mlp
     }
     return papc_sa_pool_finish_f32(pmax, pmin, scale, shift, src->B, src->S,
                                    mlp->layers[L - 1].cout, out, out_layout, stream);
+}
+
+
+// ============================================================ pointwise MLP (no grouping, no pool)
+// (Conv1D 1x1 + BatchNorm1D + ReLU) x L over M rows: the tail of PointNetFeaturePropagation
+// (layers.py:332-335).  Same layer kernels and BatchNorm handling as papc_sa_mlp_f32; the last layer's
+// pre-BN output is materialised too and a final elementwise pass applies its BN + ReLU.
+namespace {
+__global__ void __launch_bounds__(256)
+bn_relu_apply_kernel(const float *__restrict__ y, const float *__restrict__ scale,
+                     const float *__restrict__ shift, size_t total, int C, float *__restrict__ out) {
+    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; e < total; e += stride) {
+        const int c = (int)(e % C);
+        out[e] = fmaxf(fmaf(y[e], scale[c], shift[c]), 0.f);
+    }
+}
+__global__ void __launch_bounds__(256)
+pad_weight_kernel(const float *__restrict__ w, int cout, int cin, int ld, float *__restrict__ wp) {
+    const int total = cout * ld;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int r = e / ld, k = e - r * ld;
+        wp[e] = k < cin ? w[(size_t)r * cin + k] : 0.f;
+    }
+}
+struct PwPlan {
+    size_t y[2], partial, scale, shift, wimg, wimg_bytes, counters, colscale, colscale_stride, wpad, total;
+};
+static int plan_pw(int64_t M, int32_t ld_x, const papc_mlp *mlp, PwPlan *p) {
+    if (!mlp || M < 0 || mlp->num_layers < 1 || mlp->num_layers > PAPC_MAX_MLP_LAYERS) return PAPC_EINVAL;
+    if (ld_x < mlp->cin || mlp->cin <= 0) return PAPC_EINVAL;
+    int maxc = 0;
+    for (int l = 0; l < mlp->num_layers; ++l) {
+        if (mlp->layers[l].cout <= 0) return PAPC_EINVAL;
+        maxc = mlp->layers[l].cout > maxc ? mlp->layers[l].cout : maxc;
+    }
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    p->y[0] = take((size_t)M * maxc * sizeof(float));
+    p->y[1] = take((size_t)M * maxc * sizeof(float));
+    p->partial = take((size_t)grid_rows(M) * 2 * maxc * sizeof(double));
+    p->scale = take((size_t)maxc * sizeof(float));
+    p->shift = take((size_t)maxc * sizeof(float));
+    size_t wb = 0;
+    int c_in = ld_x;
+    for (int l = 0; l < mlp->num_layers; ++l) {
+        const size_t b = papc_mlp_layer_workspace_bytes(c_in, mlp->layers[l].cout);
+        wb = b > wb ? b : wb;
+        c_in = mlp->layers[l].cout;
+    }
+    p->wimg_bytes = wb;
+    p->wimg = take(wb);
+    p->counters = take(256);
+    p->colscale_stride = align_up((size_t)maxc * sizeof(float), 256);
+    p->colscale = take(2 * p->colscale_stride);
+    p->wpad = take(ld_x != mlp->cin ? (size_t)mlp->layers[0].cout * ld_x * sizeof(float) : 0);
+    p->total = off;
+    return PAPC_OK;
+}
+}  // namespace
+
+extern "C" size_t papc_pointwise_mlp_workspace_bytes(int64_t M, int32_t ld_x, const papc_mlp *mlp) {
+    PwPlan p;
+    if (plan_pw(M, ld_x, mlp, &p) != PAPC_OK) return 0;
+    return p.total;
+}
+
+extern "C" int papc_pointwise_mlp_f32(const float *x, int64_t M, int32_t ld_x, const papc_mlp *mlp,
+                                      float *out, void *workspace, size_t workspace_bytes,
+                                      papc_stream_t stream) {
+    PwPlan p;
+    int rc = plan_pw(M, ld_x, mlp, &p);
+    if (rc != PAPC_OK) return rc;
+    if (mlp->bn_mode != PAPC_BN_BATCH && mlp->bn_mode != PAPC_BN_RUNNING) return PAPC_EINVAL;
+    if (M == 0) return PAPC_OK;
+    if (!x || !out) return PAPC_EINVAL;
+    if (!workspace || workspace_bytes < p.total) return PAPC_EWORKSPACE;
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255u) != 0) return PAPC_EINVAL;
+    cudaStream_t st = as_stream(stream);
+    char *ws = reinterpret_cast<char *>(workspace);
+    float *ybuf[2] = {reinterpret_cast<float *>(ws + p.y[0]), reinterpret_cast<float *>(ws + p.y[1])};
+    double *partial = reinterpret_cast<double *>(ws + p.partial);
+    float *scale = reinterpret_cast<float *>(ws + p.scale);
+    float *shift = reinterpret_cast<float *>(ws + p.shift);
+    unsigned int *counters = reinterpret_cast<unsigned int *>(ws + p.counters);
+    float *colscale[2] = {reinterpret_cast<float *>(ws + p.colscale),
+                          reinterpret_cast<float *>(ws + p.colscale + p.colscale_stride)};
+    const bool batch = mlp->bn_mode == PAPC_BN_BATCH;
+    const int L = mlp->num_layers;
+    for (int l = 0; l < L; ++l) {
+        const papc_mlp_layer &ly = mlp->layers[l];
+        if (!ly.weight) return PAPC_EINVAL;
+        if (!batch && (!ly.running_mean || !ly.running_var)) return PAPC_EINVAL;
+    }
+    PAPC_CUDA_TRY(cudaMemsetAsync(counters, 0, 256, st));
+    const float *w0 = mlp->layers[0].weight;
+    if (ld_x != mlp->cin) {  // rows are padded (with zeros) to ld_x columns: pad the first weight alike
+        float *wp = reinterpret_cast<float *>(ws + p.wpad);
+        const int total = mlp->layers[0].cout * ld_x;
+        pad_weight_kernel<<<ceil_div(total, 256), 256, 0, st>>>(w0, mlp->layers[0].cout, mlp->cin, ld_x, wp);
+        PAPC_LAUNCH_CHECK();
+        w0 = wp;
+    }
+    const float sqrt_m = nextafterf((float)sqrt((double)M), INFINITY);
+    int cin = ld_x;
+    const float *xprev = x;
+    bool this_f16 = false;
+    for (int l = 0; l < L; ++l) {
+        const papc_mlp_layer &ly = mlp->layers[l];
+        float *y = ybuf[l & 1];
+        // the next layer may run the fp16 split iff this layer's finalisation is fused (it divides
+        // scale / shift by the column scale) and the shape is eligible: decided by a dry run
+        bool next_f16 = false;
+        if (batch && l + 1 < L && ly.cout % 8 == 0) {
+            LayerArgs a{};
+            a.x = y; a.in_scale = scale; a.in_shift = shift;
+            a.K = 1; a.M = M; a.cin = ly.cout; a.cout = mlp->layers[l + 1].cout;
+            a.W = mlp->layers[l + 1].weight; a.bias = mlp->layers[l + 1].bias;
+            a.y = ybuf[(l + 1) & 1]; a.stats_partial = partial;
+            const TtOpts od{tt::PREC_F16, nullptr, nullptr, 0.f, nullptr, ws + p.wimg, p.wimg_bytes, true, false};
+            next_f16 = try_tt(a, false, 1, nullptr, od, st) == 1;
+        }
+        FusedBn bn{counters + l, ly.gamma, ly.beta, mlp->eps, (double)M, sqrt_m,
+                   scale, shift, ly.batch_mean, ly.batch_var, next_f16 ? colscale[l & 1] : nullptr};
+        TtOpts o{this_f16 ? tt::PREC_F16 : tt::PREC_TF32,
+                 this_f16 ? mlp->layers[l - 1].gamma : nullptr, this_f16 ? mlp->layers[l - 1].beta : nullptr,
+                 sqrt_m, nullptr, ws + p.wimg, p.wimg_bytes, false, l > 0};
+        bool fused_done = false;
+        rc = layer_forward(nullptr, xprev, l == 0 ? nullptr : scale, l == 0 ? nullptr : shift, M, cin, ly.cout, 1,
+                           l == 0 ? w0 : ly.weight, ly.bias, y, nullptr, nullptr, batch ? partial : nullptr,
+                           ws + p.wimg, p.wimg_bytes, batch ? &bn : nullptr, &o, &fused_done, stream);
+        if (rc != PAPC_OK) return rc;
+        if (this_f16 && !fused_done && batch) return PAPC_EUNSUPPORTED;  // the dry run promised the tt kernel
+        this_f16 = false;
+        if (batch) {
+            if (!fused_done) {
+                bn_from_partials_kernel<<<ceil_div(ly.cout, 32), dim3(32, 16), 0, st>>>(
+                    partial, papc_mlp_stats_partial_rows(M), ly.cout, (double)M, ly.gamma, ly.beta,
+                    mlp->eps, scale, shift, ly.batch_mean, ly.batch_var);
+                PAPC_LAUNCH_CHECK();
+            } else {
+                this_f16 = next_f16;
+            }
+        } else {
+            rc = papc_bn_running_scale_shift_f32(ly.running_mean, ly.running_var, ly.gamma, ly.beta,
+                                                 mlp->eps, ly.cout, scale, shift, stream);
+            if (rc != PAPC_OK) return rc;
+        }
+        xprev = y;
+        cin = ly.cout;
+    }
+    const int clast = mlp->layers[L - 1].cout;
+    const size_t total = (size_t)M * clast;
+    size_t blocks = (total + 255) / 256;
+    if (blocks > (size_t)kNumSMs * 16) blocks = (size_t)kNumSMs * 16;
+    ProfScope prof(st, "bn_relu_apply", M, 0, clast, 0.0, 8.0 * (double)total);
+    bn_relu_apply_kernel<<<(unsigned)blocks, 256, 0, st>>>(xprev, scale, shift, total, clast, out);
+    PAPC_LAUNCH_CHECK();
+    return PAPC_OK;
 }

@@ -1212,8 +1212,8 @@ bool eligible(const TtProblem &p) {
     if (p.cin < epu(p.prec) || p.cin % epu(p.prec) != 0) return false;
     if (p.mode == SRC_POINTMLP) {
         if (p.cin > kMaxFold) return false;
-    } else if (p.cin > kMaxAct) {
-        return false;
+    } else if (p.cin > kMaxAct && !(p.mode == SRC_PLAIN && p.no_act)) {
+        return false;  // the scale / shift / column-scale tables hold kMaxAct channels
     }
     if (p.mode == SRC_GATHER && (p.D != p.cin || p.prec != PREC_TF32)) return false;
     if (p.pool && !(p.K == 32 || p.K == 64 || p.K == 128)) return false;

@@ -72,6 +72,7 @@ struct TtArgs {
 struct TtProblem {
     int mode, prec, cin, cout, K, D;
     bool pool;
+    bool no_act = false;  // SRC_PLAIN without an input activation: no scale / shift table, any cin
 };
 bool eligible(const TtProblem &p);
 // Division by a runtime constant d >= 1 for dividends < 2^31: q = d == 1 ? x : umulhi(x, mul) >> shr

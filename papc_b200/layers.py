@@ -512,3 +512,87 @@ class PointNetSetAbstractionMsg(_SAMixin):
                 self.update_running_stats, self.sync_bn_group))
         new_points_concat = torch.cat(outs, dim=2)                                   # :280 (channels-last)
         return _tag_ready(new_xyz.transpose(1, 2), ev), new_points_concat.transpose(1, 2)
+
+
+# ---------------------------------------------------------------------------------------------
+class Conv1D(Conv2D):
+    """Parameter holder mirroring ``paddle.nn.Conv1D(cin, cout, 1)``: weight [cout,cin,1], bias [cout]."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=1, device=None, generator=None):
+        super().__init__(in_channels, out_channels, kernel_size, device, generator)
+        self.weight = self.weight.reshape(out_channels, in_channels, 1)
+
+
+class BatchNorm1D(BatchNorm2D):
+    """Parameter holder mirroring ``paddle.nn.BatchNorm1D(c)`` (epsilon 1e-5, momentum 0.9)."""
+
+
+def feature_interpolate(xyz1, xyz2, points1, points2, pad_to=8):
+    """layers.py:306-329 on channels-last inputs: xyz1 [B,N,3], xyz2 [B,S,3], points1 [B,N,D1] | None,
+    points2 [B,S,D2] -> rows [B*N, ld] = [points1 | interpolated | 0-padding], ld = D1+D2 rounded up
+    to ``pad_to`` (what the tensor-core MLP wants).  Returns (rows, D1 + D2)."""
+    L.require_cuda(xyz1, xyz2, points1, points2)
+    xyz1, xyz2, points2 = L.f32c(xyz1), L.f32c(xyz2), L.f32c(points2)
+    points1 = L.f32c(points1) if points1 is not None else None
+    B, N, _ = xyz1.shape
+    S = xyz2.shape[1]
+    D1 = 0 if points1 is None else points1.shape[2]
+    D2 = points2.shape[2]
+    if xyz2.shape[0] != B or points2.shape[:2] != (B, S) or (points1 is not None and points1.shape[:2] != (B, N)):
+        raise ValueError("feature_interpolate: inconsistent shapes")
+    ld = (D1 + D2 + pad_to - 1) // pad_to * pad_to
+    out = torch.empty((B * N, ld), dtype=torch.float32, device=xyz1.device)
+    L.check(L.lib().papc_fp_interpolate_f32(L.ptr(xyz1), L.ptr(xyz2), L.ptr(points1), L.ptr(points2), B, N, S,
+                                            D1, D2, ld, L.ptr(out), L.stream_ptr(xyz1.device)), "fp_interpolate")
+    return out, D1 + D2
+
+
+class PointNetFeaturePropagation(_SAMixin):
+    """layers.py:284-335.  The conv/bn holders live in plain lists like the
+    reference's (:287-294), so -- as for the SetAbstraction layers -- BatchNorm runs on batch
+    statistics unless ``bn_mode='running'``.  The reference's interpolation quirk (weights of the
+    three nearest sampled points applied to the features of sampled points 0, 1, 2, :317-318) is
+    reproduced; see include/papc_b200.h."""
+
+    def __init__(self, in_channel, mlp):
+        super().__init__()
+        self.mlp_convs = []
+        self.mlp_bns = []
+        last_channel = in_channel
+        for out_channel in mlp:
+            self.mlp_convs.append(Conv1D(last_channel, out_channel, 1))
+            self.mlp_bns.append(BatchNorm1D(out_channel))
+            last_channel = out_channel
+        self.in_channel = in_channel
+
+    def _holders(self):
+        return list(self.mlp_convs) + list(self.mlp_bns)
+
+    def forward(self, xyz1, xyz2, points1, points2):
+        """xyz1 [B,C,N], xyz2 [B,C,S], points1 [B,D,N] | None, points2 [B,D,S] -> [B,D',N]."""
+        L.require_cuda(xyz1, xyz2, points1, points2)
+        x1 = L.f32c(xyz1.transpose(1, 2))                                   # :306
+        x2 = L.f32c(xyz2.transpose(1, 2))                                   # :307
+        p2 = L.f32c(points2.transpose(1, 2))                                # :309
+        p1 = L.f32c(points1.transpose(1, 2)) if points1 is not None else None  # :327
+        B, N, _ = x1.shape
+        rows, cin = feature_interpolate(x1, x2, p1, p2)                     # :311-329
+        if cin != self.in_channel:
+            raise ValueError(f"in_channel={self.in_channel} but the concatenated input has {cin} channels")
+        dev = rows.device
+        if any(c.weight.device != dev for c in self.mlp_convs):
+            raise L.PapcError("layer parameters are not on the input's device; call .to(device)")
+        runner = _MlpRunner(self.mlp_convs, self.mlp_bns)
+        mlp, keep, stats = runner._mlp_struct(cin, self.bn_mode, dev, self.update_running_stats)
+        lib = L.lib()
+        M, ld = rows.shape
+        cout = self.mlp_convs[-1].weight.shape[0]
+        out = torch.empty((B, N, cout), dtype=torch.float32, device=dev)
+        wsb = lib.papc_pointwise_mlp_workspace_bytes(M, ld, C.byref(mlp))
+        ws = _ws(wsb, dev)
+        L.check(lib.papc_pointwise_mlp_f32(L.ptr(rows), M, ld, C.byref(mlp), L.ptr(out), L.ptr(ws), wsb,
+                                           L.stream_ptr(dev)), "pointwise_mlp")    # :332-335
+        if stats:
+            runner._update_running(stats)
+        del keep
+        return out.transpose(1, 2)

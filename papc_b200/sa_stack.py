@@ -8,7 +8,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from .layers import PointNetSetAbstraction, PointNetSetAbstractionMsg
+from .layers import PointNetFeaturePropagation, PointNetSetAbstraction, PointNetSetAbstractionMsg
 
 
 def load_conv_bn(convs, bns, params):
@@ -60,3 +60,27 @@ class MSGSegSetAbstractionStack(torch.nn.Module):
         l2_xyz, l2_points = self.sa2(l1_xyz, l1_points, start_idx=start_idx[1])
         l3_xyz, l3_points = self.sa3(l2_xyz, l2_points)
         return l3_xyz, l3_points
+
+
+class MSGSegEncoderDecoder(torch.nn.Module):
+    """SetAbstraction + FeaturePropagation part of PointNet2_MSG_Seg (normal_channel=False), wired as
+    segment/pointnet2/pointnet2.py:62-67 and :84-93: sa1 -> sa2 -> sa3 -> fp3 -> fp2 -> fp1 -> l0_points
+    [B,128,N].  ``cls_one_hot`` is the ``Categorical`` label tile [B,16,N] (layers.py:7-14) the caller
+    supplies; the FC head (conv1/bn1/conv2, :68-71) is outside this library's scope."""
+
+    def __init__(self, num_classes=16, additional_channel=0):
+        super().__init__()
+        self.enc = MSGSegSetAbstractionStack(additional_channel)
+        self.fp3 = PointNetFeaturePropagation(in_channel=1536, mlp=[256, 256])
+        self.fp2 = PointNetFeaturePropagation(in_channel=576, mlp=[256, 128])
+        self.fp1 = PointNetFeaturePropagation(in_channel=128 + num_classes + 6 + additional_channel, mlp=[128, 128])
+
+    def forward(self, xyz, cls_one_hot, start_idx=(None, None)):
+        l0_xyz, l0_points = xyz, xyz
+        l1_xyz, l1_points = self.enc.sa1(l0_xyz, l0_points, start_idx=start_idx[0])
+        l2_xyz, l2_points = self.enc.sa2(l1_xyz, l1_points, start_idx=start_idx[1])
+        l3_xyz, l3_points = self.enc.sa3(l2_xyz, l2_points)
+        l2_points = self.fp3(l2_xyz, l3_xyz, l2_points, l3_points)
+        l1_points = self.fp2(l1_xyz, l2_xyz, l1_points, l2_points)
+        l0_points = self.fp1(l0_xyz, l1_xyz, torch.cat([cls_one_hot, l0_xyz, l0_points], dim=1), l1_points)
+        return l0_points

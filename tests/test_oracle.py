@@ -200,3 +200,29 @@ def test_pfn_and_scatter_oracle_shapes():
     p = 17
     np.testing.assert_array_equal(canvas[0, :, c[p, 1], c[p, 2]], out[p])
     assert int((np.abs(canvas).sum(1) > 0).sum()) <= v.shape[0]
+
+
+def test_feature_propagation_restatement_quirk_and_shapes():
+    """layers.py:316-324: idx is the argsort of the already sorted distances (identity), so the
+    interpolation mixes the features of sampled points 0, 1, 2 with the 3 smallest-distance weights."""
+    from oracle import layers_np as o
+    rng = np.random.default_rng(5)
+    B, N, S, D1, D2 = 2, 32, 8, 3, 5
+    xyz1 = rng.standard_normal((B, 3, N)).astype(np.float32)
+    xyz2 = np.ascontiguousarray(xyz1[:, :, :S])
+    p1 = rng.standard_normal((B, D1, N)).astype(np.float32)
+    p2 = rng.standard_normal((B, D2, S)).astype(np.float32)
+    fp = o.PointNetFeaturePropagation(D1 + D2, [4, 6])
+    z = fp.interpolate(xyz1, xyz2, p1, p2)
+    assert z.shape == (B, N, D1 + D2)
+    np.testing.assert_array_equal(z[:, :, :D1], p1.transpose(0, 2, 1))
+    # hand computation for one point
+    d = np.sort(o.square_distance(xyz1.transpose(0, 2, 1), xyz2.transpose(0, 2, 1)), -1)[0, 7, :3]
+    w = (np.float32(1) / (d + np.float32(1e-8)))
+    w = w / w.sum()
+    want = (p2[0, :, :3] * w[None, :]).sum(1)
+    np.testing.assert_allclose(z[0, 7, D1:], want, rtol=1e-6, atol=1e-6)
+    # S == 1 tiles
+    z1 = fp.interpolate(xyz1, xyz2[:, :, :1], None, p2[:, :, :1])
+    np.testing.assert_array_equal(z1, np.tile(p2[:, :, :1].transpose(0, 2, 1), [1, N, 1]))
+    assert fp(xyz1, xyz2, p1, p2).shape == (B, 6, N)

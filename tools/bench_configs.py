@@ -43,6 +43,14 @@ ms = timeit(lambda: msg(xyz, xyz, start_idx=(st1, st2)))
 out["C3_msg_seg_B16_N2048"] = {"ms_per_forward": ms, "points_per_s": B * N / (ms / 1e3), "gflop": 142.6,
                                "tflops": 142.6e9 / (ms / 1e3) / 1e12}
 
+# ---- C3 + the decoder: sa1..sa3 -> fp3 -> fp2 -> fp1
+seg = sa_stack.MSGSegEncoderDecoder().to(dev)
+onehot = torch.zeros((B, 16, N), device=dev)
+onehot[:, 3, :] = 1.0
+ms2 = timeit(lambda: seg(xyz, onehot, start_idx=(st1, st2)))
+out["C3_msg_seg_with_feature_propagation"] = {"ms_per_forward": ms2, "points_per_s": B * N / (ms2 / 1e3),
+                                              "decoder_ms": ms2 - ms}
+
 # ---- C4: pillar encode, 2 frames of 20 000 points (yaml geometry), device-resident chain
 frames = [torch.from_numpy(synth.lidar_frame(20000, seed=s)).to(dev) for s in (0, 1)]
 pfn = pillars.PillarFeatureNet(num_input_features=4, use_norm=True, num_filters=(64,), with_distance=False,
