@@ -84,3 +84,42 @@ class MSGSegEncoderDecoder(torch.nn.Module):
         l1_points = self.fp2(l1_xyz, l2_xyz, l1_points, l2_points)
         l0_points = self.fp1(l0_xyz, l1_xyz, torch.cat([cls_one_hot, l0_xyz, l0_points], dim=1), l1_points)
         return l0_points
+
+
+class GraphedForward:
+    """A forward pass captured once in a CUDA graph and replayed: the ~25 launches, event forks and
+    memsets of a SetAbstraction stack become one ``cudaGraphLaunch`` (the side-stream sampling
+    overlap and the programmatic dependent launches are captured as graph edges).  Inputs live in
+    static buffers: ``g(x)`` copies ``x`` into them, replays, and returns the static outputs (valid
+    until the next replay).  Shapes and parameters are frozen at capture time.
+
+        g = GraphedForward(lambda x: model(x, None, start_idx=(st1, st2)), xyz_example)
+        l3_xyz, l3_points = g(xyz)
+    """
+
+    def __init__(self, fn, *example_inputs, warmup=3):
+        from . import _lib as L
+        self.inputs = tuple(t.clone() for t in example_inputs)
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):      # warm up off the capture: one-time kernel attribute calls,
+            for _ in range(warmup):        # allocator pools, lazy module loads
+                fn(*self.inputs)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        lib = L.lib()
+        n0 = lib.papc_launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.outputs = fn(*self.inputs)
+        self.kernels_per_replay = int(lib.papc_launch_count() - n0)   # library kernels inside the graph
+
+    def replay(self):
+        self.graph.replay()
+        return self.outputs
+
+    def __call__(self, *inputs):
+        for dst, src in zip(self.inputs, inputs):
+            dst.copy_(src, non_blocking=True)
+        return self.replay()

@@ -309,3 +309,25 @@ def test_launch_profiler_records_kernels():
     assert all(r["ms"] > 0 and r["bytes"] > 0 for r in recs)
     assert recs[0]["M"] == 4 * 256 and recs[0]["cin"] == 64
     assert lib.papc_prof_count() == 0
+
+
+def test_graphed_forward_matches_eager():
+    """sa_stack.GraphedForward: the captured graph (side-stream sampling and dependent launches
+    included) replays to exactly the eager result, also after the input buffer is refilled."""
+    from papc_b200 import sa_stack
+    B, N = 4, 1024
+    model = sa_stack.SSGSetAbstractionStack().to(DEV)
+    for i, sa in enumerate(model.layers_()):
+        c = [(3, [64, 64, 128]), (131, [128, 128, 256]), (259, [256, 512, 1024])][i]
+        sa_stack.load_conv_bn(sa.mlp_convs, sa.mlp_bns, synth.mlp_params(c[0], c[1], seed=20 + i))
+    st1 = _cu(synth.fps_start(B, N, seed=5))
+    st2 = torch.zeros(B, dtype=torch.int64, device=DEV)
+    xa, xb = _cu(synth.clouds(B, N, seed=6)), _cu(synth.clouds(B, N, seed=7))
+    fn = lambda x: model(x, None, start_idx=(st1, st2))  # noqa: E731
+    g = sa_stack.GraphedForward(fn, xa)
+    assert g.kernels_per_replay > 10
+    for x in (xa, xb, xa):
+        want = fn(x)[1].clone()
+        got = g(x)[1]
+        torch.cuda.synchronize()
+        assert torch.equal(got, want)
