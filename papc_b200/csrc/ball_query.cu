@@ -95,7 +95,7 @@ gather_rows_kernel(const float *__restrict__ points, const int64_t *__restrict__
 // ------------------------------------------------------------------ query_ball_point
 constexpr int kBqWarps = 8;
 constexpr int kBqQPW = 1;       // queries per warp (4 measured slower: fewer, longer warps; scanning, not staging, is the cost)
-constexpr int kBqChunk = 2048;  // points per shared-memory stage: 24 KB xyz + 8 KB |p|^2
+constexpr int kBqChunk = 2048;  // points per shared-memory stage: 32 KB (x,y,z,|p|^2) + 24 KB AoS landing zone
 
 template <typename IdxT>
 __global__ void __launch_bounds__(kBqWarps * 32)
@@ -106,8 +106,8 @@ ball_query_kernel(const float *__restrict__ xyz, const float *__restrict__ new_x
     // [chunk] |p|^2 (small clouds take a few KB, so the kernel co-resides with the MLP kernels)
     extern __shared__ __align__(128) float s_dyn[];
     const int chunk = N < kBqChunk ? ((N + 3) & ~3) : kBqChunk;
-    float *s_p = s_dyn;
-    float *s_n = s_dyn + chunk * 3;
+    float4 *s_q = reinterpret_cast<float4 *>(s_dyn);  // [chunk] (x, y, z, |p|^2): one LDS.128 per test
+    float *s_p = s_dyn + chunk * 4;                    // [chunk*3] AoS landing zone of the bulk copy
     __shared__ __align__(8) uint64_t s_bar;
 
     const int b = blockIdx.y;
@@ -158,8 +158,10 @@ ball_query_kernel(const float *__restrict__ xyz, const float *__restrict__ new_x
             for (int i = tid; i < n * 3; i += kBqWarps * 32) s_p[i] = gsrc[i];
             __syncthreads();
         }
-        for (int j = tid; j < n; j += kBqWarps * 32)
-            s_n[j] = sq3(s_p[j * 3 + 0], s_p[j * 3 + 1], s_p[j * 3 + 2]);
+        for (int j = tid; j < n; j += kBqWarps * 32) {
+            const float x = s_p[j * 3 + 0], y = s_p[j * 3 + 1], z = s_p[j * 3 + 2];
+            s_q[j] = make_float4(x, y, z, sq3(x, y, z));
+        }
         __syncthreads();
 
 #pragma unroll
@@ -170,8 +172,8 @@ ball_query_kernel(const float *__restrict__ xyz, const float *__restrict__ new_x
                 const int j = j0 + lane;
                 bool in = false;
                 if (j < n) {
-                    const float d = sqdist_expanded(qx[i], qy[i], qz[i], qn[i], s_p[j * 3 + 0], s_p[j * 3 + 1],
-                                                    s_p[j * 3 + 2], s_n[j]);
+                    const float4 p = s_q[j];
+                    const float d = sqdist_expanded(qx[i], qy[i], qz[i], qn[i], p.x, p.y, p.z, p.w);
                     in = !(d > radius2);  // layers.py:112 masks "> r^2" OUT
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, in);
@@ -184,7 +186,7 @@ ball_query_kernel(const float *__restrict__ xyz, const float *__restrict__ new_x
                 }
             }
         }
-        __syncthreads();  // everyone done with s_p / s_n before the next stage overwrites it
+        __syncthreads();  // everyone done with s_q before the next stage overwrites it
     }
 #pragma unroll
     for (int i = 0; i < kBqQPW; ++i) {
@@ -279,7 +281,11 @@ extern "C" int papc_ball_query_f32(const float *xyz, const float *new_xyz, int B
     ProfScope prof(as_stream(stream), "ball_query", (long long)B * S, N, nsample, 0.0,
                    12.0 * B * (N + S) + (idx_bits / 8.0) * B * S * nsample);
     const int chunk = N < kBqChunk ? ((N + 3) & ~3) : kBqChunk;
-    const size_t smem = (size_t)chunk * 4 * sizeof(float);
+    const size_t smem = (size_t)chunk * 7 * sizeof(float);
+    if (smem > 48 * 1024) {  // only the largest chunk needs the opt-in
+        PAPC_CUDA_TRY(cudaFuncSetAttribute(ball_query_kernel<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PAPC_CUDA_TRY(cudaFuncSetAttribute(ball_query_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     if (idx_bits == 64)
         ball_query_kernel<int64_t><<<grid, kBqWarps * 32, smem, as_stream(stream)>>>(
             xyz, new_xyz, N, S, radius2, nsample, reinterpret_cast<int64_t *>(out_idx), empty_count);
