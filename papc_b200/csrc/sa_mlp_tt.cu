@@ -75,10 +75,17 @@ static_assert(kEpiWarps == 4 || kEpiWarps == 8, "epilogue warps: one or two per 
         if ((a).clk != nullptr && blockIdx.x == 0 && (tl) >= 8u && (tl) < 24u)                      \
             (a).clk[48 + ((tl) - 8u) * 8 + (e)] = clock64();                                        \
     } while (0)
+// epilogue detail stamps of CTA 0 warp 0 (local tiles 8..23): [176 + (tl-8)*8 + e]
+#define TT_ECLK(a, tl, e)                                                                           \
+    do {                                                                                            \
+        if ((a).clk != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && (tl) >= 8u && (tl) < 24u)  \
+            (a).clk[176 + ((tl) - 8u) * 8 + (e)] = clock64();                                       \
+    } while (0)
 #else
 #define TT_DBG(a, bit) 0
 #define TT_CLK(a, e) do { } while (0)
 #define TT_TCLK(a, tl, e) do { } while (0)
+#define TT_ECLK(a, tl, e) do { } while (0)
 #endif
 #ifndef PAPC_TT_PROD_WARPS
 #define PAPC_TT_PROD_WARPS 8
@@ -434,20 +441,28 @@ mlp_layer_tt_kernel(const TtArgs a) {
             const uint32_t buf = tl & 1;
             const long long m0 = tile * kTile;
             const int nrows = (int)((a.M - m0) < kTile ? (a.M - m0) : kTile);
+            TT_ECLK(a, tl, 0);   // loop top
             if (MODE == SRC_GATHER) mbar_wait(xyz_full + (tl & 3), (tl >> 2) & 1);
             mbar_wait(acc_full + buf, (tl >> 1) & 1);
+            TT_ECLK(a, tl, 1);   // accumulator barrier passed
             tc_fence_after();
+            TT_ECLK(a, tl, 2);   // tcgen05 fence done
             if (tid == 0 && tl == 0) TT_CLK(a, 5);
             if (tid == 0 && tl == 1) TT_CLK(a, 11);
             if (tid == 0) TT_TCLK(a, tl, 4);   // epilogue: accumulator ready
             uint64_t s2 = 0ull, q2 = 0ull;     // packed (even rows, odd rows) running sums
             float mx = -INFINITY, mn = INFINITY;
-#pragma unroll 1
+            long long pend_g[kBlkPerHalf];
+            float pend_mx[kBlkPerHalf], pend_mn[kBlkPerHalf];
+#pragma unroll
+            for (int bi = 0; bi < kBlkPerHalf; ++bi) { pend_g[bi] = -1; pend_mx[bi] = 0.f; pend_mn[bi] = 0.f; }
+#pragma unroll
             for (int bi = 0; bi < kBlkPerHalf; ++bi) {  // 32 accumulator columns (= rows) at a time
                 const int blk = half * kBlkPerHalf + bi;
                 uint32_t r[32];
                 tmem_ld32_nowait(lane_base + kColAcc + buf * kTile + blk * 32, r);
                 tmem_wait_ld();
+                TT_ECLK(a, tl, 3 + 2 * bi);   // block bi loaded
                 if (bi == kBlkPerHalf - 1) {
                     // this warp's share of the accumulator is in registers: hand the buffer back
                     tc_fence_before();
@@ -507,17 +522,28 @@ mlp_layer_tt_kernel(const TtArgs a) {
                     if (do_y) body(std::false_type{}, std::true_type{});
                     else body(std::false_type{}, std::false_type{});
                 }
+                TT_ECLK(a, tl, 4 + 2 * bi);   // block bi arithmetic done
                 // pooled groups of K rows end at multiples of K (K in {32, 64, 128})
                 // (K is 32 / 64 / 128 here: a mask, not a runtime integer division per block)
+                // The extrema are parked and stored after the LAST block of the tile: tcgen05.wait::ld
+                // also drains the warp's outstanding global stores (measured: the wait after a block
+                // with stores in flight took 1500 cycles instead of 300), so no store may sit between
+                // two accumulator loads.
                 if (POOL && kshift != 7 && ((((blk + 1) * 32) & (a.K - 1)) == 0)) {
-                    if (do_pool && nr > 0) {
-                        const long long g = ((m0 + blk * 32) >> kshift);
-                        a.pool_max[g * a.cout + cg] = mx;
-                        a.pool_min[g * a.cout + cg] = mn;
-                    }
+                    pend_g[bi] = (do_pool && nr > 0) ? (long long)((m0 + blk * 32) >> kshift) : -1;
+                    pend_mx[bi] = mx;
+                    pend_mn[bi] = mn;
                     mx = -INFINITY;
                     mn = INFINITY;
                 }
+            }
+            if (POOL && kshift != 7) {
+#pragma unroll
+                for (int bi = 0; bi < kBlkPerHalf; ++bi)
+                    if (pend_g[bi] >= 0) {
+                        a.pool_max[pend_g[bi] * a.cout + cg] = pend_mx[bi];
+                        a.pool_min[pend_g[bi] * a.cout + cg] = pend_mn[bi];
+                    }
             }
             if (POOL && kshift == 7) {  // K = 128: the tile is one group
                 if (kEpiHalves == 2) {
@@ -538,13 +564,16 @@ mlp_layer_tt_kernel(const TtArgs a) {
                 }
             }
             if (tid == 0) TT_TCLK(a, tl, 6);   // epilogue: tile done
+            TT_ECLK(a, tl, 6);   // (overwrites the block-1 stamp: stores issued)
             float sa, sb, qa, qb;
             unpack2(s2, sa, sb);
             unpack2(q2, qa, qb);
-            // one fp64 add per quantity and tile (the fp64 pipe is narrow; sa + sb in fp32 costs one
-            // rounding at 2^-24 relative, far inside the statistic's own fp32 accumulation error)
+            // one fp64 add per quantity and tile (sa + sb in fp32 costs one rounding at 2^-24
+            // relative, far inside the statistic's own fp32 accumulation error).  Flushing only every
+            // fourth tile was measured: no gain (the epilogue is starved, not fp64 bound).
             acc_s += (double)(sa + sb);
             acc_q += (double)(qa + qb);
+            TT_ECLK(a, tl, 7);   // tile bookkeeping done
         }
         if (tid == 0) TT_CLK(a, 6);
         if (kEpiHalves == 2) {  // fold the two halves' statistics (fixed order -> deterministic)
@@ -1283,8 +1312,8 @@ int launch(const TtArgs &a_in, cudaStream_t st) {
     static unsigned long long *d_clk = nullptr;
     const bool want_clk = getenv("PAPC_TT_CLK") != nullptr;
     if (want_clk) {
-        if (d_clk == nullptr) cudaMalloc(&d_clk, 176 * sizeof(unsigned long long));
-        cudaMemsetAsync(d_clk, 0, 176 * sizeof(unsigned long long), st);
+        if (d_clk == nullptr) cudaMalloc(&d_clk, 304 * sizeof(unsigned long long));
+        cudaMemsetAsync(d_clk, 0, 304 * sizeof(unsigned long long), st);
         cudaMemsetAsync(d_clk + 44, 0xff, sizeof(unsigned long long), st);  // atomicMin target
         a.clk = d_clk;
     }
@@ -1338,7 +1367,7 @@ int launch(const TtArgs &a_in, cudaStream_t st) {
     }
 #ifdef PAPC_TT_TRIAGE
     if (want_clk && rc == PAPC_OK) {
-        unsigned long long h[176];
+        unsigned long long h[304];
         cudaStreamSynchronize(st);
         cudaMemcpy(h, d_clk, sizeof(h), cudaMemcpyDeviceToHost);
         auto us = [&](int slot, int e) { return h[slot * 16 + e] ? (double)(h[slot * 16 + e] - h[slot * 16]) / 1965.0 : -1.0; };
@@ -1357,6 +1386,15 @@ int launch(const TtArgs &a_in, cudaStream_t st) {
                 auto u = [&](int e) { return q[e] ? (double)(q[e] - h[0]) / 1965.0 : -1.0; };
                 fprintf(stderr, "[tt tile] %2d: %7.2f %7.2f | %7.2f %7.2f (done %7.2f) | %7.2f %7.2f %7.2f\n", t + 8, u(0), u(1), u(2),
                         u(3), u(7), u(4), u(5), u(6));
+            }
+        }
+        if (getenv("PAPC_TT_EPICLK") != nullptr) {
+            fprintf(stderr, "[tt epi] cycles per phase (warp 0): wait_acc fence ld0 math0 ld1 math1 bookkeeping | tile total\n");
+            for (int t = 0; t < 16; ++t) {
+                const unsigned long long *q = h + 176 + t * 8;
+                if (q[7] == 0 || q[0] == 0) continue;
+                fprintf(stderr, "[tt epi] %2d: %6llu %6llu %6llu %6llu %6llu %6llu %6llu | %6llu\n", t + 8, q[1] - q[0], q[2] - q[1],
+                        q[3] - q[2], q[4] - q[3], q[5] - q[4], q[6] - q[5], q[7] - q[6], q[7] - q[0]);
             }
         }
         fprintf(stderr, "[tt clk]   globaltimer: first entry -> last exit %.2f us, longest CTA %.2f us, mean CTA %.2f us\n",
