@@ -674,15 +674,12 @@ mlp_layer_tt_kernel(const TtArgs a) {
         const uint32_t swz = (uint32_t)((u ^ (rb & 7)) << 4);
         const bool has_act = (MODE == SRC_PLAIN) && a.in_scale != nullptr;
         pdl_wait();
-        if (MODE == SRC_PLAIN)
-            for (int k = ptid; k < kMaxAct; k += kProdThreads) {
-                s_scale[k] = (has_act && k < a.cin) ? a.in_scale[k] : 0.f;
-                s_shift[k] = (has_act && k < a.cin) ? a.in_shift[k] : 0.f;
-            }
+        // SRC_PLAIN fills the scale / shift table after its first activation copies are in flight
+        // (below): the two global round trips overlap instead of adding up at every kernel start.
         if (MODE == SRC_POINTMLP && ptid < kMaxFold)
             s_fold[ptid] = ptid < a.cin ? reinterpret_cast<const float4 *>(a.l0_fold)[ptid]
                                         : make_float4(0.f, 0.f, 0.f, 0.f);
-        named_bar_sync(1, kProdThreads);
+        if (MODE != SRC_PLAIN) named_bar_sync(1, kProdThreads);
 
         // ---- per-row geometry pipeline (SRC_GATHER / SRC_POINTMLP)
         long long src[kRPT] = {};          // b*N + n of the rows of the tile being issued
@@ -955,6 +952,13 @@ mlp_layer_tt_kernel(const TtArgs a) {
             for (int n = 0; n < R - 1; ++n) {
                 if (ti < tiles_m) { issue(ti, ci, n); advance(ti, ci); }
                 cp_async_commit();
+            }
+            if (MODE == SRC_PLAIN) {
+                for (int k = ptid; k < kMaxAct; k += kProdThreads) {
+                    s_scale[k] = (has_act && k < a.cin) ? a.in_scale[k] : 0.f;
+                    s_shift[k] = (has_act && k < a.cin) ? a.in_shift[k] : 0.f;
+                }
+                named_bar_sync(1, kProdThreads);
             }
             // The next chunk's copies are issued AFTER this chunk has been processed: process() ends in
             // fence.proxy.async (a CTA-scope membar underneath), which waits for the thread's outstanding
