@@ -1116,45 +1116,94 @@ point_moments_kernel(const MomentArgs a) {
         // four rows per trip, their dependent load chains (index -> point, centroid) issued together;
         // the fp32 run length stays bounded (flush to fp64 every 4 trips = 16 rows)
         constexpr int R = 4;
-        const long long stride = (long long)gridDim.x * kMomThreads;
         int trips = 0;
-        for (long long row0 = (long long)blockIdx.x * kMomThreads + tid; row0 < a.M; row0 += R * stride) {
-            int n[R];
-            RowGeom rg[R];
-            bool ok[R];
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const long long row = row0 + r * stride;
-                ok[r] = row < a.M;
-                rg[r] = row_geom(ok[r] ? row : 0, a);
-                n[r] = (a.idx != nullptr && ok[r]) ? __ldg(a.idx + row) : rg[r].k;
-            }
-            float px[R], py[R], pz[R], cx[R], cy[R], cz[R];
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const int nn = min(max(n[r], 0), a.N - 1);
-                const float *q = a.xyz + (rg[r].bN + nn) * 3;
-                px[r] = __ldg(q); py[r] = __ldg(q + 1); pz[r] = __ldg(q + 2);
-                cx[r] = cy[r] = cz[r] = 0.f;
-                if (a.new_xyz != nullptr) {
-                    const float *cc = a.new_xyz + (long long)rg[r].g * 3;
-                    cx[r] = __ldg(cc); cy[r] = __ldg(cc + 1); cz[r] = __ldg(cc + 2);
-                }
-            }
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                if (!ok[r]) continue;
-                const float x = a.new_xyz != nullptr ? __fsub_rn(px[r], cx[r]) : px[r];
-                const float y = a.new_xyz != nullptr ? __fsub_rn(py[r], cy[r]) : py[r];
-                const float z = a.new_xyz != nullptr ? __fsub_rn(pz[r], cz[r]) : pz[r];
-                acc[0] += x; acc[1] += y; acc[2] += z;
-                acc[3] = fmaf(x, x, acc[3]); acc[4] = fmaf(x, y, acc[4]); acc[5] = fmaf(x, z, acc[5]);
-                acc[6] = fmaf(y, y, acc[6]); acc[7] = fmaf(y, z, acc[7]); acc[8] = fmaf(z, z, acc[8]);
-            }
+        auto accumulate = [&](float x, float y, float z) {
+            acc[0] += x; acc[1] += y; acc[2] += z;
+            acc[3] = fmaf(x, x, acc[3]); acc[4] = fmaf(x, y, acc[4]); acc[5] = fmaf(x, z, acc[5]);
+            acc[6] = fmaf(y, y, acc[6]); acc[7] = fmaf(y, z, acc[7]); acc[8] = fmaf(z, z, acc[8]);
+        };
+        auto flush = [&]() {
             if (++trips == 4) {
 #pragma unroll
                 for (int i = 0; i < 9; ++i) { dacc[i] += (double)acc[i]; acc[i] = 0.f; }
                 trips = 0;
+            }
+        };
+        if (a.nslice > 0) {
+            // Staged variant: a block works on ONE cloud.  Its points (and centroids) sit in shared
+            // memory, so the random 12-byte gathers -- the cost of this kernel: 3.7 M scattered
+            // loads through L1 -- become LDS; only the (coalesced) index reads go to global memory.
+            extern __shared__ float s_pts[];               // [N*3] xyz, then [S*3] new_xyz
+            const int b = blockIdx.x / a.nslice, sl = blockIdx.x - b * a.nslice;
+            const float *cloud = a.xyz + (long long)b * a.N * 3;
+            for (int i = tid; i < a.N * 3; i += kMomThreads) s_pts[i] = __ldg(cloud + i);
+            float *s_ctr = s_pts + a.N * 3;
+            if (a.new_xyz != nullptr) {
+                const float *ctr = a.new_xyz + (long long)b * a.S * 3;
+                for (int i = tid; i < a.S * 3; i += kMomThreads) s_ctr[i] = __ldg(ctr + i);
+            }
+            __syncthreads();
+            const int rows = a.S * a.K;                    // rows of this cloud
+            const int per = (rows + a.nslice - 1) / a.nslice;
+            const int r_end = min(rows, (sl + 1) * per);
+            const long long row_base = (long long)b * rows;
+            for (int r0 = sl * per + tid; r0 < r_end; r0 += R * kMomThreads) {
+                int n[R];
+                int g[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int rl = r0 + r * kMomThreads;
+                    const bool ok = rl < r_end;
+                    g[r] = ok ? (int)fastdiv((uint32_t)rl, a.kmul, a.kshr) : -1;
+                    n[r] = !ok ? 0 : (a.idx != nullptr ? __ldg(a.idx + row_base + rl) : rl - g[r] * a.K);
+                }
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if (g[r] < 0) continue;
+                    const int nn = min(max(n[r], 0), a.N - 1);
+                    float x = s_pts[nn * 3], y = s_pts[nn * 3 + 1], z = s_pts[nn * 3 + 2];
+                    if (a.new_xyz != nullptr) {
+                        x = __fsub_rn(x, s_ctr[g[r] * 3]);
+                        y = __fsub_rn(y, s_ctr[g[r] * 3 + 1]);
+                        z = __fsub_rn(z, s_ctr[g[r] * 3 + 2]);
+                    }
+                    accumulate(x, y, z);
+                }
+                flush();
+            }
+        } else {
+            const long long stride = (long long)gridDim.x * kMomThreads;
+            for (long long row0 = (long long)blockIdx.x * kMomThreads + tid; row0 < a.M; row0 += R * stride) {
+                int n[R];
+                RowGeom rg[R];
+                bool ok[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const long long row = row0 + r * stride;
+                    ok[r] = row < a.M;
+                    rg[r] = row_geom(ok[r] ? row : 0, a);
+                    n[r] = (a.idx != nullptr && ok[r]) ? __ldg(a.idx + row) : rg[r].k;
+                }
+                float px[R], py[R], pz[R], cx[R], cy[R], cz[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int nn = min(max(n[r], 0), a.N - 1);
+                    const float *q = a.xyz + (rg[r].bN + nn) * 3;
+                    px[r] = __ldg(q); py[r] = __ldg(q + 1); pz[r] = __ldg(q + 2);
+                    cx[r] = cy[r] = cz[r] = 0.f;
+                    if (a.new_xyz != nullptr) {
+                        const float *cc = a.new_xyz + (long long)rg[r].g * 3;
+                        cx[r] = __ldg(cc); cy[r] = __ldg(cc + 1); cz[r] = __ldg(cc + 2);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if (!ok[r]) continue;
+                    accumulate(a.new_xyz != nullptr ? __fsub_rn(px[r], cx[r]) : px[r],
+                               a.new_xyz != nullptr ? __fsub_rn(py[r], cy[r]) : py[r],
+                               a.new_xyz != nullptr ? __fsub_rn(pz[r], cz[r]) : pz[r]);
+                }
+                flush();
             }
         }
 #pragma unroll
@@ -1180,10 +1229,23 @@ point_moments_kernel(const MomentArgs a) {
         __syncthreads();
         if (s_islast == 0u) return;
         __threadfence();
-        if (tid < 9) {
-            double v = 0.0;
-            for (int b = 0; b < (int)gridDim.x; ++b) v += __ldcg(a.partial + (long long)b * 9 + tid);
-            s_tot[tid] = v / (double)a.M;
+        {
+            // 9 quantities x 28 slices of the block rows in parallel (fixed order -> deterministic):
+            // nine threads walking ~300 rows one load at a time was most of this kernel's time
+            __shared__ double s_sl[28][9];
+            const int q = tid % 9, sl = tid / 9;
+            if (sl < 28) {
+                double v = 0.0;
+                for (int b = sl; b < (int)gridDim.x; b += 28) v += __ldcg(a.partial + (long long)b * 9 + q);
+                s_sl[sl][q] = v;
+            }
+            __syncthreads();
+            if (tid < 9) {
+                double v = 0.0;
+#pragma unroll
+                for (int k = 0; k < 28; ++k) v += s_sl[k][tid];
+                s_tot[tid] = v / (double)a.M;
+            }
         }
         if (tid == 0) *a.counter = 0u;
         __syncthreads();
@@ -1420,9 +1482,31 @@ int launch_moments(const MomentArgs &a_in, cudaStream_t st) {
     a.fastgeom = a.M < (1LL << 31) && a.K >= 1 && a.S >= 1;
     make_fastdiv((uint32_t)(a.K >= 1 ? a.K : 1), &a.kmul, &a.kshr);
     make_fastdiv((uint32_t)(a.S >= 1 ? a.S : 1), &a.smul, &a.sshr);
-    const int blocks = a.running_mean != nullptr ? 1 : moment_blocks(a.M);
+    int blocks = a.running_mean != nullptr ? 1 : moment_blocks(a.M);
+    size_t smem = 0;
+    a.nslice = 0;
+    // one cloud per block, staged in shared memory, when the batch provides enough blocks and the
+    // cloud fits; B = M / (S * K)
+    const long long rows_per_cloud = (long long)a.S * a.K;
+    const long long B = rows_per_cloud > 0 ? a.M / rows_per_cloud : 0;
+    const size_t need = ((size_t)a.N + (a.new_xyz ? (size_t)a.S : 0)) * 3 * sizeof(float);
+    if (a.running_mean == nullptr && a.fastgeom && B >= 1 && B * rows_per_cloud == a.M && B <= 2 * kNumSMs &&
+        need <= 96 * 1024 && rows_per_cloud < (1LL << 31)) {
+        int ns = (int)((2 * kNumSMs) / B);
+        const int max_ns = (int)ceil_div<long long>(rows_per_cloud, 4 * kMomThreads);
+        if (ns > max_ns) ns = max_ns;
+        if (ns < 1) ns = 1;
+        a.nslice = ns;
+        blocks = (int)(B * ns);
+        smem = need;
+        static bool configured = false;
+        if (!configured && smem > 48 * 1024) {
+            PAPC_CUDA_TRY(cudaFuncSetAttribute(point_moments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            configured = true;
+        }
+    }
     ProfScope prof(st, "point_moments", a.M, 3, a.c0, 0.0, 16.0 * (double)a.M);
-    point_moments_kernel<<<blocks, kMomThreads, 0, st>>>(a);
+    point_moments_kernel<<<blocks, kMomThreads, smem, st>>>(a);
     PAPC_LAUNCH_CHECK();
     return PAPC_OK;
 }

@@ -110,6 +110,7 @@ struct MomentArgs {
     float sqrt_M;
     uint32_t kmul, kshr, smul, sshr;  // as TtArgs (filled in by launch_moments)
     int fastgeom;
+    int nslice;             // > 0: staged variant, nslice blocks per cloud (filled in by launch_moments)
     double *partial;        // [blocks][9]
     unsigned int *counter;
     float *scale, *shift, *mean_out, *var_out;  // [c0] (mean/var nullable)
