@@ -216,8 +216,18 @@ def _sample(xyz, ready, npoint, start_idx, queries):
 
 
 def _tag_ready(t, ev):
-    t._papc_ready = ev
+    """Attach the producer's event (and the tensor's version counter: an in-place modification by the
+    caller after the layer returned invalidates the tag, see ``_ready_event``)."""
+    t._papc_ready = (ev, t._version)
     return t
+
+
+def _ready_event(t):
+    tag = getattr(t, "_papc_ready", None)
+    if tag is None:
+        return None
+    ev, version = tag
+    return ev if t._version == version else None
 
 
 class Conv2D:
@@ -433,7 +443,7 @@ class PointNetSetAbstraction(_SAMixin):
     def forward(self, xyz, points, start_idx=None):
         """xyz [B,3,N], points [B,D,N] | None -> (new_xyz [B,3,S], new_points [B,D',S])."""
         L.require_cuda(xyz, points)
-        ready = getattr(xyz, "_papc_ready", None)
+        ready = _ready_event(xyz)
         xyz = L.f32c(xyz.transpose(1, 2))                                  # :203
         feats = L.f32c(points.transpose(1, 2)) if points is not None else None  # :205
         B, N, Cc = xyz.shape
@@ -489,7 +499,7 @@ class PointNetSetAbstractionMsg(_SAMixin):
 
     def forward(self, xyz, points, start_idx=None):
         L.require_cuda(xyz, points)
-        ready = getattr(xyz, "_papc_ready", None)
+        ready = _ready_event(xyz)
         xyz = L.f32c(xyz.transpose(1, 2))
         feats = L.f32c(points.transpose(1, 2)) if points is not None else None
         B, N, Cc = xyz.shape

@@ -281,7 +281,9 @@ def test_sampling_overlap_is_transparent(monkeypatch):
     for flag in (True, False):
         monkeypatch.setattr(layers, "OVERLAP_SAMPLING", flag)
         l1_xyz, _ = model.sa1(xyz, None, start_idx=st1)
-        assert hasattr(l1_xyz, "_papc_ready")
+        assert hasattr(l1_xyz, "_papc_ready") and layers._ready_event(l1_xyz) is not None
+        l1_xyz.add_(0.0)   # an in-place edit by the caller invalidates the tag (no stale overlap)
+        assert layers._ready_event(l1_xyz) is None
         for _ in range(3):  # repeated calls exercise the side stream's buffer reuse
             l3_xyz, l3 = model(xyz, None, start_idx=(st1, st2))
         torch.cuda.synchronize()
