@@ -333,3 +333,25 @@ def test_graphed_forward_matches_eager():
         got = g(x)[1]
         torch.cuda.synchronize()
         assert torch.equal(got, want)
+
+
+def test_msg_sa1_c3_shapes_vs_oracle():
+    """BASELINE config 3 (PointNet2_MSG_Seg sa1, segment/pointnet2/pointnet2.py:62: 2048 points,
+    512 centroids, radii .1/.2/.4 with 32/64/128 samples, features = xyz) at the real layer sizes
+    with a reduced batch, against the oracle: new_xyz bit-exact, [B,320,512] features within 1e-5."""
+    rng = np.random.default_rng(31)
+    B, N = 2, 2048
+    xyz = synth.clouds(B, N, seed=12)
+    start = synth.fps_start(B, N, seed=13)
+    margs = (512, [0.1, 0.2, 0.4], [32, 64, 128], 3, [[32, 32, 64], [64, 64, 128], [64, 96, 128]])
+    gpu = layers.PointNetSetAbstractionMsg(*margs)
+    ref = layers_np.PointNetSetAbstractionMsg(*margs)
+    for i, m in enumerate(margs[4]):
+        _set_params(gpu.conv_blocks[i], gpu.bn_blocks[i], ref.conv_blocks[i], ref.bn_blocks[i],
+                    synth.mlp_params(6, m, seed=14 + i), rng)
+    gpu.to(DEV)
+    gx, gp = gpu(_cu(xyz), _cu(xyz), start_idx=_cu(start))
+    rx, rp = ref(xyz, xyz, start_idx=start)
+    assert tuple(gp.shape) == rp.shape == (B, 320, 512)
+    np.testing.assert_array_equal(gx.cpu().numpy(), rx)
+    np.testing.assert_allclose(gp.cpu().numpy(), rp, **TOL)
