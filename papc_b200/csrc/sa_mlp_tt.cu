@@ -153,7 +153,7 @@ struct SmemLayout {
     static constexpr uint32_t xstat = xpool + 2 * kTile * 8;         // [128] double2: statistic sums
     static constexpr uint32_t cs = xstat + kTile * 16;               // [512] float: fp16 column scale of W
     static constexpr uint32_t bars = cs + kMaxAct * 4;
-    static constexpr uint32_t nbars = 2 * 6 + 2 + 2 + 1 + 4;
+    static constexpr uint32_t nbars = 2 * 6 + 2 + 2 + 1 + 4 + 2 * 4;  // ... + raw_full[4], raw_empty[4]
     static constexpr uint32_t misc = bars + nbars * 8;               // tmem slot, last-CTA flag
     static constexpr uint32_t ring = (misc + 16 + 1023) / 1024 * 1024;  // operand ring (1024-aligned)
 };
@@ -266,7 +266,7 @@ prep_wimg_kernel(const float *__restrict__ W, int wld, int wk0, int cin, int cou
 // WMODE 0: W resident in tensor memory (TS UMMA).  WMODE 1: W chunks streamed through the ring.
 template <int MODE, int PREC, int WMODE, bool POOL>
 __global__ void __launch_bounds__(kThreads, 1)
-mlp_layer_tt_kernel(const TtArgs a) {
+mlp_layer_tt_kernel(const __grid_constant__ TtArgs a) {
     using P = Prec<PREC>;
     using CF = Cfg<MODE, PREC, WMODE>;
     constexpr int kStages = CF::kStages;
@@ -284,6 +284,8 @@ mlp_layer_tt_kernel(const TtArgs a) {
     uint64_t *acc_empty = acc_full + 2;
     uint64_t *w_ready = acc_empty + 2;
     uint64_t *xyz_full = w_ready + 1;
+    uint64_t *raw_full = xyz_full + 4;    // SRC_PLAIN: the raw stage's 128 row copies (TMA) have landed
+    uint64_t *raw_empty = raw_full + 4;   // ... every producer warp has read the raw stage
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SmemLayout::misc);
     uint32_t *s_last = tmem_slot + 1;
 
@@ -318,6 +320,10 @@ mlp_layer_tt_kernel(const TtArgs a) {
         }
         mbar_init(w_ready, kEpiWarps);
         for (int b = 0; b < 4; ++b) mbar_init(xyz_full + b, kProdWarps);
+        for (int b = 0; b < 4; ++b) {
+            mbar_init(raw_full + b, a.tma2d ? 1 : kTile);  // one arrive.expect_tx per issuing thread
+            mbar_init(raw_empty + b, kProdWarps);
+        }
         fence_mbar_init();
     }
     if (warp == kMmaWarp) tmem_alloc<kTmemCols>(tmem_slot);
@@ -743,32 +749,44 @@ mlp_layer_tt_kernel(const TtArgs a) {
             return sm + CF::raw + rs * CF::kRawStageBytes + kProdThreads * 16 * (kRPT * NV) +
                    4 * (q * kTile + rb + kRowStride * (u & (kRPT - 1)));
         };
+        uint32_t raw_issued = 0, raw_read = 0;  // SRC_PLAIN: chunks issued into / read from the raw ring
         auto issue = [&](long long tile, int c, int rs) {  // chunk (tile, c) -> raw stage rs
             if (TT_DBG(a, 16)) return;                          // triage: no global loads
             const long long m0 = tile * kTile;
             const int k0 = c * P::kEPC + u * P::kEPU;
             if (MODE == SRC_PLAIN) {
-                const bool ok = k0 < a.cin;
-                if (m0 + kTile <= a.M) {
-                    // full tile: one 64-bit multiply, the rows are a constant stride apart
-                    const float *p = ok ? a.x + ((m0 + rb) * a.cin + k0) : a.x;
-                    const long long rstep = ok ? (long long)kRowStride * a.cin : 0;
-#pragma unroll
-                    for (int j = 0; j < kRPT; ++j) {
-#pragma unroll
-                        for (int h = 0; h < NV; ++h) cp_async16(raw_slot(rs, j * NV + h), p + (ok ? 4 * h : 0), ok);
-                        p += rstep;
+                // The raw fp32 tile arrives through the TMA unit, not through the LSU: the LSU / MIO path of
+                // this SM is shared with the epilogue's TMEM loads and stores, and 2 048 16-byte cp.async per
+                // chunk cost 25-40 % of the kernel at a third of the HBM rate.  Default: ONE 2-D tensor copy
+                // per chunk (measured on B200: sa2.l3 141 -> 98 us, sa1.l3 87 -> 59 us, step 0.645 -> 0.601 ms).
+                // Fallback (no descriptor: M >= 2^31 or the driver entry point is missing): one bulk copy per
+                // row, thread r < 128 owns row r (correct but slower than cp.async: 128 small copies per chunk).
+                if (a.tma2d) {
+                    // one 2-D tensor copy per chunk: box = 128 rows x kEPC floats at (k = c*kEPC, row = m0);
+                    // rows >= M and columns >= cin arrive as zeros (out-of-bounds fill)
+                    if (ptid == 0) {
+                        const uint32_t use = raw_issued / (uint32_t)(CF::kRawStages > 0 ? CF::kRawStages : 1);
+                        mbar_wait(raw_empty + rs, (use & 1u) ^ 1u);
+                        mbar_expect_tx(raw_full + rs, (uint32_t)(kTile * P::kEPC * 4));
+                        asm volatile(
+                            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                            ::"r"(sm + CF::raw + rs * CF::kRawStageBytes), "l"(reinterpret_cast<uint64_t>(&a.xmap)),
+                            "r"(c * P::kEPC), "r"((int)m0), "r"(smem_u32(raw_full + rs))
+                            : "memory");
                     }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < kRPT; ++j) {
-                        long long row = m0 + rb + kRowStride * j;
-                        row = row < a.M ? row : a.M - 1;
-                        const float *p = ok ? a.x + row * a.cin + k0 : a.x;
-#pragma unroll
-                        for (int h = 0; h < NV; ++h) cp_async16(raw_slot(rs, j * NV + h), p + (ok ? 4 * h : 0), ok);
-                    }
+                } else if (ptid < kTile) {
+                    long long row = m0 + ptid;
+                    row = row < a.M ? row : a.M - 1;
+                    if (TT_DBG(a, 128)) row = ptid;
+                    const int kleft = a.cin - c * P::kEPC;                       // > 0
+                    const uint32_t bytes = (uint32_t)(kleft < P::kEPC ? kleft : P::kEPC) * 4u;
+                    const uint32_t use = raw_issued / (uint32_t)(CF::kRawStages > 0 ? CF::kRawStages : 1);  // previous uses of this stage
+                    mbar_wait(raw_empty + rs, (use & 1u) ^ 1u);
+                    mbar_expect_tx(raw_full + rs, bytes);
+                    bulk_g2s(smem + CF::raw + rs * CF::kRawStageBytes + ptid * (P::kEPC * 4),
+                             a.x + row * a.cin + c * P::kEPC, bytes, raw_full + rs);
                 }
+                ++raw_issued;
             } else if (MODE == SRC_GATHER) {
                 if (c == 0) {
 #pragma unroll
@@ -812,12 +830,28 @@ mlp_layer_tt_kernel(const TtArgs a) {
             float e0 = 0.f, e1 = 0.f, e2 = 0.f;
             if (MODE == SRC_PLAIN || MODE == SRC_GATHER) {
                 float4 v[kRPT][NV];
+                if (MODE == SRC_PLAIN && !TT_DBG(a, 16)) {
+                    mbar_wait(raw_full + rs, (raw_read / (uint32_t)(CF::kRawStages > 0 ? CF::kRawStages : 1)) & 1u);
+                    const bool kok = k0 < a.cin;  // whole 16-byte units are valid or not (cin % kEPU == 0)
 #pragma unroll
-                for (int j = 0; j < kRPT; ++j)
+                    for (int j = 0; j < kRPT; ++j)
 #pragma unroll
-                    for (int h = 0; h < NV; ++h)
-                        v[j][h] = TT_DBG(a, 16) ? make_float4(1.f, 2.f, 3.f, (float)c)
-                                               : lds128f(raw_slot(rs, j * NV + h));
+                        for (int h = 0; h < NV; ++h) {
+                            const float4 t = lds128f(sm + CF::raw + rs * CF::kRawStageBytes +
+                                                     (uint32_t)(rb + kRowStride * j) * (P::kEPC * 4) + (u * NV + h) * 16);
+                            v[j][h] = kok ? t : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(raw_empty + rs);  // the values are in registers
+                    ++raw_read;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < kRPT; ++j)
+#pragma unroll
+                        for (int h = 0; h < NV; ++h)
+                            v[j][h] = TT_DBG(a, 16) ? make_float4(1.f, 2.f, 3.f, (float)c)
+                                                   : lds128f(raw_slot(rs, j * NV + h));
+                }
                 if (MODE == SRC_GATHER && c == 0 && u < kRPT && !TT_DBG(a, 16)) {
                     e0 = lds32f(raw_xyz(rs, 0)); e1 = lds32f(raw_xyz(rs, 1)); e2 = lds32f(raw_xyz(rs, 2));
                     if (a.new_xyz != nullptr) {
@@ -1417,6 +1451,33 @@ int launch(const TtArgs &a_in, cudaStream_t st) {
     if (gm > tiles_m) gm = tiles_m;
     if (a.stats_partial != nullptr && gm > a.partial_rows) gm = a.partial_rows;
     const int grid = (int)(gm * nt);
+    a.tma2d = 0;
+    {
+        const char *e = getenv("PAPC_TT_TMA2D");  // A/B switch: PAPC_TT_TMA2D=0 falls back to per-row bulk copies
+        if (a.mode == SRC_PLAIN && !(e && e[0] == '0') && a.M < (1LL << 31)) {
+            typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                         const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                         CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+            static EncodeFn encode = [] {
+                void *fn = nullptr;
+                cudaDriverEntryPointQueryResult qres;
+                if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+                    qres != cudaDriverEntryPointSuccess)
+                    fn = nullptr;
+                return reinterpret_cast<EncodeFn>(fn);
+            }();
+            if (encode != nullptr) {
+                const cuuint64_t gdim[2] = {(cuuint64_t)a.cin, (cuuint64_t)a.M};
+                const cuuint64_t gstride[1] = {(cuuint64_t)a.cin * 4};
+                const cuuint32_t box[2] = {(cuuint32_t)epc(a.prec), (cuuint32_t)kTile};
+                const cuuint32_t estr[2] = {1, 1};
+                if (encode(&a.xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(a.x), gdim, gstride, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+                    a.tma2d = 1;
+            }
+        }
+    }
     int rc = PAPC_EINVAL;
     switch (a.mode) {
         case SRC_PLAIN:

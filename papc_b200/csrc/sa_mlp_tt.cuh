@@ -1,6 +1,7 @@
 // sa_mlp_tt.cuh -- interface of the transposed tcgen05 layer kernel and of the point-moment kernel
 // that lets a cin<=8 first layer be recomputed on the fly.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -66,6 +67,10 @@ struct TtArgs {
     int fastgeom;
     int dbg;  // PAPC_TT_DBG bit mask (performance triage only): 1 = producers skip loads+math,
               // 2 = no MMAs issued, 4 = epilogue skips its math / stores
+    // SRC_PLAIN: 2-D TMA descriptor of x [M, cin] (box = 128 rows x one chunk), built by launch();
+    // tma2d != 0: one cp.async.bulk.tensor per chunk replaces the per-row copies
+    alignas(64) CUtensorMap xmap;
+    int tma2d;
     unsigned long long *clk;  // triage builds: [3][16] per-phase clock64() stamps (CTA 0, CTA 1, last CTA)
 };
 

@@ -557,6 +557,34 @@ def feature_interpolate(xyz1, xyz2, points1, points2, pad_to=8):
     return out, D1 + D2
 
 
+def pointwise_mlp_rows(rows, cin, convs, bns, bn_mode="batch", update_running=False):
+    """(1x1 conv -> BatchNorm -> ReLU) x len(convs) over channels-last rows [M, ld] (ld >= cin, ld % 4 == 0,
+    columns >= cin ignored) -> [M, cout], on the tcgen05 layer kernels (``papc_pointwise_mlp_f32``).
+    ``bn_mode`` 'batch' normalises with the statistics of the M rows, 'running' with the holders'
+    ``_mean`` / ``_variance``; ``update_running`` folds the batch statistics into them (Paddle momentum)."""
+    L.require_cuda(rows)
+    if bn_mode not in ("batch", "running"):
+        raise ValueError("bn_mode must be 'batch' or 'running'")
+    rows = L.f32c(rows)
+    dev = rows.device
+    if any(c.weight.device != dev for c in convs):
+        raise L.PapcError("layer parameters are not on the input's device; call .to(device)")
+    runner = _MlpRunner(convs, bns)
+    mlp, keep, stats = runner._mlp_struct(cin, bn_mode, dev, update_running)
+    lib = L.lib()
+    M, ld = rows.shape
+    cout = convs[-1].weight.shape[0]
+    out = torch.empty((M, cout), dtype=torch.float32, device=dev)
+    wsb = lib.papc_pointwise_mlp_workspace_bytes(M, ld, C.byref(mlp))
+    ws = _ws(wsb, dev)
+    L.check(lib.papc_pointwise_mlp_f32(L.ptr(rows), M, ld, C.byref(mlp), L.ptr(out), L.ptr(ws), wsb,
+                                       L.stream_ptr(dev)), "pointwise_mlp")
+    if stats:
+        runner._update_running(stats)
+    del keep
+    return out
+
+
 class PointNetFeaturePropagation(_SAMixin):
     """layers.py:284-335.  The conv/bn holders live in plain lists like the
     reference's (:287-294), so -- as for the SetAbstraction layers -- BatchNorm runs on batch
@@ -589,20 +617,6 @@ class PointNetFeaturePropagation(_SAMixin):
         rows, cin = feature_interpolate(x1, x2, p1, p2)                     # :311-329
         if cin != self.in_channel:
             raise ValueError(f"in_channel={self.in_channel} but the concatenated input has {cin} channels")
-        dev = rows.device
-        if any(c.weight.device != dev for c in self.mlp_convs):
-            raise L.PapcError("layer parameters are not on the input's device; call .to(device)")
-        runner = _MlpRunner(self.mlp_convs, self.mlp_bns)
-        mlp, keep, stats = runner._mlp_struct(cin, self.bn_mode, dev, self.update_running_stats)
-        lib = L.lib()
-        M, ld = rows.shape
-        cout = self.mlp_convs[-1].weight.shape[0]
-        out = torch.empty((B, N, cout), dtype=torch.float32, device=dev)
-        wsb = lib.papc_pointwise_mlp_workspace_bytes(M, ld, C.byref(mlp))
-        ws = _ws(wsb, dev)
-        L.check(lib.papc_pointwise_mlp_f32(L.ptr(rows), M, ld, C.byref(mlp), L.ptr(out), L.ptr(ws), wsb,
-                                           L.stream_ptr(dev)), "pointwise_mlp")    # :332-335
-        if stats:
-            runner._update_running(stats)
-        del keep
-        return out.transpose(1, 2)
+        out = pointwise_mlp_rows(rows, cin, self.mlp_convs, self.mlp_bns, self.bn_mode,   # :332-335
+                                 update_running=self.update_running_stats)
+        return out.reshape(B, N, -1).transpose(1, 2)

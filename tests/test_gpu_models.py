@@ -1,0 +1,136 @@
+"""GPU parity tests of the four PointNet++ model definitions: the product
+models of papc_b200/models.py (CUDA through the C ABI; heads as documented there) against the NumPy
+restatement oracle/models_np.py on the same seeded inputs and the same explicit parameters.
+
+Indices (FPS, ball query) depend on xyz only and are bit-exact; the logits go through up to 23
+stacked conv+BatchNorm layers, each within 1e-5 of the oracle on its own (tests/test_gpu_sa.py,
+tests/test_gpu_fp.py) -- the whole-model bound asserted here is 1e-4 (abs + rel)."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import models_np  # noqa: E402
+from papc_b200 import models, synth  # noqa: E402
+
+DEV = "cuda:0"
+TOL = dict(rtol=1e-4, atol=1e-4)
+
+
+def _cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def _randomise_and_copy(prod, orc, seed):
+    """Non-trivial bias / gamma / beta / running statistics on the product model, then the same
+    parameters installed in the oracle model."""
+    g = torch.Generator().manual_seed(seed)
+
+    def u(n, lo, hi):
+        return (torch.rand(n, generator=g) * (hi - lo) + lo).to(DEV)
+
+    for name in ("sa1", "sa2", "sa3", "fp1", "fp2", "fp3"):
+        if not hasattr(prod, name):
+            continue
+        for (pc, pb), (oc, ob) in zip(models_np.conv_bn_lists(getattr(prod, name)),
+                                      models_np.conv_bn_lists(getattr(orc, name))):
+            for conv, bn, oconv, obn in zip(pc, pb, oc, ob):
+                cout = conv.weight.shape[0]
+                conv.bias = u(cout, -0.1, 0.1)
+                bn.weight, bn.bias = u(cout, 0.5, 1.5), u(cout, -0.2, 0.2)
+                oconv.weight = conv.weight.reshape(cout, -1, 1, 1).cpu().numpy()
+                oconv.bias = conv.bias.cpu().numpy()
+                obn.weight, obn.bias = bn.weight.cpu().numpy(), bn.bias.cpu().numpy()
+    if hasattr(prod, "fc1"):
+        with torch.no_grad():
+            for fc, bn in (("fc1", "bn1"), ("fc2", "bn2"), ("fc3", None)):
+                lin = getattr(prod, fc)
+                lin.bias.copy_(u(lin.bias.shape[0], -0.1, 0.1))
+                getattr(orc, fc).weight = lin.weight.detach().t().contiguous().cpu().numpy()   # Paddle [in,out]
+                getattr(orc, fc).bias = lin.bias.detach().cpu().numpy()
+                if bn:
+                    b, ob = getattr(prod, bn), getattr(orc, bn)
+                    n = b.weight.shape[0]
+                    b.weight.copy_(u(n, 0.5, 1.5)); b.bias.copy_(u(n, -0.2, 0.2))
+                    b._mean.copy_(u(n, -0.1, 0.1)); b._variance.copy_(u(n, 0.5, 1.5))
+                    ob.weight, ob.bias = b.weight.detach().cpu().numpy(), b.bias.detach().cpu().numpy()
+                    ob._mean, ob._variance = b._mean.cpu().numpy(), b._variance.cpu().numpy()
+    else:
+        for cname in ("conv1", "conv2"):
+            conv, oconv = getattr(prod, cname), getattr(orc, cname)
+            cout = conv.weight.shape[0]
+            conv.bias = u(cout, -0.1, 0.1)
+            oconv.weight = conv.weight.reshape(cout, -1, 1, 1).cpu().numpy()
+            oconv.bias = conv.bias.cpu().numpy()
+        b, ob = prod.bn1, orc.bn1
+        b.weight, b.bias = u(128, 0.5, 1.5), u(128, -0.2, 0.2)
+        b._mean, b._variance = u(128, -0.1, 0.1), u(128, 0.5, 1.5)
+        ob.weight, ob.bias = b.weight.cpu().numpy(), b.bias.cpu().numpy()
+        ob._mean, ob._variance = b._mean.cpu().numpy(), b._variance.cpu().numpy()
+
+
+def _inputs(B, N, normal_channel, seed):
+    xyz = synth.clouds(B, N, seed=seed)                                   # [B,3,N]
+    if normal_channel:
+        rng = np.random.default_rng(seed + 7)
+        nrm = rng.standard_normal((B, 3, N)).astype(np.float32)
+        nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+        xyz = np.concatenate([xyz, nrm], axis=1)
+    st1 = synth.fps_start(B, N, seed=seed + 1)
+    st2 = synth.fps_start(B, 512, seed=seed + 2)
+    return xyz, st1, st2
+
+
+@pytest.mark.parametrize("name,normal_channel", [("PointNet2_SSG_Clas", False), ("PointNet2_SSG_Clas", True),
+                                                 ("PointNet2_MSG_Clas", False)])
+@pytest.mark.parametrize("training", [False, True])
+def test_classify_models_match_oracle(name, normal_channel, training):
+    B, N = 4, 1024
+    torch.manual_seed(11)
+    prod = getattr(models, name)(num_classes=16, normal_channel=normal_channel).to(DEV)
+    orc = getattr(models_np, name)(num_classes=16, normal_channel=normal_channel)
+    _randomise_and_copy(prod, orc, seed=5)
+    prod.train(training); orc.train(training)
+    prod.drop1.p = prod.drop2.p = 0.0          # Paddle's dropout mask is not reproducible; see the oracle header
+    xyz, st1, st2 = _inputs(B, N, normal_channel, seed=3)
+    got = prod(_cu(xyz), start_idx=(_cu(st1), _cu(st2)))
+    ref = orc(xyz, start_idx=(st1, st2))
+    assert tuple(got.shape) == (B, 16)
+    np.testing.assert_allclose(got.detach().cpu().numpy(), ref, **TOL)
+    if training:                                # registered BatchNorm1D: running statistics moved (momentum 0.9)
+        for bn in ("bn1", "bn2"):
+            np.testing.assert_allclose(getattr(prod, bn)._mean.cpu().numpy(), getattr(orc, bn)._mean,
+                                       rtol=1e-4, atol=1e-5)
+            np.testing.assert_allclose(getattr(prod, bn)._variance.cpu().numpy(), getattr(orc, bn)._variance,
+                                       rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("name,normal_channel", [("PointNet2_SSG_Seg", False), ("PointNet2_MSG_Seg", False),
+                                                 ("PointNet2_MSG_Seg", True)])
+@pytest.mark.parametrize("training", [False, True])
+def test_segment_models_match_oracle(name, normal_channel, training):
+    B, N = 2, 1024
+    torch.manual_seed(12)
+    prod = getattr(models, name)(num_classes=16, num_parts=50, normal_channel=normal_channel).to(DEV)
+    orc = getattr(models_np, name)(num_classes=16, num_parts=50, normal_channel=normal_channel)
+    _randomise_and_copy(prod, orc, seed=6)
+    prod.train(training); orc.train(training)
+    prod.drop1.p = 0.0
+    xyz, st1, st2 = _inputs(B, N, normal_channel, seed=4)
+    labels = np.array([[3], [15]], dtype=np.int64)
+    got = prod((_cu(xyz), labels), start_idx=(_cu(st1), _cu(st2)))
+    ref = orc((xyz, labels), start_idx=(st1, st2))
+    assert tuple(got.shape) == (B, N, 50)
+    np.testing.assert_allclose(got.detach().cpu().numpy(), ref, **TOL)
+    if training:                                # bn1 is a registered layer: its running statistics move
+        np.testing.assert_allclose(prod.bn1._mean.cpu().numpy(), orc.bn1._mean, rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(prod.bn1._variance.cpu().numpy(), orc.bn1._variance, rtol=1e-4, atol=1e-5)
+
+
+def test_categorical_matches_oracle():
+    y = np.array([[0], [7], [15]], dtype=np.int64)
+    got = models.Categorical(y, 16, device=DEV).cpu().numpy()
+    np.testing.assert_array_equal(got, models_np.Categorical(y, 16))
+    with pytest.raises(IndexError):
+        models.Categorical(np.array([[16]]), 16, device=DEV)
