@@ -81,8 +81,19 @@ static_assert(kEpiWarps == 4 || kEpiWarps == 8, "epilogue warps: one or two per 
         if ((a).clk != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && (tl) >= 8u && (tl) < 24u)  \
             (a).clk[176 + ((tl) - 8u) * 8 + (e)] = clock64();                                       \
     } while (0)
+// per-CTA %globaltimer stamps of a launch (PAPC_TT_GCLK=1; no host synchronisation, so programmatic
+// dependent launch and the real kernel-to-kernel boundaries are observed): [blockIdx][8]
+#define TT_GCLK(a, e)                                                                      \
+    do {                                                                                   \
+        if ((a).gclk != nullptr) {                                                         \
+            unsigned long long t_;                                                         \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                         \
+            (a).gclk[blockIdx.x * 16 + (e)] = t_;                                           \
+        }                                                                                  \
+    } while (0)
 #else
 #define TT_DBG(a, bit) 0
+#define TT_GCLK(a, e) do { } while (0)
 #define TT_CLK(a, e) do { } while (0)
 #define TT_TCLK(a, tl, e) do { } while (0)
 #define TT_ECLK(a, tl, e) do { } while (0)
@@ -293,6 +304,7 @@ mlp_layer_tt_kernel(const __grid_constant__ TtArgs a) {
     const int warp = tid >> 5;
     const int lane = tid & 31;
     if (tid == 0) TT_CLK(a, 0);
+    if (tid == 0) TT_GCLK(a, 0);   // entry
 #ifdef PAPC_TT_TRIAGE
     unsigned long long gt0 = 0;
     if (tid == 0 && a.clk != nullptr) {
@@ -332,6 +344,7 @@ mlp_layer_tt_kernel(const __grid_constant__ TtArgs a) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (tid == 0) TT_CLK(a, 1);
+    if (tid == 0) TT_GCLK(a, 1);   // barriers initialised, tensor memory allocated
     // Programmatic dependent launch.  As the primary: let the next kernel's CTAs be scheduled on
     // SMs as ours retire (they only run their prologue until we are completely done).  As the
     // dependent (a.pdl): everything up to pdl_wait() reads launch arguments and the weights only.
@@ -426,7 +439,9 @@ mlp_layer_tt_kernel(const __grid_constant__ TtArgs a) {
             if (lane == 0) mbar_arrive(w_ready);
         }
         if (tid == 0) TT_CLK(a, 2);
+        if (tid == 0) TT_GCLK(a, 2);   // W staged
         pdl_wait();
+        if (tid == 0) TT_GCLK(a, 3);   // the previous kernel has completed
         const float bias = (a.bias != nullptr && cvalid) ? a.bias[cg] : 0.f;
         float wx = 0.f, wy = 0.f, wz = 0.f;
         const bool has_xyz = (MODE == SRC_GATHER) && a.wxyz >= 0;
@@ -454,6 +469,7 @@ mlp_layer_tt_kernel(const __grid_constant__ TtArgs a) {
             tc_fence_after();
             TT_ECLK(a, tl, 2);   // tcgen05 fence done
             if (tid == 0 && tl == 0) TT_CLK(a, 5);
+            if (tid == 0 && tl == 0) TT_GCLK(a, 4);   // first accumulator ready
             if (tid == 0 && tl == 1) TT_CLK(a, 11);
             if (tid == 0) TT_TCLK(a, tl, 4);   // epilogue: accumulator ready
             uint64_t s2 = 0ull, q2 = 0ull;     // packed (even rows, odd rows) running sums
@@ -663,6 +679,7 @@ mlp_layer_tt_kernel(const __grid_constant__ TtArgs a) {
                     mma_commit(x_empty + s);                       // chunk reusable once these MMAs have read it
                     if (c == KC - 1) mma_commit(acc_full + buf);   // accumulator complete
                     if (it == 0) TT_CLK(a, 4);
+                    if (it == 0) TT_GCLK(a, 11);           // first MMAs issued
                     if (c == KC - 1) TT_TCLK(a, tl, 3);   // MMA: last chunk issued + committed
                 }
                 __syncwarp();
@@ -832,6 +849,7 @@ mlp_layer_tt_kernel(const __grid_constant__ TtArgs a) {
                 float4 v[kRPT][NV];
                 if (MODE == SRC_PLAIN && !TT_DBG(a, 16)) {
                     mbar_wait(raw_full + rs, (raw_read / (uint32_t)(CF::kRawStages > 0 ? CF::kRawStages : 1)) & 1u);
+                    if (ptid == 0 && raw_read == 0) TT_GCLK(a, 13);  // first raw chunk landed
                     const bool kok = k0 < a.cin;  // whole 16-byte units are valid or not (cin % kEPU == 0)
 #pragma unroll
                     for (int j = 0; j < kRPT; ++j)
@@ -946,6 +964,7 @@ mlp_layer_tt_kernel(const __grid_constant__ TtArgs a) {
             if (TT_DBG(a, 32)) __nanosleep(1500);  // triage: producers step aside after every chunk
             if (ptid == 0 && c == KC - 1) TT_TCLK(a, ptl, 1);  // producer: last chunk of the tile published
             if (ptid == 0 && it == 0) TT_CLK(a, 3);
+            if (ptid == 0 && it == 0) TT_GCLK(a, 10);  // first operand stage published
             if (ptid == 0 && it == 1) TT_CLK(a, 12);
             if (ptid == 0) TT_CLK(a, 10);
             ++it;
@@ -1015,6 +1034,7 @@ mlp_layer_tt_kernel(const __grid_constant__ TtArgs a) {
     __syncthreads();
     tc_fence_after();
     if (tid == 0) TT_CLK(a, 7);
+    if (tid == 0) TT_GCLK(a, 5);   // all tiles done
     if (warp == kMmaWarp) tmem_dealloc<kTmemCols>(tmem_base);
 
     // ---- fused BatchNorm finalisation: the last CTA reduces the partial rows in fixed order
@@ -1029,11 +1049,16 @@ mlp_layer_tt_kernel(const __grid_constant__ TtArgs a) {
 #ifdef PAPC_TT_TRIAGE
             if (tid == 0 && a.clk != nullptr) a.clk[32 + 7] = clock64();
 #endif
+            if (tid == 0) TT_GCLK(a, 7);   // this CTA is the last one: finalisation starts
             // gm partial rows x 2*cout doubles (sum | sum^2 per channel), read as 16-byte column pairs:
             // up to 512 pairs per pass, the rows split over S = 512 / pairs thread slices so that a
             // thread's loads are all independent and few (fixed order -> deterministic); slices are
             // combined through shared memory.  This is a serial tail of the kernel (one CTA works,
             // the GPU waits), so it is arranged for the fewest dependent L2 round trips.
+            // Measured (profiles/r01_layer_boundary_timeline.txt): 5-7 us per layer whatever the row count.
+            // Two rewrites were timed on the B200 and dropped because the step did not move: a two-level
+            // tree (last CTA of every 16-row group folds its group, the last of those folds the groups)
+            // and TMA bulk staging of the rows into the idle operand ring.
             double2 *red = reinterpret_cast<double2 *>(smem + SmemLayout::ring);            // [512]
             double *all = reinterpret_cast<double *>(smem + SmemLayout::ring + kXBytes);    // [2*cout]
             const int npairs = a.cout;  // 2*cout doubles
@@ -1086,6 +1111,7 @@ mlp_layer_tt_kernel(const __grid_constant__ TtArgs a) {
 #ifdef PAPC_TT_TRIAGE
             if (tid == 0 && a.clk != nullptr) a.clk[32 + 10] = clock64();
 #endif
+            if (tid == 0) TT_GCLK(a, 8);   // last CTA: partial rows reduced
             // fp64 division and square root are long software sequences on a slow pipe and this is the
             // kernel's serial tail: reciprocal of the count from the host, 1/sqrt by two Newton steps
             // from the fp32 estimate (full double accuracy)
@@ -1112,6 +1138,7 @@ mlp_layer_tt_kernel(const __grid_constant__ TtArgs a) {
                 if (a.var_out) a.var_out[ch] = (float)var;
             }
             if (tid == 0) *a.counter = 0u;  // self-cleaning for the next launch
+            if (tid == 0) TT_GCLK(a, 9);   // last CTA: scale / shift written (this thread's share)
 #ifdef PAPC_TT_TRIAGE
             __syncthreads();
             if (tid == 0 && a.clk != nullptr) { a.clk[32 + 8] = clock64(); a.clk[32 + 9] = blockIdx.x; }
@@ -1119,6 +1146,7 @@ mlp_layer_tt_kernel(const __grid_constant__ TtArgs a) {
         }
         if (tid == 0) TT_CLK(a, 8);
     }
+    if (tid == 0) TT_GCLK(a, 6);       // exit (after the finalisation in the last CTA)
 #ifdef PAPC_TT_TRIAGE
     if (tid == 0 && a.clk != nullptr) {
         unsigned long long gt1;
@@ -1402,6 +1430,49 @@ static int launch_mp(const TtArgs &a, bool streamed, bool pool, int grid, cudaSt
     return pool ? launch_inst<MODE, PREC, 0, true>(a, grid, st) : launch_inst<MODE, PREC, 0, false>(a, grid, st);
 }
 
+#ifdef PAPC_TT_TRIAGE
+// PAPC_TT_GCLK=1: every launch gets a [152][16] slice of one device buffer (zeroed once, 64 launches);
+// papc_tt_gclk_dump() writes them out after the run.
+namespace {
+constexpr int kGclkLaunches = 64, kGclkCtas = 152;
+unsigned long long *g_gclk = nullptr;
+int g_gclk_n = 0;
+struct GclkMeta { int mode, prec, cin, cout; long long M; } g_gclk_meta[kGclkLaunches];
+unsigned long long *gclk_slice(const TtArgs &a) {
+    if (getenv("PAPC_TT_GCLK") == nullptr || g_gclk_n >= kGclkLaunches) return nullptr;
+    if (g_gclk == nullptr) {
+        cudaMalloc(&g_gclk, sizeof(unsigned long long) * kGclkLaunches * kGclkCtas * 16);
+        cudaMemset(g_gclk, 0, sizeof(unsigned long long) * kGclkLaunches * kGclkCtas * 16);
+    }
+    g_gclk_meta[g_gclk_n] = GclkMeta{a.mode, a.prec, a.cin, a.cout, a.M};
+    return g_gclk + (size_t)(g_gclk_n++) * kGclkCtas * 16;
+}
+}  // namespace
+extern "C" int papc_tt_gclk_dump(const char *path) {
+    if (g_gclk == nullptr) return -1;
+    cudaDeviceSynchronize();
+    const size_t n = (size_t)kGclkLaunches * kGclkCtas * 16;
+    unsigned long long *h = new unsigned long long[n];
+    cudaMemcpy(h, g_gclk, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    FILE *f = fopen(path, "w");
+    if (f == nullptr) { delete[] h; return -2; }
+    for (int l = 0; l < g_gclk_n; ++l) {
+        const GclkMeta &m = g_gclk_meta[l];
+        fprintf(f, "launch %d mode %d prec %d M %lld cin %d cout %d\n", l, m.mode, m.prec, m.M, m.cin, m.cout);
+        for (int c = 0; c < kGclkCtas; ++c) {
+            const unsigned long long *q = h + ((size_t)l * kGclkCtas + c) * 16;
+            if (q[0] == 0) continue;
+            fprintf(f, "cta %d", c);
+            for (int e = 0; e < 16; ++e) fprintf(f, " %llu", q[e]);
+            fprintf(f, "\n");
+        }
+    }
+    fclose(f);
+    delete[] h;
+    return g_gclk_n;
+}
+#endif
+
 int launch(const TtArgs &a_in, cudaStream_t st) {
     TtArgs a = a_in;
     {
@@ -1417,6 +1488,9 @@ int launch(const TtArgs &a_in, cudaStream_t st) {
         cudaMemsetAsync(d_clk + 44, 0xff, sizeof(unsigned long long), st);  // atomicMin target
         a.clk = d_clk;
     }
+#endif
+#ifdef PAPC_TT_TRIAGE
+    a.gclk = gclk_slice(a_in);
 #endif
     const bool pool = a.pool_max != nullptr;
     if (!pool && a.y == nullptr) return PAPC_EINVAL;

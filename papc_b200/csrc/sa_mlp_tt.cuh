@@ -71,6 +71,7 @@ struct TtArgs {
     // tma2d != 0: one cp.async.bulk.tensor per chunk replaces the per-row copies
     alignas(64) CUtensorMap xmap;
     int tma2d;
+    unsigned long long *gclk; // triage builds (PAPC_TT_GCLK=1): [grid][8] %globaltimer stamps of this launch
     unsigned long long *clk;  // triage builds: [3][16] per-phase clock64() stamps (CTA 0, CTA 1, last CTA)
 };
 

@@ -4,7 +4,13 @@ restatement oracle/models_np.py on the same seeded inputs and the same explicit 
 
 Indices (FPS, ball query) depend on xyz only and are bit-exact; the logits go through up to 23
 stacked conv+BatchNorm layers, each within 1e-5 of the oracle on its own (tests/test_gpu_sa.py,
-tests/test_gpu_fp.py) -- the whole-model bound asserted here is 1e-4 (abs + rel)."""
+tests/test_gpu_fp.py).  Whole-model bounds asserted here: 1e-4 (abs + rel) for the classifiers; for
+the segmentation models the bound is taken from the graph's own conditioning -- the decoder
+normalises over as few as B*128 rows, and the ORACLE evaluated with fp32 instead of fp64
+accumulation already moves the logits by ~1.2e-4 (max) on these inputs -- so the product must stay
+within 1e-4 + 4 x that distance (max) and within 4 x its mean."""
+import copy
+
 import numpy as np
 import pytest
 
@@ -120,9 +126,17 @@ def test_segment_models_match_oracle(name, normal_channel, training):
     xyz, st1, st2 = _inputs(B, N, normal_channel, seed=4)
     labels = np.array([[3], [15]], dtype=np.int64)
     got = prod((_cu(xyz), labels), start_idx=(_cu(st1), _cu(st2)))
+    orc32 = copy.deepcopy(orc)                  # the same graph with fp32 accumulation: its conditioning
+    orc32.acc = np.float32
+    for lname in ("sa1", "sa2", "sa3", "fp1", "fp2", "fp3"):
+        getattr(orc32, lname).acc = np.float32
     ref = orc((xyz, labels), start_idx=(st1, st2))
+    ref32 = orc32((xyz, labels), start_idx=(st1, st2))
     assert tuple(got.shape) == (B, N, 50)
-    np.testing.assert_allclose(got.detach().cpu().numpy(), ref, **TOL)
+    err = np.abs(got.detach().cpu().numpy() - ref)
+    cond = np.abs(ref32 - ref)
+    assert err.max() <= 1e-4 + 4.0 * cond.max(), (err.max(), cond.max())
+    assert err.mean() <= 1e-5 + 4.0 * cond.mean(), (err.mean(), cond.mean())
     if training:                                # bn1 is a registered layer: its running statistics move
         np.testing.assert_allclose(prod.bn1._mean.cpu().numpy(), orc.bn1._mean, rtol=1e-4, atol=1e-5)
         np.testing.assert_allclose(prod.bn1._variance.cpu().numpy(), orc.bn1._variance, rtol=1e-4, atol=1e-5)
