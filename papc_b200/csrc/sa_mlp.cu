@@ -611,6 +611,8 @@ struct FusedBn {
     float sqrt_count;     // (float)sqrt(count), rounded up: argument of tt::f16_colscale_sq
     float *scale, *shift, *mean_out, *var_out;
     float *out_colscale;  // non-null: the NEXT layer runs the fp16 split (see tt::TtArgs)
+    // zeroed, self-cleaning [4][cout] 64-bit accumulators + flag (tt::TtArgs::fix_acc); nullable
+    unsigned long long *fix_acc = nullptr;
 };
 
 // Per-launch options of the transposed tcgen05 kernel.
@@ -672,7 +674,9 @@ static int try_tt(const LayerArgs &a, bool gather, int K, const FusedBn *bn, con
     t.wimg = o.wimg;
     if (o.dry_run) return 1;
     if (bn != nullptr && a.stats_partial != nullptr) {
-        t.counter = bn->counter; t.gamma = bn->gamma; t.beta = bn->beta; t.eps = bn->eps;
+        t.counter = bn->counter;
+        t.fix_acc = bn->fix_acc;
+        t.gamma = bn->gamma; t.beta = bn->beta; t.eps = bn->eps;
         t.count = bn->count; t.sqrt_count = bn->sqrt_count; t.scale = bn->scale; t.shift = bn->shift;
         t.mean_out = bn->mean_out; t.var_out = bn->var_out; t.out_colscale = bn->out_colscale;
     }
@@ -867,6 +871,7 @@ namespace {
 struct WsPlan {
     size_t y[2], pool_max, pool_min, partial, sums, scale, shift, wimg, wimg_bytes;
     size_t counters, fold, mom_partial, colscale, colscale_stride, total;
+    size_t counters_bytes;  // 256 bytes of counters + the fixed-point statistic accumulators (see FusedBn)
 };
 static int plan_ws(const papc_group_source *src, const papc_mlp *mlp, WsPlan *p) {
     if (!src || !mlp) return PAPC_EINVAL;
@@ -904,7 +909,8 @@ static int plan_ws(const papc_group_source *src, const papc_mlp *mlp, WsPlan *p)
     }
     p->wimg_bytes = wb;
     p->wimg = take(wb);
-    p->counters = take(256);
+    p->counters_bytes = 256 + ((size_t)4 * maxc + 8) * sizeof(unsigned long long);
+    p->counters = take(p->counters_bytes);
     p->fold = take((size_t)128 * 4 * sizeof(float));
     p->mom_partial = take((size_t)2 * kNumSMs * 9 * sizeof(double));
     p->colscale_stride = align_up((size_t)maxc * sizeof(float), 256);
@@ -967,7 +973,7 @@ extern "C" int papc_sa_mlp_f32(const papc_group_source *src, const papc_mlp *mlp
         if (!batch && (!ly.running_mean || !ly.running_var)) return PAPC_EINVAL;
     }
     // the in-kernel "last CTA" counters start at zero (they clean themselves afterwards)
-    PAPC_CUDA_TRY(cudaMemsetAsync(counters, 0, 256, st));
+    PAPC_CUDA_TRY(cudaMemsetAsync(counters, 0, p.counters_bytes, st));
 
     int cin = mlp->cin;
     const float *xprev = nullptr;
@@ -1027,6 +1033,7 @@ extern "C" int papc_sa_mlp_f32(const papc_group_source *src, const papc_mlp *mlp
         const bool next_f16 = f16_ok(l + 1, ly.cout);
         FusedBn bn{counters + l, ly.gamma, ly.beta, mlp->eps, (double)M, sqrt_m,
                    scale, shift, ly.batch_mean, ly.batch_var, next_f16 ? colscale[l & 1] : nullptr};
+        bn.fix_acc = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(counters) + 256);
         TtOpts o{this_f16 ? tt::PREC_F16 : tt::PREC_TF32,
                  this_f16 ? mlp->layers[l - 1].gamma : nullptr, this_f16 ? mlp->layers[l - 1].beta : nullptr,
                  sqrt_m, nullptr, ws + p.wimg, p.wimg_bytes, false, prev_is_kernel};
@@ -1106,6 +1113,7 @@ pad_weight_kernel(const float *__restrict__ w, int cout, int cin, int ld, float 
 }
 struct PwPlan {
     size_t y[2], partial, scale, shift, wimg, wimg_bytes, counters, colscale, colscale_stride, wpad, total;
+    size_t counters_bytes;
 };
 static int plan_pw(int64_t M, int32_t ld_x, const papc_mlp *mlp, PwPlan *p) {
     if (!mlp || M < 0 || mlp->num_layers < 1 || mlp->num_layers > PAPC_MAX_MLP_LAYERS) return PAPC_EINVAL;
@@ -1131,7 +1139,8 @@ static int plan_pw(int64_t M, int32_t ld_x, const papc_mlp *mlp, PwPlan *p) {
     }
     p->wimg_bytes = wb;
     p->wimg = take(wb);
-    p->counters = take(256);
+    p->counters_bytes = 256 + ((size_t)4 * maxc + 8) * sizeof(unsigned long long);
+    p->counters = take(p->counters_bytes);
     p->colscale_stride = align_up((size_t)maxc * sizeof(float), 256);
     p->colscale = take(2 * p->colscale_stride);
     p->wpad = take(ld_x != mlp->cin ? (size_t)mlp->layers[0].cout * ld_x * sizeof(float) : 0);
@@ -1173,7 +1182,7 @@ extern "C" int papc_pointwise_mlp_f32(const float *x, int64_t M, int32_t ld_x, c
         if (!ly.weight) return PAPC_EINVAL;
         if (!batch && (!ly.running_mean || !ly.running_var)) return PAPC_EINVAL;
     }
-    PAPC_CUDA_TRY(cudaMemsetAsync(counters, 0, 256, st));
+    PAPC_CUDA_TRY(cudaMemsetAsync(counters, 0, p.counters_bytes, st));
     const float *w0 = mlp->layers[0].weight;
     if (ld_x != mlp->cin) {  // rows are padded (with zeros) to ld_x columns: pad the first weight alike
         float *wp = reinterpret_cast<float *>(ws + p.wpad);
@@ -1203,6 +1212,7 @@ extern "C" int papc_pointwise_mlp_f32(const float *x, int64_t M, int32_t ld_x, c
         }
         FusedBn bn{counters + l, ly.gamma, ly.beta, mlp->eps, (double)M, sqrt_m,
                    scale, shift, ly.batch_mean, ly.batch_var, next_f16 ? colscale[l & 1] : nullptr};
+        bn.fix_acc = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(counters) + 256);
         TtOpts o{this_f16 ? tt::PREC_F16 : tt::PREC_TF32,
                  this_f16 ? mlp->layers[l - 1].gamma : nullptr, this_f16 ? mlp->layers[l - 1].beta : nullptr,
                  sqrt_m, nullptr, ws + p.wimg, p.wimg_bytes, false, l > 0};

@@ -617,6 +617,22 @@ mlp_layer_tt_kernel(const __grid_constant__ TtArgs a) {
                 a.stats_partial[(rr * 2 + 0) * a.cout + cg] = 0.0;
                 a.stats_partial[(rr * 2 + 1) * a.cout + cg] = 0.0;
             }
+            if (a.fix_acc != nullptr && a.counter != nullptr) {
+                // the same sums once more, for the last CTA's fast path (TtArgs::fix_acc)
+                const double v2[2] = {acc_s, acc_q};
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const double p = v2[i];
+                    if (fabs(p) < 0x1p53) {   // <= 296 CTAs: the integer words cannot overflow
+                        const double ip = trunc(p);
+                        atomicAdd(a.fix_acc + (size_t)(2 * i) * a.cout + cg, (unsigned long long)(long long)ip);
+                        atomicAdd(a.fix_acc + (size_t)(2 * i + 1) * a.cout + cg,
+                                  (unsigned long long)__double2ll_rn((p - ip) * 0x1p54));
+                    } else {
+                        atomicOr(a.fix_acc + (size_t)4 * a.cout, 1ull);
+                    }
+                }
+            }
             __threadfence();
         }
     } else if (warp == kMmaWarp) {
@@ -1066,7 +1082,25 @@ mlp_layer_tt_kernel(const __grid_constant__ TtArgs a) {
             const int S = 512 / P;
             const int pair_l = tid % P, sl = tid / P;
             const double2 *part = reinterpret_cast<const double2 *>(a.stats_partial);
-            for (int base = 0; base < npairs; base += P) {
+            // Fast path: the CTAs' sums were also added into fix_acc with integer atomics; 4*cout words to
+            // read instead of gm rows of 2*cout doubles (303 KB through one SM's L2 port: 5 us).
+            bool fixed = false;
+            if (a.fix_acc != nullptr && (a.dbg & 256) == 0) {   // PAPC_TT_DBG=256: A/B switch, partial rows
+                fixed = __ldcg(a.fix_acc + (size_t)4 * a.cout) == 0ull;
+                __syncthreads();   // everyone has read the flag before it is cleaned
+                for (int i = tid; i < 2 * a.cout; i += kThreads) {
+                    const int which = i / a.cout, ch = i - which * a.cout;   // 0: sum, 1: sum of squares
+                    unsigned long long *pi = a.fix_acc + (size_t)(2 * which) * a.cout + ch;
+                    unsigned long long *pf = a.fix_acc + (size_t)(2 * which + 1) * a.cout + ch;
+                    const long long vi = (long long)__ldcg(pi), vf = (long long)__ldcg(pf);
+                    if (fixed) all[i] = (double)vi + (double)vf * 0x1p-54;
+                    *pi = 0ull;   // self-cleaning for the next launch
+                    *pf = 0ull;
+                }
+                if (tid == 0) a.fix_acc[(size_t)4 * a.cout] = 0ull;
+                __syncthreads();
+            }
+            for (int base = fixed ? npairs : 0; base < npairs; base += P) {
                 const int pr = base + pair_l;
                 if (sl < S && pr < npairs) {
                     double ax = 0.0, ay = 0.0;
@@ -1095,7 +1129,9 @@ mlp_layer_tt_kernel(const __grid_constant__ TtArgs a) {
                     ay += by;
                     red[sl * P + pair_l] = make_double2(ax, ay);
                 }
+                if (tid == 0 && base == 0) TT_GCLK(a, 12);  // thread 0: its loads and adds done
                 __syncthreads();
+                if (tid == 0 && base == 0) TT_GCLK(a, 14);  // every thread's loads and adds done
                 if (sl == 0 && pr < npairs) {
                     double ax = 0.0, ay = 0.0;
                     for (int q = 0; q < S; ++q) {

@@ -55,6 +55,12 @@ struct TtArgs {
     // out_colscale (nullable): per-channel power of two 2^e such that relu(bn(y)) / 2^e < 2^15 for
     // every possible y (bound |gamma| sqrt(count) + |beta|); scale/shift are written divided by it.
     unsigned int *counter;
+    // nullable: zeroed, self-cleaning unsigned long long [4][cout] (+1 flag word at [4*cout]): every CTA adds
+    // its fp64 statistic sums as an exact (integer part, 2^-54 fraction) pair with 64-bit integer
+    // atomics -- associative, so still deterministic -- and the last CTA reads 4*cout words instead
+    // of reducing gridDim partial rows.  The flag is raised by a sum outside +-2^53 (or NaN): the last
+    // CTA then falls back to the partial rows.
+    unsigned long long *fix_acc;
     const float *gamma, *beta;
     float eps;
     double count;

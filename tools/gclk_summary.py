@@ -30,6 +30,8 @@ for L in step:
     fin = [c for c in fin if c[7] > c[5]]
     if fin:
         c = fin[0]
+        if len(c) > 14 and c[12]:
+            print(f"   last CTA reduction: thread 0 done {(c[12] - t0) / 1e3:8.2f}, all threads done {(c[14] - t0) / 1e3:8.2f}")
         red = f", reduced {(c[8] - t0) / 1e3:8.2f}, scale/shift written {(c[9] - t0) / 1e3:8.2f}" if len(c) > 9 and c[8] else ""
         print(f"   last CTA: tiles done {(c[5] - t0) / 1e3:8.2f}, finalisation starts {(c[7] - t0) / 1e3:8.2f}{red}, exits {(c[6] - t0) / 1e3:8.2f}")
     prev_exit = max((c[6] - t0) / 1e3 for c in cs)
