@@ -168,6 +168,10 @@ def time_cpu_baseline(steps, warmup, batch):
     return batch * N_POINTS / (ms / 1e3), ms, cores, sample
 
 
+WORKLOAD = ("PointNet++SSG classify SetAbstraction stack sa1+sa2+sa3, 1024-pt clouds, "
+            "B=32 per GPU (BASELINE configs[1]; N=8 is configs[4], B=256)")
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path.  PaddlePaddle cannot
     be installed here (no wheel, no network), so this is the oracle port -- the line-by-line NumPy
@@ -182,9 +186,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "PointNet++SSG classify SetAbstraction stack, 1024 pts (BASELINE configs[1])",
-                   "clouds_per_step": batch, "n_points": N_POINTS, "bn": "batch statistics",
-                   "note": "Paddle unavailable: CPU restatement of the reference path (oracle port)"},
+        "config": {"workload": WORKLOAD, "global_batch": B_PER_GPU * max(1, args.gpus), "n_points": N_POINTS,
+                   "bn": "train-mode batch statistics, as the reference's unregistered SA layers run",
+                   "sample": f"{batch} of the {B_PER_GPU} clouds per step (points/s is per point, so the "
+                             "rate is that of the full batch on the same cores)",
+                   "note": "Paddle unavailable: CPU restatement of the reference path (oracle port), rank 0 only"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -384,8 +390,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "PointNet++SSG classify SetAbstraction stack sa1+sa2+sa3, 1024-pt clouds, "
-                               "B=32 per GPU (BASELINE configs[1]; N=8 is configs[4], B=256)",
+        "config": {"workload": WORKLOAD,
                    "global_batch": Bg, "n_points": N_POINTS, "parallelism": f"batch-shard x{world}",
                    "bn": "train-mode batch statistics (per shard), as the reference's unregistered SA layers run",
                    "collective": "one all-gather of l3 features" if world > 1 else "none",
