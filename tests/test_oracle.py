@@ -226,3 +226,22 @@ def test_feature_propagation_restatement_quirk_and_shapes():
     z1 = fp.interpolate(xyz1, xyz2[:, :, :1], None, p2[:, :, :1])
     np.testing.assert_array_equal(z1, np.tile(p2[:, :, :1].transpose(0, 2, 1), [1, N, 1]))
     assert fp(xyz1, xyz2, p1, p2).shape == (B, 6, N)
+
+
+def test_pc_normalize_matches_reference_golden(golden_dir):
+    """layers.py:17-23: outputs of the reference's own function (tests/golden/make_golden_pc_normalize.py);
+    the synthetic cloud generator applies the same normalisation per cloud."""
+    from papc_b200 import synth
+    g = np.load(os.path.join(golden_dir, "pc_normalize.npz"))
+    for x, y in ((g["x32"], g["y32"]), (g["x64"], g["y64"])):
+        out = layers_np.pc_normalize(x)
+        assert out.dtype == y.dtype
+        np.testing.assert_array_equal(out, y)
+    # synth.clouds(B, N, seed) == pc_normalize of the same raw draws, cloud by cloud
+    B, N = 3, 1024
+    raw = np.random.default_rng(0).uniform(-1.0, 1.0, (B, N, 3)).astype(np.float32)
+    np.testing.assert_array_equal(raw[0], g["x32"])          # the golden input IS cloud 0 of seed 0
+    got = synth.clouds(B, N, seed=0).transpose(0, 2, 1)
+    np.testing.assert_allclose(got[0], g["y32"], rtol=0, atol=2e-7)
+    for b in range(B):
+        np.testing.assert_allclose(got[b], layers_np.pc_normalize(raw[b]), rtol=0, atol=2e-7)
