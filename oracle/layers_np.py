@@ -10,9 +10,12 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline``
 
 PARITY UNPINNED: the reference executes these lines inside PaddlePaddle, which is not
 installable in the build image, and the reference ships no tests or golden vectors.
-The restatement is pinned by (i) the hand-derivable known-answer vectors K1-K4 of
-SURVEY.md section 8(c) (tests/test_oracle.py), (ii) agreement with the arithmetic-pinned
-C restatement in oracle/papc_oracle.c.
+The restatement is pinned by (i) vectors produced by EXECUTING the reference's own source
+over a NumPy stand-in for its paddle calls (tests/golden/make_golden_layers.py ->
+tests/golden/layers_ref.npz, checked bit-exactly in tests/test_oracle_vs_reference_source.py;
+this pins the logic, not the arithmetic inside Paddle's kernels), (ii) the known-answer
+vectors K1-K4 of SURVEY.md section 8(c), (iii) agreement with the arithmetic-pinned C
+restatement in oracle/papc_oracle.c.
 
 BatchNorm follows Paddle 2.x semantics: training mode normalises with the *biased*
 batch variance over (B, H, W) per channel, eps 1e-5 (BatchNorm2D default), momentum 0.9
