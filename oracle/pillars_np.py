@@ -13,8 +13,11 @@ may import this module.
 
 Parity status: ``points_to_voxel`` is PINNED -- the reference's numba kernel imports and
 runs in the build container (only needs numba + numpy), and tests/golden/voxel_*.npz hold
-its outputs (tests/golden/make_golden.py).  PillarFeatureNet / PointPillarsScatter are
-"parity unpinned" (they execute inside PaddlePaddle, absent here; no reference tests).
+its outputs (tests/golden/make_golden.py).  PillarFeatureNet / PointPillarsScatter: their LOGIC
+is pinned to vectors produced by executing the reference's own classes over a NumPy stand-in for
+paddle (tests/golden/make_golden_pillars.py -> pillars_ref.npz; decoration and canvas bit-exact,
+tests/test_oracle_vs_reference_source.py); the Linear / BatchNorm1D arithmetic remains "parity
+unpinned" (it executes inside PaddlePaddle, absent here; no reference tests).
 """
 from __future__ import annotations
 

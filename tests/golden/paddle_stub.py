@@ -11,9 +11,11 @@ Python scalars adopt the tensor's dtype (NumPy >= 2 does the same).  What this d
 arithmetic inside Paddle's kernels (e.g. the accumulation order of ``matmul``): vectors produced here
 pin the oracle's *logic* to the reference's code; they are not outputs of Paddle itself.
 
-Layers with parameters (``nn.Conv2D``, ``nn.BatchNorm2D`` ...) are deliberately NOT provided: the
+Convolution layers (``nn.Conv2D``, ``nn.BatchNorm2D`` ...) are deliberately NOT provided: the PointNet++
 golden cases build the reference's layers with empty ``mlp`` lists, which exercises grouping, concat
-order, transposes and the max-pool of the reference forward passes with no restated numerics.
+order, transposes and the max-pool of the reference forward passes with no restated numerics.  The
+pillar cases need ``nn.Linear`` / ``nn.BatchNorm1D``; those two ARE restated here (fp64 accumulation)
+and labelled as such -- the pillar vectors pin the reference's wiring around them.
 """
 from __future__ import annotations
 
@@ -68,6 +70,15 @@ class Tensor:
     def sum(self, axis=None, keepdim=False):
         return Tensor(self.a.sum(axis=axis, keepdims=keepdim, dtype=self.a.dtype))
 
+    def squeeze(self, axis=None):
+        return Tensor(np.squeeze(self.a, axis=axis))
+
+    def t(self):
+        return Tensor(self.a.T)
+
+    def any(self):
+        return Tensor(np.array([self.a.any()]))      # Paddle 2.0: a 1-element tensor
+
     # ---- indexing
     def __getitem__(self, idx):
         return Tensor(self.a[idx])
@@ -97,13 +108,20 @@ class Tensor:
         self.a = np.add(self.a, _unwrap(o)).astype(self.a.dtype)
         return self
 
+    def __imul__(self, o):
+        self.a = np.multiply(self.a, _unwrap(o)).astype(self.a.dtype)
+        return self
+
     def __isub__(self, o):
         self.a = np.subtract(self.a, _unwrap(o)).astype(self.a.dtype)
         return self
 
 
 def to_tensor(x):
-    return Tensor(np.array(_unwrap(x)))   # a NumPy array keeps its dtype (only Python floats become float32)
+    a = np.array(_unwrap(x))              # a NumPy array keeps its dtype; Python ints become int64,
+    if not isinstance(_unwrap(x), np.ndarray) and a.dtype == np.float64:
+        a = a.astype(np.float32)          # Python floats the default float32
+    return Tensor(a)
 
 
 def matmul(x, y):
@@ -114,8 +132,8 @@ def sum(x, axis=None, keepdim=False):     # noqa: A001 (paddle.sum)
     return x.sum(axis=axis, keepdim=keepdim)
 
 
-def max(x, axis=None):                    # noqa: A001 (paddle.max)
-    return Tensor(_unwrap(x).max(axis=axis))
+def max(x, axis=None, keepdim=False):     # noqa: A001 (paddle.max)
+    return Tensor(_unwrap(x).max(axis=axis, keepdims=keepdim))
 
 
 def argmax(x, axis=None):
@@ -134,12 +152,34 @@ def tile(x, reps):
     return x.tile(reps)
 
 
-def arange(n):
-    return Tensor(np.arange(n, dtype=np.int64))
+def arange(n, dtype="int64"):
+    return Tensor(np.arange(n, dtype=dtype))
 
 
-def zeros(shape):
-    return Tensor(np.zeros(shape, dtype=np.float32))
+def zeros(shape, dtype="float32"):
+    return Tensor(np.zeros(shape, dtype=dtype))
+
+
+def zeros_like(x):
+    return Tensor(np.zeros_like(_unwrap(x)))
+
+
+def unsqueeze(x, axis):
+    return x.unsqueeze(axis)
+
+
+def norm(x, p, axis, keepdim=False):
+    assert p == 2
+    a = _unwrap(x)
+    return Tensor(np.sqrt((a * a).sum(axis=axis, keepdims=keepdim, dtype=a.dtype)))
+
+
+def index_select(x, index, axis=0):
+    return Tensor(np.take(_unwrap(x), _unwrap(index), axis=axis))
+
+
+def stack(xs, axis=0):
+    return Tensor(np.stack([_unwrap(x) for x in xs], axis=axis))
 
 
 def ones(shape):
@@ -170,9 +210,46 @@ def _missing(name):
     return ctor
 
 
+class _Linear(_Layer):
+    """paddle.nn.Linear restated (x @ W [+ b], W [in,out]; fp64 accumulation, fp32 result) -- used by the
+    PILLAR golden cases only, and recorded there as restated numerics: what those cases pin is the
+    reference's wiring around it (decorations, mask, max / tile / concat)."""
+
+    def __init__(self, in_features, out_features, bias_attr=True):
+        self.weight = Tensor(np.zeros((in_features, out_features), np.float32))
+        self.bias = Tensor(np.zeros((out_features,), np.float32)) if bias_attr else None
+        self.inputs = []                  # every input is recorded for the golden file
+
+    def forward(self, x):
+        self.inputs.append(x.numpy())
+        y = x.a.astype(np.float64) @ self.weight.a.astype(np.float64)
+        if self.bias is not None:
+            y = y + self.bias.a.astype(np.float64)
+        return Tensor(y.astype(np.float32))
+
+
+class _BatchNorm1D(_Layer):
+    """paddle.nn.BatchNorm1D restated, training mode, input [N,C,L]: biased batch variance over (N, L)."""
+
+    def __init__(self, num_features, momentum=0.9, epsilon=1e-5):
+        self.weight = Tensor(np.ones((num_features,), np.float32))
+        self.bias = Tensor(np.zeros((num_features,), np.float32))
+        self._epsilon = epsilon
+
+    def forward(self, x):
+        a = x.a.astype(np.float64)
+        mean, var = a.mean(axis=(0, 2)), a.var(axis=(0, 2))
+        y = (a - mean[None, :, None]) / np.sqrt(var[None, :, None] + np.float64(self._epsilon))
+        y = y * self.weight.a.astype(np.float64)[None, :, None] + self.bias.a.astype(np.float64)[None, :, None]
+        return Tensor(y.astype(np.float32))
+
+
 nn = types.ModuleType("paddle.nn")
 nn.Layer = _Layer
-for _n in ("Conv1D", "Conv2D", "BatchNorm1D", "BatchNorm2D", "Linear", "Dropout"):
+nn.LayerList = list
+nn.Linear = _Linear
+nn.BatchNorm1D = _BatchNorm1D
+for _n in ("Conv1D", "Conv2D", "BatchNorm2D", "Dropout"):
     setattr(nn, _n, _missing(_n))
 functional = types.ModuleType("paddle.nn.functional")
 functional.relu = lambda x: Tensor(np.maximum(_unwrap(x), 0))

@@ -95,3 +95,36 @@ def test_forward_passes_with_empty_mlps_match_the_reference_code(g):
     np.testing.assert_array_equal(fp(xyz_cf, xyz2, feats_cf, p2), g["fp_out"])
     np.testing.assert_array_equal(layers_np.PointNetFeaturePropagation(9, [])(xyz_cf, xyz2, None, p2), g["fp_out_nop1"])
     np.testing.assert_array_equal(fp(xyz_cf, xyz2[:, :, :1], feats_cf, p2[:, :, :1]), g["fp_out_s1"])
+
+
+# ---------------------------------------------------------------------------------- pillar path
+@pytest.fixture(scope="module")
+def gp(golden_dir):
+    return np.load(os.path.join(golden_dir, "pillars_ref.npz"))
+
+
+@pytest.mark.parametrize("tag,filters,dist", [("one", (64,), False), ("two", (32, 64), False), ("dist", (16,), True)])
+def test_pillar_feature_net_matches_the_reference_classes(gp, tag, filters, dist):
+    """tests/golden/make_golden_pillars.py: the reference's PillarFeatureNet / PFNLayer executed over the
+    stub.  The decorated tensor (input of the first Linear) is an exact reference for pillars.py:81-102;
+    the output additionally goes through the stub's Linear / BatchNorm1D arithmetic."""
+    from oracle import pillars_np
+    from papc_b200 import synth
+    net = pillars_np.PillarFeatureNet(4, True, filters, dist, synth.KITTI_VOXEL_SIZE, synth.KITTI_PC_RANGE)
+    for i, pfn in enumerate(net.pfn_layers):
+        pfn.weight, pfn.gamma, pfn.beta = gp[f"{tag}_w{i}"], gp[f"{tag}_gamma{i}"], gp[f"{tag}_beta{i}"]
+    feats, num, coors = gp["features"], gp["num_voxels"], gp["coors"]
+    np.testing.assert_array_equal(net.decorate(feats, num, coors), gp[f"{tag}_decorated"])
+    out = net(feats, num, coors)
+    assert out.shape == gp[f"{tag}_out"].shape
+    np.testing.assert_allclose(out, gp[f"{tag}_out"], rtol=1e-6, atol=1e-6)
+
+
+def test_pillar_scatter_matches_the_reference_class(gp):
+    from oracle import pillars_np
+    nx, ny = int(gp["nx"]), int(gp["ny"])
+    vf = gp["one_out"]
+    sc = pillars_np.PointPillarsScatter([1, 1, ny, nx], num_input_features=vf.shape[1])
+    np.testing.assert_array_equal(sc.forward(vf, gp["coors"], 2), gp["canvas_b2"])
+    np.testing.assert_array_equal(sc.forward(vf, gp["coors_b3"], 3), gp["canvas_b3"])   # sample 1 is empty
+    assert not gp["canvas_b3"][1].any()
