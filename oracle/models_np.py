@@ -5,8 +5,11 @@ NOT PRODUCT (only tests/ may import it).
   PointNet2_SSG_Seg  / PointNet2_MSG_Seg    PAPC/models/segment/pointnet2/pointnet2.py:6-51, :53-98
   Categorical                               PAPC/models/layers/pointnet2_basic_layers.py:7-14
 
-built on the layer restatements of ``oracle/layers_np.py``.  PARITY UNPINNED like those: the
-reference executes inside PaddlePaddle (absent here) and ships no golden vectors for these models.
+built on the layer restatements of ``oracle/layers_np.py``.  The WIRING is pinned: the reference's own
+model classes, executed unmodified over a NumPy stand-in for paddle (tests/golden/make_golden_models.py
+-> tests/golden/models_ref.npz), give the same logits and head running statistics as these classes with
+identical parameters (tests/test_oracle_vs_reference_source.py).  The arithmetic inside Paddle's layers
+stays PARITY UNPINNED: the reference executes inside PaddlePaddle (absent here) and ships no vectors.
 
 Paddle semantics restated for the heads: ``nn.Linear`` is ``x @ W + b`` with ``W`` [in,out];
 ``nn.BatchNorm1D`` (registered, so it follows train()/eval()): eps 1e-5, momentum 0.9, biased batch

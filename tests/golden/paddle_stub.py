@@ -11,11 +11,13 @@ Python scalars adopt the tensor's dtype (NumPy >= 2 does the same).  What this d
 arithmetic inside Paddle's kernels (e.g. the accumulation order of ``matmul``): vectors produced here
 pin the oracle's *logic* to the reference's code; they are not outputs of Paddle itself.
 
-Convolution layers (``nn.Conv2D``, ``nn.BatchNorm2D`` ...) are deliberately NOT provided: the PointNet++
-golden cases build the reference's layers with empty ``mlp`` lists, which exercises grouping, concat
-order, transposes and the max-pool of the reference forward passes with no restated numerics.  The
-pillar cases need ``nn.Linear`` / ``nn.BatchNorm1D``; those two ARE restated here (fp64 accumulation)
-and labelled as such -- the pillar vectors pin the reference's wiring around them.
+Layers with parameters: the PointNet++ LAYER cases (make_golden_layers.py) build the reference's layers
+with empty ``mlp`` lists, which exercises grouping, concat order, transposes and the max-pool of the
+reference forward passes with no restated numerics at all.  The pillar and MODEL cases need
+``nn.Linear`` / ``nn.Conv1D`` / ``nn.Conv2D`` (kernel 1) / ``nn.BatchNorm1D`` / ``nn.BatchNorm2D`` /
+``nn.Dropout``; those ARE restated below (fp64 accumulation, Paddle 2.x BatchNorm semantics) and
+labelled as such -- the vectors of those cases pin the reference's wiring around them, including which
+BatchNorms follow ``eval()`` (attribute-registered ones) and which do not (the ones kept in lists).
 """
 from __future__ import annotations
 
@@ -196,9 +198,32 @@ def randint(low, high, shape):
     return Tensor(v)
 
 
+_param_rng = np.random.default_rng(2024)   # initial weights of the restated layers (the generators overwrite
+                                            # or export every parameter, so only reproducibility matters)
+
+
 class _Layer:
+    """paddle.nn.Layer as far as the reference uses it: sublayers assigned as ATTRIBUTES are registered and
+    follow train() / eval(); layers kept in plain Python lists are not (which is why the reference's
+    SetAbstraction / FeaturePropagation BatchNorms stay in training mode after model.eval())."""
+
     def __init__(self, *a, **k):
-        pass
+        object.__setattr__(self, "_sub", {})
+        object.__setattr__(self, "training", True)
+
+    def __setattr__(self, name, value):
+        if isinstance(value, _Layer):
+            self._sub[name] = value
+        object.__setattr__(self, name, value)
+
+    def train(self, mode=True):
+        object.__setattr__(self, "training", mode)
+        for sub in self._sub.values():
+            sub.train(mode)
+        return self
+
+    def eval(self):
+        return self.train(False)
 
     def __call__(self, *a, **k):
         return self.forward(*a, **k)
@@ -210,15 +235,17 @@ def _missing(name):
     return ctor
 
 
+# ---- layers with parameters: RESTATED numerics (fp64 accumulation, fp32 results), labelled as such in the
+#      generators' docstrings; what the cases that use them pin is the reference's wiring around them.
 class _Linear(_Layer):
-    """paddle.nn.Linear restated (x @ W [+ b], W [in,out]; fp64 accumulation, fp32 result) -- used by the
-    PILLAR golden cases only, and recorded there as restated numerics: what those cases pin is the
-    reference's wiring around it (decorations, mask, max / tile / concat)."""
+    """paddle.nn.Linear: x @ W [+ b], W [in,out]."""
 
     def __init__(self, in_features, out_features, bias_attr=True):
-        self.weight = Tensor(np.zeros((in_features, out_features), np.float32))
+        super().__init__()
+        self.weight = Tensor((_param_rng.standard_normal((in_features, out_features)) / np.sqrt(in_features))
+                             .astype(np.float32))
         self.bias = Tensor(np.zeros((out_features,), np.float32)) if bias_attr else None
-        self.inputs = []                  # every input is recorded for the golden file
+        self.inputs = []                  # every input is recorded for the golden files
 
     def forward(self, x):
         self.inputs.append(x.numpy())
@@ -228,29 +255,76 @@ class _Linear(_Layer):
         return Tensor(y.astype(np.float32))
 
 
-class _BatchNorm1D(_Layer):
-    """paddle.nn.BatchNorm1D restated, training mode, input [N,C,L]: biased batch variance over (N, L)."""
+class _ConvK1(_Layer):
+    """paddle.nn.Conv1D / Conv2D with kernel size 1: weight [out,in,1(,1)], bias [out]; channel axis 1."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, nd):
+        super().__init__()
+        assert kernel_size == 1
+        shape = (out_channels, in_channels) + (1,) * nd
+        self.weight = Tensor((_param_rng.standard_normal(shape) * np.sqrt(2.0 / in_channels)).astype(np.float32))
+        self.bias = Tensor(np.zeros((out_channels,), np.float32))
+
+    def forward(self, x):
+        a = x.a
+        w = self.weight.a.reshape(self.weight.a.shape[0], -1).astype(np.float64)
+        flat = np.ascontiguousarray(a).reshape(a.shape[0], a.shape[1], -1).astype(np.float64)
+        y = np.matmul(w, flat) + self.bias.a.astype(np.float64)[None, :, None]
+        return Tensor(y.reshape((a.shape[0], w.shape[0]) + a.shape[2:]).astype(np.float32))
+
+
+class _BatchNorm(_Layer):
+    """paddle.nn.BatchNorm1D / BatchNorm2D, channel axis 1 of a 2-, 3- or 4-D input: training mode normalises
+    with the biased batch variance and moves ``_mean`` / ``_variance`` (momentum * running + (1 - momentum) *
+    batch); eval mode uses the running statistics."""
 
     def __init__(self, num_features, momentum=0.9, epsilon=1e-5):
+        super().__init__()
         self.weight = Tensor(np.ones((num_features,), np.float32))
         self.bias = Tensor(np.zeros((num_features,), np.float32))
-        self._epsilon = epsilon
+        self._mean = Tensor(np.zeros((num_features,), np.float32))
+        self._variance = Tensor(np.ones((num_features,), np.float32))
+        self._momentum, self._epsilon = momentum, epsilon
 
     def forward(self, x):
         a = x.a.astype(np.float64)
-        mean, var = a.mean(axis=(0, 2)), a.var(axis=(0, 2))
-        y = (a - mean[None, :, None]) / np.sqrt(var[None, :, None] + np.float64(self._epsilon))
-        y = y * self.weight.a.astype(np.float64)[None, :, None] + self.bias.a.astype(np.float64)[None, :, None]
+        axes = tuple(i for i in range(a.ndim) if i != 1)
+        shp = [1, -1] + [1] * (a.ndim - 2)
+        if self.training:
+            mean, var = a.mean(axis=axes), a.var(axis=axes)
+            m = self._momentum
+            self._mean = Tensor((m * self._mean.a + (1 - m) * mean).astype(np.float32))
+            self._variance = Tensor((m * self._variance.a + (1 - m) * var).astype(np.float32))
+        else:
+            mean, var = self._mean.a.astype(np.float64), self._variance.a.astype(np.float64)
+        y = (a - mean.reshape(shp)) / np.sqrt(var.reshape(shp) + np.float64(self._epsilon))
+        y = y * self.weight.a.astype(np.float64).reshape(shp) + self.bias.a.astype(np.float64).reshape(shp)
         return Tensor(y.astype(np.float32))
+
+
+class _Dropout(_Layer):
+    """paddle.nn.Dropout (upscale_in_train): identity in eval mode or with p == 0; a random mask otherwise,
+    which no golden case uses."""
+
+    def __init__(self, p=0.5):
+        super().__init__()
+        self.p = p
+
+    def forward(self, x):
+        if not self.training or self.p == 0:
+            return x
+        raise NotImplementedError("Dropout with p > 0 in training mode is not reproducible outside Paddle")
 
 
 nn = types.ModuleType("paddle.nn")
 nn.Layer = _Layer
-nn.LayerList = list
+nn.LayerList = list            # (Paddle registers the members of a LayerList; the pillar cases never call eval())
 nn.Linear = _Linear
-nn.BatchNorm1D = _BatchNorm1D
-for _n in ("Conv1D", "Conv2D", "BatchNorm2D", "Dropout"):
-    setattr(nn, _n, _missing(_n))
+nn.BatchNorm1D = _BatchNorm
+nn.BatchNorm2D = _BatchNorm
+nn.Conv1D = lambda i, o, k: _ConvK1(i, o, k, 1)
+nn.Conv2D = lambda i, o, k: _ConvK1(i, o, k, 2)
+nn.Dropout = _Dropout
 functional = types.ModuleType("paddle.nn.functional")
 functional.relu = lambda x: Tensor(np.maximum(_unwrap(x), 0))
 nn.functional = functional

@@ -128,3 +128,41 @@ def test_pillar_scatter_matches_the_reference_class(gp):
     np.testing.assert_array_equal(sc.forward(vf, gp["coors"], 2), gp["canvas_b2"])
     np.testing.assert_array_equal(sc.forward(vf, gp["coors_b3"], 3), gp["canvas_b3"])   # sample 1 is empty
     assert not gp["canvas_b3"][1].any()
+
+
+# ---------------------------------------------------------------------------------- model definitions
+MODEL_CASES = [("PointNet2_SSG_Clas", False, False), ("PointNet2_SSG_Clas", True, False),
+               ("PointNet2_MSG_Clas", False, False), ("PointNet2_SSG_Seg", False, True),
+               ("PointNet2_MSG_Seg", True, True)]
+
+
+@pytest.mark.parametrize("name,normal_channel,seg", MODEL_CASES)
+def test_model_definitions_match_the_reference_classes(golden_dir, name, normal_channel, seg):
+    """tests/golden/make_golden_models.py: the reference's PointNet2_* classes executed over the stub.  Pins
+    the oracle's model wiring, ``Categorical``, the heads and which BatchNorms follow eval(); the conv /
+    linear / batch-norm arithmetic on both sides is an fp64-accumulated restatement (hence 1e-5, not 0)."""
+    import sys
+    sys.path.insert(0, golden_dir)
+    import param_gen
+    from oracle import models_np
+    gm = np.load(os.path.join(golden_dir, "models_ref.npz"))
+    tag = name + ("_nc" if normal_channel else "")
+    model = getattr(models_np, name)(normal_channel=normal_channel)
+    n = len(param_gen.install(model, tag))
+    assert n == {"PointNet2_SSG_Clas": 23, "PointNet2_MSG_Clas": 47, "PointNet2_SSG_Seg": 35, "PointNet2_MSG_Seg": 51}[name]
+    x = np.concatenate([gm["xyz"], gm["normals"]], 1) if normal_channel else gm["xyz"]
+    inputs = (x, gm["labels"]) if seg else x
+    start = (gm["start1"], gm["start2"])
+
+    def check(y, key):
+        if seg:
+            np.testing.assert_allclose(y[:, ::8], gm[key + ":sub8"], rtol=1e-5, atol=1e-5)
+            s = np.array([y.astype(np.float64).sum(), np.abs(y.astype(np.float64)).sum()])
+            np.testing.assert_allclose(s, gm[key + ":sum"], rtol=1e-6)
+        else:
+            np.testing.assert_allclose(y, gm[key], rtol=1e-5, atol=1e-5)
+
+    check(model.eval()(inputs, start_idx=start), f"{tag}:eval")
+    check(model.train()(inputs, start_idx=start), f"{tag}:train")
+    np.testing.assert_allclose(model.bn1._mean, gm[f"{tag}:bn1_mean_after_train"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(model.bn1._variance, gm[f"{tag}:bn1_var_after_train"], rtol=1e-5, atol=1e-6)
