@@ -166,3 +166,28 @@ def test_model_definitions_match_the_reference_classes(golden_dir, name, normal_
     check(model.train()(inputs, start_idx=start), f"{tag}:train")
     np.testing.assert_allclose(model.bn1._mean, gm[f"{tag}:bn1_mean_after_train"], rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(model.bn1._variance, gm[f"{tag}:bn1_var_after_train"], rtol=1e-5, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------- pillar glue (pure NumPy in the reference)
+def test_voxel_generator_and_batch_merge_match_the_reference(golden_dir):
+    """tests/golden/make_golden_pillar_glue.py: VoxelGenerator geometry (voxel_generator.py:5-43) and the batch
+    layout of merge_second_batch (preprocess.py:16-42), produced by the reference's own code; checked on the
+    oracle AND on the product's host-side mirrors (both run without a GPU)."""
+    torch = pytest.importorskip("torch")
+    from oracle import pillars_np
+    from papc_b200 import pillars
+    gg = np.load(os.path.join(golden_dir, "pillar_glue_ref.npz"))
+    for tag in ("yaml", "default", "odd"):
+        a = gg[f"{tag}_args"]
+        gen = pillars.VoxelGenerator(tuple(a[:3]), tuple(a[3:]), 100, 12000)
+        for got, key in ((gen.voxel_size, "voxel_size"), (gen.point_cloud_range, "range"), (gen.grid_size, "grid")):
+            assert got.dtype == gg[f"{tag}_{key}"].dtype
+            np.testing.assert_array_equal(got, gg[f"{tag}_{key}"])
+        assert gen.max_num_points_per_voxel == 100
+    coors = [gg[f"batch{i}_coordinates"] for i in range(3)]
+    np.testing.assert_array_equal(pillars_np.merge_coordinates(coors), gg["merged_coordinates"])
+    got = pillars.merge_coordinates([torch.from_numpy(c) for c in coors])
+    assert got.dtype == torch.int32
+    np.testing.assert_array_equal(got.numpy(), gg["merged_coordinates"])
+    np.testing.assert_array_equal(np.concatenate([gg[f"batch{i}_voxels"] for i in range(3)]), gg["merged_voxels"])
+    np.testing.assert_array_equal(np.concatenate([gg[f"batch{i}_num_points"] for i in range(3)]), gg["merged_num_points"])
