@@ -96,6 +96,19 @@ if __name__ == "__main__":
     out["fp_out_nop1"] = R.PointNetFeaturePropagation(9, [])(T(xyz_cf), T(xyz2), None, T(p2)).numpy()
     out["fp_out_s1"] = R.PointNetFeaturePropagation(D + 9, [])(T(xyz_cf), T(xyz2[:, :, :1]), T(feats_cf),
                                                                T(p2[:, :, :1])).numpy()
+    # ---- error behaviour of the reference: what its own code does, recorded as exception names
+    def raised(fn):
+        try:
+            fn()
+            return "none"
+        except Exception as e:      # noqa: BLE001 (the type is the datum)
+            return type(e).__name__
+    far = np.full((1, 1, 3), 50.0, np.float32)
+    out["err_empty_ball_query"] = np.array(raised(lambda: R.query_ball_point(0.2, 4, T(k3), T(far))))
+    out["err_empty_ball_value"] = R.query_ball_point(0.2, 4, T(k3), T(far)).numpy()      # N in every slot
+    out["err_empty_ball_gather"] = np.array(raised(
+        lambda: R.index_points(T(k3), R.query_ball_point(0.2, 4, T(k3), T(far)))))
+    out["err_nsample_gt_n"] = np.array(raised(lambda: R.query_ball_point(0.2, 7, T(k3), T(k3[:, :1]))))
     assert not paddle_stub._next_randint
     np.savez_compressed(os.path.join(HERE, "layers_ref.npz"), **out)
     for k, v in out.items():

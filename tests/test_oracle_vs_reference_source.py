@@ -191,3 +191,22 @@ def test_voxel_generator_and_batch_merge_match_the_reference(golden_dir):
     np.testing.assert_array_equal(got.numpy(), gg["merged_coordinates"])
     np.testing.assert_array_equal(np.concatenate([gg[f"batch{i}_voxels"] for i in range(3)]), gg["merged_voxels"])
     np.testing.assert_array_equal(np.concatenate([gg[f"batch{i}_num_points"] for i in range(3)]), gg["merged_num_points"])
+
+
+def test_error_behaviour_of_the_reference_code(g):
+    """SURVEY 8(b) error conventions, as the reference's own code behaves: an empty ball leaves N in every
+    slot (no exception until the gather, which raises IndexError); nsample > N raises IndexError.  The oracle
+    behaves the same; the product returns N-filled groups (``check_empty=True`` raises IndexError) and turns
+    nsample > N into a ValueError before launch (tests/test_gpu_sa.py::test_ball_query_errors)."""
+    assert str(g["err_empty_ball_query"]) == "none"
+    assert (g["err_empty_ball_value"] == 6).all()
+    assert str(g["err_empty_ball_gather"]) == "IndexError"
+    assert str(g["err_nsample_gt_n"]) == "IndexError"
+    k3 = g["kat_k3_xyz"]
+    far = np.full((1, 1, 3), 50.0, np.float32)
+    idx = layers_np.query_ball_point(0.2, 4, k3, far)
+    np.testing.assert_array_equal(idx, g["err_empty_ball_value"])
+    with pytest.raises(IndexError):
+        layers_np.index_points(k3, idx)
+    with pytest.raises(IndexError):
+        layers_np.query_ball_point(0.2, 7, k3, k3[:, :1])
