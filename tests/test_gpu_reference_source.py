@@ -79,3 +79,18 @@ def test_feature_interpolation(g):
         rows, cin = layers.feature_interpolate(_cu(xyz1), _cu(a2), _cu(a1) if a1 is not None else None, _cu(b2))
         got = rows.cpu().numpy().reshape(B, N, -1)[:, :, :cin].transpose(0, 2, 1)
         np.testing.assert_allclose(got, g[key], rtol=1e-5, atol=1e-5, err_msg=key)
+
+
+def test_indices_at_baseline_config_2(golden_dir):
+    """The bench workload's sampling / grouping indices (32 x 1024 points; sa1: FPS 512, r 0.2, K 32; sa2: FPS 128,
+    r 0.4, K 64) against the reference's own code (tests/golden/make_golden_c2.py): bit-exact."""
+    from papc_b200 import synth
+    gc = np.load(os.path.join(golden_dir, "c2_indices_ref.npz"))
+    B, N = 32, 1024
+    xyz = _cu(np.ascontiguousarray(synth.clouds(B, N, seed=0).transpose(0, 2, 1)))
+    f1, l1 = layers.farthest_point_sample_idx(xyz, 512, _cu(synth.fps_start(B, N, seed=1)), return_xyz=True)
+    np.testing.assert_array_equal(f1.cpu().numpy(), gc["fps1"])
+    np.testing.assert_array_equal(layers.query_ball_point(0.2, 32, xyz, l1).cpu().numpy(), gc["ball1"])
+    f2, l2 = layers.farthest_point_sample_idx(l1, 128, _cu(np.zeros(B, np.int64)), return_xyz=True)
+    np.testing.assert_array_equal(f2.cpu().numpy(), gc["fps2"])
+    np.testing.assert_array_equal(layers.query_ball_point(0.4, 64, l1, l2).cpu().numpy(), gc["ball2"])

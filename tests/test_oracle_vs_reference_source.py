@@ -210,3 +210,20 @@ def test_error_behaviour_of_the_reference_code(g):
         layers_np.index_points(k3, idx)
     with pytest.raises(IndexError):
         layers_np.query_ball_point(0.2, 7, k3, k3[:, :1])
+
+
+def test_c_oracle_indices_at_baseline_config_2(golden_dir):
+    """tests/golden/make_golden_c2.py: FPS and ball-query indices of the bench workload (32 x 1024 points, sa1 and
+    sa2 of PointNet++ SSG) from the reference's own code; the C oracle -- the arithmetic the kernels use --
+    reproduces all 20 480 groups."""
+    from papc_b200 import synth
+    gc = np.load(os.path.join(golden_dir, "c2_indices_ref.npz"))
+    B, N = 32, 1024
+    xyz = np.ascontiguousarray(synth.clouds(B, N, seed=0).transpose(0, 2, 1))
+    f1 = capi.farthest_point_sample(xyz, 512, synth.fps_start(B, N, seed=1))
+    np.testing.assert_array_equal(f1, gc["fps1"])
+    l1 = layers_np.index_points(xyz, f1)
+    np.testing.assert_array_equal(capi.query_ball_point(0.2, 32, xyz, l1)[0], gc["ball1"])
+    f2 = capi.farthest_point_sample(l1, 128, np.zeros(B, np.int64))
+    np.testing.assert_array_equal(f2, gc["fps2"])
+    np.testing.assert_array_equal(capi.query_ball_point(0.4, 64, l1, layers_np.index_points(l1, f2))[0], gc["ball2"])
