@@ -94,3 +94,28 @@ def test_indices_at_baseline_config_2(golden_dir):
     f2, l2 = layers.farthest_point_sample_idx(l1, 128, _cu(np.zeros(B, np.int64)), return_xyz=True)
     np.testing.assert_array_equal(f2.cpu().numpy(), gc["fps2"])
     np.testing.assert_array_equal(layers.query_ball_point(0.4, 64, l1, l2).cpu().numpy(), gc["ball2"])
+
+
+def test_indices_at_baseline_config_3(golden_dir):
+    """PointNet++ MSG segment (16 x 2048 points; sa1: FPS 512, r .1/.2/.4, K 32/64/128; sa2: FPS 128, r .4/.8,
+    K 64/128) against sha256 digests of the reference code's index arrays (tests/golden/make_golden_c3.py)."""
+    import hashlib
+    from papc_b200 import synth
+
+    def digest(t):
+        return hashlib.sha256(np.ascontiguousarray(t.cpu().numpy().astype(np.int64)).tobytes()).hexdigest()
+
+    gc = np.load(os.path.join(golden_dir, "c3_indices_ref.npz"))
+    B, N = 16, 2048
+    xyz = _cu(np.ascontiguousarray(synth.clouds(B, N, seed=0).transpose(0, 2, 1)))
+    f1, l1 = layers.farthest_point_sample_idx(xyz, 512, _cu(synth.fps_start(B, N, seed=1)), return_xyz=True)
+    np.testing.assert_array_equal(f1[0].cpu().numpy(), gc["fps1:cloud0"])
+    assert digest(f1) == str(gc["fps1:sha256"])
+    for r, k in ((0.1, 32), (0.2, 64), (0.4, 128)):
+        b = layers.query_ball_point(r, k, xyz, l1)
+        np.testing.assert_array_equal(b[0].cpu().numpy(), gc[f"sa1_ball_r{r}_k{k}:cloud0"], err_msg=str((r, k)))
+        assert digest(b) == str(gc[f"sa1_ball_r{r}_k{k}:sha256"]), (r, k)
+    f2, l2 = layers.farthest_point_sample_idx(l1, 128, _cu(np.zeros(B, np.int64)), return_xyz=True)
+    assert digest(f2) == str(gc["fps2:sha256"])
+    for r, k in ((0.4, 64), (0.8, 128)):
+        assert digest(layers.query_ball_point(r, k, l1, l2)) == str(gc[f"sa2_ball_r{r}_k{k}:sha256"]), (r, k)

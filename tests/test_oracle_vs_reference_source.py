@@ -227,3 +227,30 @@ def test_c_oracle_indices_at_baseline_config_2(golden_dir):
     f2 = capi.farthest_point_sample(l1, 128, np.zeros(B, np.int64))
     np.testing.assert_array_equal(f2, gc["fps2"])
     np.testing.assert_array_equal(capi.query_ball_point(0.4, 64, l1, layers_np.index_points(l1, f2))[0], gc["ball2"])
+
+
+def _digest(a):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(np.asarray(a).astype(np.int64)).tobytes()).hexdigest()
+
+
+def test_c_oracle_indices_at_baseline_config_3(golden_dir):
+    """tests/golden/make_golden_c3.py: PointNet++ MSG segment, 16 x 2048 points, three + two radii (2.2 M indices,
+    committed as sha256 digests + cloud 0): the C oracle reproduces every array of the reference's code."""
+    from papc_b200 import synth
+    gc = np.load(os.path.join(golden_dir, "c3_indices_ref.npz"))
+    B, N = 16, 2048
+    xyz = np.ascontiguousarray(synth.clouds(B, N, seed=0).transpose(0, 2, 1))
+    f1 = capi.farthest_point_sample(xyz, 512, synth.fps_start(B, N, seed=1))
+    assert _digest(f1) == str(gc["fps1:sha256"])
+    np.testing.assert_array_equal(f1[0], gc["fps1:cloud0"])
+    l1 = layers_np.index_points(xyz, f1)
+    for r, k in ((0.1, 32), (0.2, 64), (0.4, 128)):
+        b, empty = capi.query_ball_point(r, k, xyz, l1)
+        assert empty == 0 and _digest(b) == str(gc[f"sa1_ball_r{r}_k{k}:sha256"]), (r, k)
+        np.testing.assert_array_equal(b[0], gc[f"sa1_ball_r{r}_k{k}:cloud0"])
+    f2 = capi.farthest_point_sample(l1, 128, np.zeros(B, np.int64))
+    assert _digest(f2) == str(gc["fps2:sha256"])
+    l2 = layers_np.index_points(l1, f2)
+    for r, k in ((0.4, 64), (0.8, 128)):
+        assert _digest(capi.query_ball_point(r, k, l1, l2)[0]) == str(gc[f"sa2_ball_r{r}_k{k}:sha256"]), (r, k)
