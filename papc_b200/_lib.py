@@ -13,7 +13,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpapc_b200.so")
+# PAPC_B200_LIB: development override (e.g. the triage build of tools/build_triage.sh)
+LIB_PATH = os.environ.get("PAPC_B200_LIB") or os.path.join(_HERE, "lib", "libpapc_b200.so")
 
 PAPC_OK = 0
 XYZ_FIRST, FEATS_FIRST = 0, 1

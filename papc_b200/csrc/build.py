@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 OUT_DIR = os.path.join(os.path.dirname(HERE), "lib")
 OUT = os.path.join(OUT_DIR, "libpapc_b200.so")
-SOURCES = ["capi.cu", "fps.cu", "ball_query.cu", "sa_mlp.cu", "sa_mlp_tc.cu", "sa_mlp_tt.cu", "pillars.cu", "feature_prop.cu"]
+SOURCES = ["capi.cu", "fps.cu", "ball_query.cu", "sa_mlp.cu", "sa_mlp_tc.cu", "sa_mlp_tt.cu", "sa_chain.cu", "pillars.cu", "feature_prop.cu"]
 # per-file flags.  fps.cu: the distance is pinned as separately rounded multiplies and adds.
 EXTRA = {"fps.cu": ["-fmad=false"]}
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -49,7 +49,8 @@ def build(force=False, verbose=False, ptxas_info=False):
     failed = [s for s, p in procs if p.wait() != 0]
     if failed:
         raise RuntimeError("nvcc failed for " + ", ".join(failed))
-    if procs or force or not os.path.exists(OUT):
+    stale_link = not os.path.exists(OUT) or any(os.path.getmtime(o) > os.path.getmtime(OUT) for o in objs)
+    if procs or force or stale_link:
         cmd = [NVCC, "-shared", "-o", OUT, *objs, "-lcudart"]
         if verbose:
             print(" ".join(cmd))

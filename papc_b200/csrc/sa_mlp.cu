@@ -16,6 +16,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "sa_chain.cuh"
 #include "sa_mlp_tc.cuh"
 #include "sa_mlp_tt.cuh"
 
@@ -868,11 +869,54 @@ extern "C" int papc_sa_pool_finish_f32(const float *pool_max, const float *pool_
 
 // ---- monolithic driver: workspace carving ------------------------------------------------
 namespace {
+static bool pointmlp_shape_ok(int c0) { return c0 >= 16 && c0 <= 128 && c0 % 16 == 0; }
 struct WsPlan {
     size_t y[2], pool_max, pool_min, partial, sums, scale, shift, wimg, wimg_bytes;
     size_t counters, fold, mom_partial, colscale, colscale_stride, total;
     size_t counters_bytes;  // 256 bytes of counters + the fixed-point statistic accumulators (see FusedBn)
+    // chained path (sa_chain.cu): 0 = off, 1 = points only (folded first layer), 2 = gathered source image
+    int chain;
+    size_t ch_scale[3], ch_shift[3], ch_colscale[3];  // per-layer BatchNorm scale / shift / fp16 column scale
+    size_t ch_wimg[3];                                // per-layer pre-split weight images (chain::prep_weights)
+    size_t image, image_cs, image_absmax, mid;
 };
+
+// PAPC_CHAIN=1 runs eligible 3-layer stacks on the chained kernels (sa_chain.cu): 4x less DRAM traffic, but as
+// measured on the B200 (profiles/r02_chain_*.txt) still slower than the layer-at-a-time kernels at BASELINE
+// config 2 (sa1 185 vs 129 us, sa2 230 vs 219 us), so the default stays the layer path.
+static bool chain_enabled() {
+    const char *e = getenv("PAPC_CHAIN");
+    return e && e[0] == '1';
+}
+
+// Which chained plan (if any) runs this 3-layer batch-statistics MLP?  Shapes only, so that the workspace
+// query and the run agree.
+static int chain_kind(const papc_group_source *src, const papc_mlp *mlp) {
+    if (!chain_enabled() || tc_level() < 2) return 0;
+    if (src->grouped || mlp->num_layers != 3 || mlp->bn_mode != PAPC_BN_BATCH) return 0;
+    if (src->new_xyz == nullptr || src->idx == nullptr) return 0;   // group_all stacks keep the layer kernels
+    const long long M = (long long)src->B * src->S * src->K;
+    if (M <= 0 || M >= (1LL << 31)) return 0;
+    if (!(src->K == 32 || src->K == 64 || src->K == 128)) return 0;
+    const int c1 = mlp->layers[0].cout, c2 = mlp->layers[1].cout, c3 = mlp->layers[2].cout;
+    if (c1 % 16 != 0 || c2 % 16 != 0 || c1 > 128 || c2 > 128 || c3 > 256 || c3 < 1) return 0;
+    chain::ChainArgs a{};
+    a.M = M; a.K = src->K; a.nl = 2; a.ca = c2; a.cb = c3; a.nt = (c3 + 127) / 128; a.ka = c1;
+    if (src->D == 0 && mlp->cin == 3) {
+        a.in_mode = chain::IN_POINTMLP;
+        if (!chain::eligible(a)) return 0;
+        return pointmlp_shape_ok(c1) ? 1 : 0;
+    }
+    if (src->D > 0 && (reinterpret_cast<uintptr_t>(src->feats) & 15u) == 0) {
+        // pass B: gather -> L1 -> L2 (store);  pass C: tiles -> L2 -> L3
+        chain::ChainArgs b = a;
+        b.in_mode = chain::IN_GATHER; b.ka = chain::image_ld(src->D); b.ca = c1; b.cb = c2; b.nt = 1; b.store_mid = 1;
+        a.in_mode = chain::IN_TILE;
+        if (!chain::eligible(a) || !chain::eligible(b)) return 0;
+        return 2;
+    }
+    return 0;
+}
 static int plan_ws(const papc_group_source *src, const papc_mlp *mlp, WsPlan *p) {
     if (!src || !mlp) return PAPC_EINVAL;
     if (mlp->num_layers < 1 || mlp->num_layers > PAPC_MAX_MLP_LAYERS) return PAPC_EINVAL;
@@ -880,11 +924,13 @@ static int plan_ws(const papc_group_source *src, const papc_mlp *mlp, WsPlan *p)
     const long long G = (long long)src->B * src->S;
     int maxc = 0;
     size_t ybytes[2] = {0, 0};
+    for (int l = 0; l < mlp->num_layers; ++l)
+        if (mlp->layers[l].cout <= 0) return PAPC_EINVAL;
+    p->chain = chain_kind(src, mlp);
     for (int l = 0; l < mlp->num_layers; ++l) {
         const int c = mlp->layers[l].cout;
-        if (c <= 0) return PAPC_EINVAL;
         maxc = c > maxc ? c : maxc;
-        if (l + 1 < mlp->num_layers) {
+        if (l + 1 < mlp->num_layers && p->chain == 0) {
             const size_t b = (size_t)M * c * sizeof(float);
             if (b > ybytes[l & 1]) ybytes[l & 1] = b;
         }
@@ -915,6 +961,23 @@ static int plan_ws(const papc_group_source *src, const papc_mlp *mlp, WsPlan *p)
     p->mom_partial = take((size_t)2 * kNumSMs * 9 * sizeof(double));
     p->colscale_stride = align_up((size_t)maxc * sizeof(float), 256);
     p->colscale = take(2 * p->colscale_stride);
+    p->image = p->image_cs = p->image_absmax = p->mid = 0;
+    if (p->chain != 0) {
+        for (int l = 0; l < 3; ++l) {
+            p->ch_scale[l] = take((size_t)maxc * sizeof(float));
+            p->ch_shift[l] = take((size_t)maxc * sizeof(float));
+            p->ch_colscale[l] = take((size_t)maxc * sizeof(float));
+            const int kin = l == 0 ? chain::image_ld(src->D) : mlp->layers[l - 1].cout;
+            p->ch_wimg[l] = take(chain::weight_image_bytes(mlp->layers[l].cout, (kin + 15) / 16 * 16));
+        }
+    }
+    if (p->chain == 2) {
+        const long long R = (long long)src->B * src->N;
+        p->image = take(chain::image_bytes(R, src->D));
+        p->image_cs = take((size_t)(src->D + 6) * sizeof(float));
+        p->image_absmax = take((size_t)(src->D + 3) * sizeof(unsigned int));
+        p->mid = take((size_t)ceil_div<long long>(M, 128) * (size_t)mlp->layers[0].cout * 512);
+    }
     p->total = off;
     return PAPC_OK;
 }
@@ -931,6 +994,157 @@ static bool pointmlp_ok(const papc_group_source *src, const papc_mlp *mlp) {
     if (!tt::eligible(prob)) return false;
     const long long M = (long long)src->B * src->S * src->K;
     return !(pool && M % src->K != 0);
+}
+}  // namespace
+
+// ---- the chained plan: statistics passes recompute, the chain keeps the hidden activation on the SM
+namespace {
+static int run_chain(const papc_group_source *src, const papc_mlp *mlp, const WsPlan &p, char *ws, float *out,
+                     int out_layout, papc_stream_t stream) {
+    cudaStream_t st = as_stream(stream);
+    const long long M = (long long)src->B * src->S * src->K;
+    const papc_mlp_layer &l1 = mlp->layers[0], &l2 = mlp->layers[1], &l3 = mlp->layers[2];
+    const int c1 = l1.cout, c2 = l2.cout, c3 = l3.cout;
+    float *pmax = reinterpret_cast<float *>(ws + p.pool_max);
+    float *pmin = reinterpret_cast<float *>(ws + p.pool_min);
+    double *partial = reinterpret_cast<double *>(ws + p.partial);
+    unsigned int *counters = reinterpret_cast<unsigned int *>(ws + p.counters);
+    unsigned long long *fix_acc = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(counters) + 256);
+    float *scale[3], *shift[3], *colscale[3];
+    uint32_t *wimg[3];
+    for (int l = 0; l < 3; ++l) {
+        scale[l] = reinterpret_cast<float *>(ws + p.ch_scale[l]);
+        shift[l] = reinterpret_cast<float *>(ws + p.ch_shift[l]);
+        colscale[l] = reinterpret_cast<float *>(ws + p.ch_colscale[l]);
+        wimg[l] = reinterpret_cast<uint32_t *>(ws + p.ch_wimg[l]);
+    }
+    const float sqrt_m = nextafterf((float)sqrt((double)M), INFINITY);
+    const double f1 = 2.0 * (double)M * mlp->cin * c1, f2 = 2.0 * (double)M * c1 * c2, f3 = 2.0 * (double)M * c2 * c3;
+    const double G = (double)(M / src->K);
+    int rc;
+
+    // fields shared by every launch of this call
+    chain::ChainArgs base{};
+    base.M = M; base.K = src->K; base.N = src->N; base.S = src->S;
+    base.xyz = src->xyz; base.new_xyz = src->new_xyz; base.idx = src->idx;
+    base.stats_partial = partial; base.partial_rows = grid_rows(M);
+    base.fix_acc = fix_acc; base.eps = mlp->eps; base.count = (double)M; base.sqrt_count = sqrt_m;
+    base.nt = 1;
+    auto set_bn_out = [&](chain::ChainArgs &a, int l, bool next_f16) {
+        const papc_mlp_layer &ly = mlp->layers[l];
+        a.counter = counters + l;
+        a.gamma = ly.gamma; a.beta = ly.beta;
+        a.scale = scale[l]; a.shift = shift[l]; a.mean_out = ly.batch_mean; a.var_out = ly.batch_var;
+        a.out_colscale = next_f16 ? colscale[l] : nullptr;
+    };
+    // weight images of layers 2 and 3 (their column scales follow from the previous layer's BatchNorm
+    // parameters, nothing data dependent); layer 1's image (gathered case) is added below
+    chain::WeightSpec wspec[3];
+    int nspec = 0;
+    auto bn_scaled = [&](int l) {   // layer l (1 or 2, zero based) with the fp16 column scale of layer l-1's output
+        chain::WeightSpec w{};
+        const papc_mlp_layer &ly = mlp->layers[l], &prev = mlp->layers[l - 1];
+        w.W = ly.weight; w.rows = ly.cout; w.ld = prev.cout; w.K = prev.cout; w.k0 = 0; w.nk = prev.cout; w.xyz = -1;
+        w.cs_on = 1; w.cs_gamma = prev.gamma; w.cs_beta = prev.beta; w.cs_sqrt_count = sqrt_m;
+        w.image = wimg[l];
+        return w;
+    };
+
+    if (p.chain == 1) {
+        wspec[nspec++] = bn_scaled(1);
+        wspec[nspec++] = bn_scaled(2);
+        rc = chain::prep_weights(wspec, nspec, st);
+        if (rc != PAPC_OK) return rc;
+        // layer 1 (3 -> c1) analytically from the moments of the centred points (as the layer path does)
+        tt::MomentArgs m{};
+        m.xyz = src->xyz; m.new_xyz = src->new_xyz; m.idx = src->idx;
+        m.N = src->N; m.S = src->S; m.K = src->K; m.M = M;
+        m.W0 = l1.weight; m.b0 = l1.bias; m.gamma = l1.gamma; m.beta = l1.beta;
+        m.eps = mlp->eps; m.c0 = c1; m.sqrt_M = sqrt_m;
+        m.partial = reinterpret_cast<double *>(ws + p.mom_partial);
+        m.counter = counters + PAPC_MAX_MLP_LAYERS;
+        m.scale = scale[0]; m.shift = shift[0]; m.mean_out = l1.batch_mean; m.var_out = l1.batch_var;
+        m.l0_fold = reinterpret_cast<float *>(ws + p.fold);
+        m.out_colscale = colscale[0];
+        rc = tt::launch_moments(m, st);
+        if (rc != PAPC_OK) return rc;
+        // pass "stats 2": points -> [L1 folded] -> L2 -> sum / sum^2
+        chain::ChainArgs a = base;
+        a.in_mode = chain::IN_POINTMLP; a.nl = 1; a.pdl = 1;
+        a.l0_fold = m.l0_fold;
+        a.ka = c1; a.ca = c2; a.wimgA = wimg[1];
+        a.biasA = l2.bias;
+        set_bn_out(a, 1, true);
+        a.prof_flops = f1 + f2; a.prof_bytes = 16.0 * (double)M; a.prof_cin = c1; a.prof_cout = c2;
+        rc = chain::launch(a, st);
+        if (rc != PAPC_OK) return rc;
+        // pass "chain": points -> L2 -> BN2 + ReLU -> L3 -> statistics + max / min pool
+        chain::ChainArgs b = a;
+        b.nl = 2; b.pool = 1; b.nt = (c3 + 127) / 128;
+        b.scaleA = scale[1]; b.shiftA = shift[1];
+        b.cb = c3; b.wimgB = wimg[2]; b.biasB = l3.bias;
+        b.pool_max = pmax; b.pool_min = pmin;
+        set_bn_out(b, 2, false);
+        b.prof_flops = f3; b.prof_bytes = 16.0 * (double)M + 8.0 * G * c3; b.prof_cin = c2; b.prof_cout = c3;
+        rc = chain::launch(b, st);
+        if (rc != PAPC_OK) return rc;
+    } else {
+        const long long R = (long long)src->B * src->N;
+        uint8_t *image = reinterpret_cast<uint8_t *>(ws + p.image);
+        float *img_cs = reinterpret_cast<float *>(ws + p.image_cs);
+        unsigned int *absmax = reinterpret_cast<unsigned int *>(ws + p.image_absmax);
+        uint8_t *mid = reinterpret_cast<uint8_t *>(ws + p.mid);
+        rc = chain::build_image(src->feats, src->xyz, R, src->D, image, img_cs, absmax, st);
+        if (rc != PAPC_OK) return rc;
+        const bool xyz_first = src->order == PAPC_XYZ_FIRST;
+        const int ld_img = chain::image_ld(src->D);
+        {
+            chain::WeightSpec w{};
+            w.W = l1.weight; w.rows = c1; w.ld = mlp->cin; w.K = ld_img;
+            w.k0 = xyz_first ? 3 : 0; w.nk = src->D; w.xyz = xyz_first ? 0 : src->D;
+            w.colscale = img_cs; w.image = wimg[0];
+            wspec[nspec++] = w;
+        }
+        wspec[nspec++] = bn_scaled(1);
+        wspec[nspec++] = bn_scaled(2);
+        rc = chain::prep_weights(wspec, nspec, st);
+        if (rc != PAPC_OK) return rc;
+        // pass "stats 1": gather -> L1 -> sum / sum^2
+        chain::ChainArgs a = base;
+        a.in_mode = chain::IN_GATHER; a.nl = 1; a.pdl = 1;
+        a.image = image; a.img_rows = (int)R; a.img_ld = ld_img;
+        a.ka = ld_img; a.ca = c1; a.wimgA = wimg[0];
+        a.wxyz = l1.weight + (xyz_first ? 0 : src->D); a.wxyz_ld = mlp->cin;
+        a.biasA = l1.bias;
+        set_bn_out(a, 0, true);
+        a.prof_flops = f1; a.prof_bytes = 4.0 * (double)M * (3 + src->D); a.prof_cin = mlp->cin; a.prof_cout = c1;
+        rc = chain::launch(a, st);
+        if (rc != PAPC_OK) return rc;
+        // pass "stats 2": gather -> L1 -> BN1 + ReLU (stored as operand tiles) -> L2 -> sum / sum^2
+        chain::ChainArgs b = a;
+        b.nl = 2; b.store_mid = 1; b.mid_out = mid; b.pdl = 1;
+        b.scaleA = scale[0]; b.shiftA = shift[0];
+        b.cb = c2; b.wimgB = wimg[1]; b.biasB = l2.bias;
+        set_bn_out(b, 1, true);
+        b.prof_flops = f2; b.prof_bytes = 4.0 * (double)M * (3 + src->D) + 4.0 * (double)M * c1;
+        b.prof_cin = c1; b.prof_cout = c2;
+        rc = chain::launch(b, st);
+        if (rc != PAPC_OK) return rc;
+        // pass "chain": tiles -> L2 -> BN2 + ReLU -> L3 -> statistics + max / min pool (newest tiles first)
+        chain::ChainArgs c = base;
+        c.in_mode = chain::IN_TILE; c.nl = 2; c.pool = 1; c.nt = (c3 + 127) / 128; c.reverse = 1; c.pdl = 1;
+        c.mid_in = mid;
+        c.ka = c1; c.ca = c2; c.wimgA = wimg[1];
+        c.biasA = l2.bias;
+        c.scaleA = scale[1]; c.shiftA = shift[1];
+        c.cb = c3; c.wimgB = wimg[2]; c.biasB = l3.bias;
+        c.pool_max = pmax; c.pool_min = pmin;
+        set_bn_out(c, 2, false);
+        c.prof_flops = f3; c.prof_bytes = 4.0 * (double)M * c1 + 8.0 * G * c3; c.prof_cin = c2; c.prof_cout = c3;
+        rc = chain::launch(c, st);
+        if (rc != PAPC_OK) return rc;
+    }
+    return papc_sa_pool_finish_f32(pmax, pmin, scale[2], shift[2], src->B, src->S, c3, out, out_layout, stream);
 }
 }  // namespace
 
@@ -974,6 +1188,7 @@ extern "C" int papc_sa_mlp_f32(const papc_group_source *src, const papc_mlp *mlp
     }
     // the in-kernel "last CTA" counters start at zero (they clean themselves afterwards)
     PAPC_CUDA_TRY(cudaMemsetAsync(counters, 0, p.counters_bytes, st));
+    if (p.chain != 0) return run_chain(src, mlp, p, ws, out, out_layout, stream);
 
     int cin = mlp->cin;
     const float *xprev = nullptr;

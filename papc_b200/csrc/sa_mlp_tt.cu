@@ -753,7 +753,9 @@ mlp_layer_tt_kernel(const __grid_constant__ TtArgs a) {
         //      shared-memory table -- instead of every thread gathering its rows' points itself.
         int idx1 = 0, grp1 = 0;
         long long bN1 = 0;
-        float4 pt1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        // raw loads of a later tile's point and centroid; they are combined only when that tile is published (any
+        // arithmetic on them here would stall this in-order warp for the whole global round trip)
+        float px1 = 0.f, py1 = 0.f, pz1 = 0.f, cx1 = 0.f, cy1 = 0.f, cz1 = 0.f;
         auto fetch_idx1 = [&](long long tile) {
             long long row = tile * kTile + (ptid & (kTile - 1));
             row = row < a.M ? row : a.M - 1;
@@ -762,17 +764,14 @@ mlp_layer_tt_kernel(const __grid_constant__ TtArgs a) {
             grp1 = rg.g;
             idx1 = a.idx != nullptr ? __ldg(a.idx + row) : rg.k;
         };
-        auto fetch_pt1 = [&]() {  // idx1 (arrived) -> pt1
+        auto fetch_pt1 = [&]() {  // idx1 (arrived) -> raw point / centroid loads
             const int n = min(max(idx1, 0), a.N - 1);
             const float *q = a.xyz + (bN1 + n) * 3;
-            float px = __ldg(q), py = __ldg(q + 1), pz = __ldg(q + 2);
+            px1 = __ldg(q); py1 = __ldg(q + 1); pz1 = __ldg(q + 2);
             if (a.new_xyz != nullptr) {
                 const float *cc = a.new_xyz + (long long)grp1 * 3;
-                px = __fsub_rn(px, __ldg(cc));
-                py = __fsub_rn(py, __ldg(cc + 1));
-                pz = __fsub_rn(pz, __ldg(cc + 2));
+                cx1 = __ldg(cc); cy1 = __ldg(cc + 1); cz1 = __ldg(cc + 2);
             }
-            pt1 = make_float4(px, py, pz, 0.f);
         };
 
         // ---- raw ring (SRC_PLAIN / SRC_GATHER): every thread lands ITS OWN 16-byte units of a chunk
@@ -925,7 +924,9 @@ mlp_layer_tt_kernel(const __grid_constant__ TtArgs a) {
                     // pt1 holds this tile's point of row ptid (issued one tile ago): publish it, pick up
                     // the rows this thread expands, then refill pt1 / idx1 for the next tiles
                     const uint32_t tab = sm + SmemLayout::xyz + 16u * (uint32_t)((ptl & 1) * kTile);
-                    if (ptid < kTile) sts128f(tab + 16u * (uint32_t)ptid, pt1);
+                    if (ptid < kTile)
+                        sts128f(tab + 16u * (uint32_t)ptid,
+                                make_float4(__fsub_rn(px1, cx1), __fsub_rn(py1, cy1), __fsub_rn(pz1, cz1), 0.f));
                     named_bar_sync(1, kProdThreads);
 #pragma unroll
                     for (int j = 0; j < kRPT; ++j) p_cur[j] = lds128f(tab + 16u * (uint32_t)(rb + kRowStride * j));
