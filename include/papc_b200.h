@@ -20,7 +20,10 @@
  *   - Return value: PAPC_OK (0) or a negative papc_status.  Invalid arguments are rejected
  *     before anything is launched.  papc_status_string() names a code.
  *   - Re-entrant: no global mutable state; concurrent calls on distinct streams/workspaces
- *     are safe.
+ *     are safe.  A few environment variables are read as kernel-selection A/B switches
+ *     (PAPC_MLP_TC, PAPC_CHAIN, PAPC_TT_PDL, PAPC_TT_TMA2D, PAPC_FPS_WIDE): every setting gives
+ *     the same results within the stated tolerances.  Switches that change results exist in
+ *     triage builds only (-DPAPC_TRIAGE / -DPAPC_TT_TRIAGE).
  */
 #ifndef PAPC_B200_H_
 #define PAPC_B200_H_
@@ -223,6 +226,12 @@ int papc_sa_pool_finish_f32(const float *pool_max, const float *pool_min, const 
  *     of x [M, ld_x] (ld_x >= mlp->cin, padding columns must be zero) -> out [M, cout_last].
  *     bn_mode / eps / per-layer pointers as in papc_mlp.
  */
+/*   papc_bn_relu_apply_f32: out = relu(scale * y + shift) over rows [M,cout] -- the last step of the step-wise
+ *     (batch-sharded, SyncBN) form of papc_pointwise_mlp_f32: per layer papc_mlp_layer_forward_f32 (src = NULL,
+ *     K = 1, no pooling) -> papc_mlp_stats_reduce_f64 -> all-reduce -> papc_bn_scale_shift_f32, then this.
+ */
+int papc_bn_relu_apply_f32(const float *y, const float *scale, const float *shift, int64_t M,
+                           int32_t cout, float *out, papc_stream_t stream);
 int papc_fp_interpolate_f32(const float *xyz1, const float *xyz2, const float *points1,
                             const float *points2, int B, int N, int S, int D1, int D2, int ld_out,
                             float *out, papc_stream_t stream);
@@ -265,6 +274,24 @@ int papc_pfn_f32(const float *features, const int32_t *num_voxels, const int32_t
                  int cout, const int32_t *num_valid, float *out, float *batch_mean,
                  float *batch_var, void *workspace, size_t workspace_bytes,
                  papc_stream_t stream);
+
+/* A10 (general form) one PFNLayer at any position                      pillars.py:9-41, 79-108
+ *     decorate != 0: x = features [P,T,F] (F >= 3); the layer input is the decorated tensor
+ *       [features, f_cluster(3), f_center(2), (|xyz| when with_distance, :92-94)] with padding rows zeroed
+ *       (num_voxels / coors as papc_pfn_f32).  decorate == 0: x [P,T,F] is the previous layer's output (F = cin).
+ *     y = x W (+ bias), weight [cin,units]; BatchNorm1D over all P*T rows; ReLU; max over T.
+ *     last_layer != 0: out [P,units] = the max (:34-36); else out [P,T,2*units] = [x | repeat(max)] (:38-40).
+ *     The default constructor num_filters=(64,128) is papc_pfn_layer_f32(decorate, units 32, not last) followed by
+ *     papc_pfn_layer_f32(plain, F = 64, units 128, last).  cin <= 128, units <= 128.
+ */
+size_t papc_pfn_layer_workspace_bytes(int P, int T, int units);
+int papc_pfn_layer_f32(const float *x, int decorate, int with_distance, const int32_t *num_voxels,
+                       const int32_t *coors, int P, int T, int F, float vx, float vy, float x_offset,
+                       float y_offset, const float *weight, const float *bias, const float *gamma,
+                       const float *beta, const float *running_mean, const float *running_var, int bn_mode,
+                       float eps, int units, int last_layer, const int32_t *num_valid, float *out,
+                       float *batch_mean, float *batch_var, void *workspace, size_t workspace_bytes,
+                       papc_stream_t stream);
 
 /* A11 PointPillarsScatter.forward                                     pillars.py:121-142
  *     voxel_features [P,C], coords [P,4] int32 (b,z,y,x) -> canvas [batch,C,ny,nx]; every canvas

@@ -79,6 +79,7 @@ _SIGNATURES = {
     "papc_bn_running_scale_shift_f32": (_I, [_vp, _vp, _vp, _vp, _F, C.c_int32, _vp, _vp, _vp]),
     "papc_sa_pool_finish_f32": (_I, [_vp, _vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp, _I,
                                       _vp]),
+    "papc_bn_relu_apply_f32": (_I, [_vp, _vp, _vp, _I64, C.c_int32, _vp, _vp]),
     "papc_fp_interpolate_f32": (_I, [_vp, _vp, _vp, _vp, _I, _I, _I, _I, _I, _I, _vp, _vp]),
     "papc_pointwise_mlp_workspace_bytes": (_SZ, [_I64, C.c_int32, C.POINTER(Mlp)]),
     "papc_pointwise_mlp_f32": (_I, [_vp, _I64, C.c_int32, C.POINTER(Mlp), _vp, _vp, _SZ, _vp]),
@@ -88,6 +89,9 @@ _SIGNATURES = {
     "papc_pfn_workspace_bytes": (_SZ, [_I, _I]),
     "papc_pfn_f32": (_I, [_vp, _vp, _vp, _I, _I, _I, _F, _F, _F, _F, _vp, _vp, _vp, _vp, _vp, _vp, _I,
                            _F, _I, _vp, _vp, _vp, _vp, _vp, _SZ, _vp]),
+    "papc_pfn_layer_workspace_bytes": (_SZ, [_I, _I, _I]),
+    "papc_pfn_layer_f32": (_I, [_vp, _I, _I, _vp, _vp, _I, _I, _I, _F, _F, _F, _F, _vp, _vp, _vp, _vp, _vp, _vp, _I,
+                                 _F, _I, _I, _vp, _vp, _vp, _vp, _vp, _SZ, _vp]),
     "papc_pillar_scatter_workspace_bytes": (_SZ, [_I, _I, _I]),
     "papc_pillar_scatter_f32": (_I, [_vp, _vp, _I, _I, _I, _I, _I, _vp, _vp, _vp, _SZ, _vp]),
 }

@@ -351,10 +351,12 @@ extern "C" int papc_fps_f32(const float *xyz, int B, int N, int npoint,
     if (N <= 256) { if (wide) FPS_GO(128, 2); FPS_GO(64, 4); }
     if (N <= 512) { if (wide) FPS_GO(256, 2); if (shape == 2) FPS_GO(64, 8); if (shape == 3) FPS_GO(32, 16); FPS_GO(128, 4); }
     if (N <= 1024) {
+#ifdef PAPC_TRIAGE   // timing experiments with stages of the reduction removed: WRONG RESULTS, triage builds only
         static const int dbg = [] { const char *e = getenv("PAPC_FPS_DBG"); return e ? atoi(e) : 0; }();
 #define FPS_DBG(D) if (dbg == D) return launch_fps_reg<128, 8, D>(xyz, B, N, npoint, start_idx, init_dist, out_idx, out_new_xyz, st)
         FPS_DBG(1); FPS_DBG(2); FPS_DBG(3); FPS_DBG(4); FPS_DBG(7);
 #undef FPS_DBG
+#endif
         if (wide) FPS_GO(256, 4); if (shape == 2) FPS_GO(64, 16); if (shape == 3) FPS_GO(32, 32); FPS_GO(128, 8); }
     if (N <= 2048) { if (wide) FPS_GO(512, 4); FPS_GO(256, 8); }
     if (N <= 4096) { if (wide) FPS_GO(1024, 4); FPS_GO(512, 8); }

@@ -664,6 +664,248 @@ extern "C" int papc_voxelize_f32(const float *points, int N, int F, const float 
 
 // ---------------------------------------------------------------------------------- PFN
 namespace {
+
+// ====================================================================== generic PFNLayer (any position)
+// pillars.py:29-41 for a layer that is NOT the fused (decorate + single last layer) case above: a first layer
+// with the distance channel, a non-last layer (its output is [x | max-repeat], :36-40) or a later layer reading
+// a materialised [P,T,cin] tensor.  Two kernels around the shared BatchNorm reduction (pfn_bn_kernel):
+//   pfn_gen_linear_kernel : one warp per pillar, rows of the pillar one at a time (lanes load the row, the
+//                           reduction broadcasts it with shuffles), y = x W (+ bias) -> y [P,T,u] and the
+//                           per-block sum / sum^2 over ALL P*T rows (padding rows included, as the reference);
+//   pfn_gen_finish_kernel : relu(scale * y + shift), max over T, then either [P,u] (last layer) or
+//                           [P,T,2u] = [x | repeat(max)].
+constexpr int kPfnGenMaxCin = 128;
+template <int CPL, bool DECORATE>
+__global__ void __launch_bounds__(kPfnWarps * 32)
+pfn_gen_linear_kernel(const float *__restrict__ x, const int32_t *__restrict__ num_voxels,
+                      const int32_t *__restrict__ coors, int P, int T, int F, int with_distance, float vx, float vy,
+                      float x_off, float y_off, const float *__restrict__ weight, const float *__restrict__ bias,
+                      int cin, int u, const int32_t *__restrict__ num_valid, float *__restrict__ y,
+                      double *__restrict__ partial) {
+    extern __shared__ float s_dynf[];
+    float *s_w = s_dynf;                                   // [cin][u]
+    size_t red_off = ((size_t)cin * u + 1) & ~(size_t)1;
+    double *s_red = reinterpret_cast<double *>(s_dynf + red_off);   // [warps][2][u]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < cin * u; i += blockDim.x) s_w[i] = weight[i];
+    __syncthreads();
+    const int Pv = num_valid ? min(*num_valid, P) : P;
+    float bch[CPL];
+    double ssum[CPL], ssq[CPL];
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) {
+        const int c = lane + 32 * q;
+        bch[q] = (bias && c < u) ? bias[c] : 0.f;
+        ssum[q] = 0.0;
+        ssq[q] = 0.0;
+    }
+    constexpr int XR = kPfnGenMaxCin / 32;
+    for (int p = blockIdx.x * kPfnWarps + warp; p < Pv; p += gridDim.x * kPfnWarps) {
+        float mx = 0.f, my = 0.f, mz = 0.f, ccx = 0.f, ccy = 0.f;
+        int n = T;
+        if (DECORATE) {
+            n = min(max(num_voxels[p], 0), T);
+            const float *src = x + (size_t)p * T * F;
+            float mean = 0.f;
+            if (lane < 3) {   // sequential fp32 sum over the T axis (zero padding adds nothing), pillars.py:82
+                float sacc = 0.f;
+                for (int t = 0; t < n; ++t) sacc = __fadd_rn(sacc, src[t * F + lane]);
+                mean = __fdiv_rn(sacc, (float)num_voxels[p]);
+            }
+            mx = __shfl_sync(0xffffffffu, mean, 0);
+            my = __shfl_sync(0xffffffffu, mean, 1);
+            mz = __shfl_sync(0xffffffffu, mean, 2);
+            ccx = __fadd_rn(__fmul_rn((float)coors[p * 4 + 3], vx), x_off);
+            ccy = __fadd_rn(__fmul_rn((float)coors[p * 4 + 2], vy), y_off);
+        }
+        float fs[CPL], fq[CPL];
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) { fs[q] = 0.f; fq[q] = 0.f; }
+        for (int t = 0; t < T; ++t) {
+            // the row (cin values) spread over the lanes: lane holds elements lane, lane+32, ...
+            float xr[XR];
+#pragma unroll
+            for (int j = 0; j < XR; ++j) {
+                const int k = lane + 32 * j;
+                float d = 0.f;
+                if (k < cin) {
+                    if (!DECORATE) {
+                        d = x[((size_t)p * T + t) * cin + k];
+                    } else if (t < n) {   // padding rows stay zero (features *= mask, pillars.py:102)
+                        const float *pt = x + ((size_t)p * T + t) * F;
+                        if (k < F) d = pt[k];
+                        else if (k == F) d = __fsub_rn(pt[0], mx);
+                        else if (k == F + 1) d = __fsub_rn(pt[1], my);
+                        else if (k == F + 2) d = __fsub_rn(pt[2], mz);
+                        else if (k == F + 3) d = __fsub_rn(pt[0], ccx);
+                        else if (k == F + 4) d = __fsub_rn(pt[1], ccy);
+                        else if (with_distance && k == F + 5)   // paddle.norm(features[:, :, :3], 2, 2), :93
+                            d = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(pt[0], pt[0]), __fmul_rn(pt[1], pt[1])),
+                                                     __fmul_rn(pt[2], pt[2])));
+                    }
+                }
+                xr[j] = d;
+            }
+            float acc[CPL];
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) acc[q] = bch[q];
+#pragma unroll
+            for (int j = 0; j < XR; ++j) {
+                if (32 * j >= cin) break;
+                const int kend = min(32, cin - 32 * j);
+                for (int kk = 0; kk < kend; ++kk) {
+                    const float d = __shfl_sync(0xffffffffu, xr[j], kk);
+                    const float *wr = s_w + (size_t)(32 * j + kk) * u;
+#pragma unroll
+                    for (int q = 0; q < CPL; ++q) {
+                        const int c = lane + 32 * q;
+                        if (c < u) acc[q] = fmaf(d, wr[c], acc[q]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) {
+                const int c = lane + 32 * q;
+                if (c < u) {
+                    y[((size_t)p * T + t) * u + c] = acc[q];
+                    fs[q] += acc[q];
+                    fq[q] = fmaf(acc[q], acc[q], fq[q]);
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) {
+            ssum[q] += (double)fs[q];
+            ssq[q] += (double)fq[q];
+        }
+    }
+    if (partial != nullptr) {
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) {
+            const int c = lane + 32 * q;
+            if (c < u) {
+                s_red[(warp * 2 + 0) * u + c] = ssum[q];
+                s_red[(warp * 2 + 1) * u + c] = ssq[q];
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * u; i += blockDim.x) {
+            double tot = 0.0;
+            for (int w = 0; w < kPfnWarps; ++w) tot += s_red[w * 2 * u + i];
+            partial[(size_t)blockIdx.x * 2 * u + i] = tot;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kPfnWarps * 32)
+pfn_gen_finish_kernel(const float *__restrict__ y, const float *__restrict__ scale, const float *__restrict__ shift,
+                      int P, int T, int u, int last_layer, const int32_t *__restrict__ num_valid,
+                      float *__restrict__ out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int Pv = num_valid ? min(*num_valid, P) : P;
+    for (int p = blockIdx.x * kPfnWarps + warp; p < P; p += gridDim.x * kPfnWarps) {
+        for (int c = lane; c < u; c += 32) {
+            const float sc = scale[c], sh = shift[c];
+            float m = -INFINITY;
+            if (p < Pv) {
+                for (int t = 0; t < T; ++t) {
+                    const float v = fmaxf(fmaf(y[((size_t)p * T + t) * u + c], sc, sh), 0.f);
+                    m = fmaxf(m, v);
+                    if (!last_layer) out[((size_t)p * T + t) * 2 * u + c] = v;
+                }
+            } else {
+                m = 0.f;   // rows beyond *num_valid are zero
+                if (!last_layer)
+                    for (int t = 0; t < T; ++t) out[((size_t)p * T + t) * 2 * u + c] = 0.f;
+            }
+            if (last_layer) out[(size_t)p * u + c] = m;
+            else
+                for (int t = 0; t < T; ++t) out[((size_t)p * T + t) * 2 * u + u + c] = m;
+        }
+    }
+}
+
+struct PfnGenWs {
+    size_t y, partial, scale, shift, total;
+    int nblocks;
+};
+static void plan_pfn_gen(int P, int T, int u, PfnGenWs *w) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    int nb = ceil_div(P > 0 ? P : 1, kPfnWarps);
+    if (nb > kNumSMs * 4) nb = kNumSMs * 4;
+    w->nblocks = nb;
+    w->y = take((size_t)P * T * u * 4);
+    w->partial = take((size_t)nb * 2 * u * 8);
+    w->scale = take((size_t)u * 4);
+    w->shift = take((size_t)u * 4);
+    w->total = off;
+}
+}  // namespace
+
+extern "C" size_t papc_pfn_layer_workspace_bytes(int P, int T, int units) {
+    if (P < 0 || T <= 0 || units <= 0) return 0;
+    PfnGenWs w;
+    plan_pfn_gen(P, T, units, &w);
+    return w.total;
+}
+
+extern "C" int papc_pfn_layer_f32(const float *x, int decorate, int with_distance, const int32_t *num_voxels,
+                                  const int32_t *coors, int P, int T, int F, float vx, float vy, float x_offset,
+                                  float y_offset, const float *weight, const float *bias, const float *gamma,
+                                  const float *beta, const float *running_mean, const float *running_var,
+                                  int bn_mode, float eps, int units, int last_layer, const int32_t *num_valid,
+                                  float *out, float *batch_mean, float *batch_var, void *workspace,
+                                  size_t workspace_bytes, papc_stream_t stream) {
+    if (P < 0 || T <= 0 || F < 1 || units <= 0) return PAPC_EINVAL;
+    if (bn_mode != PAPC_BN_BATCH && bn_mode != PAPC_BN_RUNNING && bn_mode != PAPC_BN_NONE) return PAPC_EINVAL;
+    if (decorate && F < 3) return PAPC_EINVAL;
+    const int cin = decorate ? F + 5 + (with_distance ? 1 : 0) : F;
+    if (cin > kPfnGenMaxCin || units > 128) return PAPC_EUNSUPPORTED;
+    if (P == 0) return PAPC_OK;
+    if (!x || !weight || !out) return PAPC_EINVAL;
+    if (decorate && (!num_voxels || !coors)) return PAPC_EINVAL;
+    if (bn_mode == PAPC_BN_RUNNING && (!running_mean || !running_var)) return PAPC_EINVAL;
+    PfnGenWs w;
+    plan_pfn_gen(P, T, units, &w);
+    if (!workspace || workspace_bytes < w.total) return PAPC_EWORKSPACE;
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255u) != 0) return PAPC_EINVAL;
+    char *ws = reinterpret_cast<char *>(workspace);
+    float *y = (float *)(ws + w.y);
+    double *partial = (double *)(ws + w.partial);
+    float *scale = (float *)(ws + w.scale), *shift = (float *)(ws + w.shift);
+    cudaStream_t st = as_stream(stream);
+    size_t smem = align_up((size_t)cin * units * 4, 8) + (size_t)kPfnWarps * 2 * units * 8;
+    double *part_arg = (bn_mode == PAPC_BN_BATCH) ? partial : nullptr;
+    const int cpl = ceil_div(units, 32);
+#define PAPC_PFNG_LAUNCH(CPL, DEC)                                                                     \
+    do {                                                                                              \
+        auto kfn = pfn_gen_linear_kernel<CPL, DEC>;                                                   \
+        if (smem > 48 * 1024)                                                                         \
+            PAPC_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        kfn<<<w.nblocks, kPfnWarps * 32, smem, st>>>(x, num_voxels, coors, P, T, F, with_distance, vx, vy, x_offset, \
+                                                     y_offset, weight, bias, cin, units, num_valid, y, part_arg); \
+    } while (0)
+    if (decorate) {
+        if (cpl <= 1) PAPC_PFNG_LAUNCH(1, true);
+        else if (cpl <= 2) PAPC_PFNG_LAUNCH(2, true);
+        else PAPC_PFNG_LAUNCH(4, true);
+    } else {
+        if (cpl <= 1) PAPC_PFNG_LAUNCH(1, false);
+        else if (cpl <= 2) PAPC_PFNG_LAUNCH(2, false);
+        else PAPC_PFNG_LAUNCH(4, false);
+    }
+#undef PAPC_PFNG_LAUNCH
+    PAPC_LAUNCH_CHECK();
+    pfn_bn_kernel<<<1, kPfnBnThreads, 0, st>>>(partial, w.nblocks, P, T, num_valid, gamma, beta, running_mean,
+                                               running_var, bn_mode, eps, units, scale, shift, batch_mean, batch_var);
+    PAPC_LAUNCH_CHECK();
+    pfn_gen_finish_kernel<<<w.nblocks, kPfnWarps * 32, 0, st>>>(y, scale, shift, P, T, units, last_layer, num_valid, out);
+    PAPC_LAUNCH_CHECK();
+    return PAPC_OK;
+}
+
+namespace {
 struct PfnWs {
     size_t pmax, pmin, partial, scale, shift, total;
     int nblocks;

@@ -884,9 +884,12 @@ chain_kernel(const __grid_constant__ ChainArgs a) {
                 const uint32_t s = it % geo.nst;
                 const int k0 = cc * 64 + u * 8;
                 float o[kRPT][8];
+                float4 fo[8];   // all eight loads in flight before the first FMA: one exposed shared-memory latency, not eight
+#pragma unroll
+                for (int qq = 0; qq < 8; ++qq) fo[qq] = lds128f(sm + SmemLayout::fold + 16 * ((k0 + qq) & 127));
 #pragma unroll
                 for (int qq = 0; qq < 8; ++qq) {
-                    const float4 f = lds128f(sm + SmemLayout::fold + 16 * ((k0 + qq) & 127));
+                    const float4 f = fo[qq];
 #pragma unroll
                     for (int j = 0; j < kRPT; ++j) {
                         const float4 p = p_cur[j];

@@ -752,8 +752,11 @@ static int layer_forward(const papc_group_source *src, const float *x, const flo
             else if (!gather && a.in_scale != nullptr && cin % 8 == 0) {
                 // step-wise API: no bound on the activations is known, so TF32 -- unless the caller
                 // vouches for |relu(in_scale*x+in_shift)| < 2^15 (benchmarks: PAPC_TT_PREC=f16)
+#ifdef PAPC_TRIAGE   // benchmarks of the fp16 split through the step-wise API; no bound on the activations is
+                     // checked, so this switch exists in triage builds only
                 const char *e = getenv("PAPC_TT_PREC");
                 if (e && e[0] == 'f') o.prec = tt::PREC_F16;
+#endif
             }
             const int r = try_tt(a, gather, K, bn, o, st);
             if (r < 0) return r;
@@ -1363,6 +1366,21 @@ static int plan_pw(int64_t M, int32_t ld_x, const papc_mlp *mlp, PwPlan *p) {
     return PAPC_OK;
 }
 }  // namespace
+
+extern "C" int papc_bn_relu_apply_f32(const float *y, const float *scale, const float *shift, int64_t M,
+                                      int32_t cout, float *out, papc_stream_t stream) {
+    if (M < 0 || cout <= 0) return PAPC_EINVAL;
+    if (M == 0) return PAPC_OK;
+    if (!y || !scale || !shift || !out) return PAPC_EINVAL;
+    const size_t total = (size_t)M * cout;
+    size_t blocks = (total + 255) / 256;
+    if (blocks > (size_t)kNumSMs * 16) blocks = (size_t)kNumSMs * 16;
+    cudaStream_t st = as_stream(stream);
+    ProfScope prof(st, "bn_relu_apply", M, 0, cout, 0.0, 8.0 * (double)total);
+    bn_relu_apply_kernel<<<(unsigned)blocks, 256, 0, st>>>(y, scale, shift, total, cout, out);
+    PAPC_LAUNCH_CHECK();
+    return PAPC_OK;
+}
 
 extern "C" size_t papc_pointwise_mlp_workspace_bytes(int64_t M, int32_t ld_x, const papc_mlp *mlp) {
     PwPlan p;

@@ -47,9 +47,11 @@ def all_reduce_sums_(sums, group=None):
     return sums
 
 
-def set_sync_bn(module, group):
-    """Enable SyncBN over the batch shards on every SetAbstraction layer under ``module``."""
+def set_sync_bn(module, group=None, enabled=True):
+    """Enable (or disable) SyncBN over the batch shards on every SetAbstraction / FeaturePropagation layer
+    and model head under ``module``.  ``group=None`` means the default (world) process group."""
     for m in module.modules():
         if hasattr(m, "sync_bn_group"):
-            m.sync_bn_group = group
+            m.sync_bn = bool(enabled)
+            m.sync_bn_group = group if enabled else None
     return module

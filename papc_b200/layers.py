@@ -48,15 +48,21 @@ def square_distance(src, dst):
     return out
 
 
-def index_points(points, idx):
+def index_points(points, idx, strict=False):
     """layers.py:43-62.  points [B,N,C]; idx [B,S] or [B,S,K] (float32 or integer, cast to int64
-    as :59 does) -> [B,S,C] / [B,S,K,C]."""
+    as :59 does) -> [B,S,C] / [B,S,K,C].
+
+    Out-of-range indices: the reference raises IndexError (NumPy fancy indexing, :58); the kernel
+    clamps them to [0, N-1] so that it never reads out of bounds.  ``strict=True`` restores the
+    reference behaviour at the price of a device synchronisation."""
     L.require_cuda(points, idx)
     points = L.f32c(points)
     B, N, Cc = points.shape
     idx64 = idx.to(torch.int64).contiguous()
     if idx64.shape[0] != B:
         raise ValueError("index_points: batch mismatch")
+    if strict and idx64.numel() and (int(idx64.min()) < -N or int(idx64.max()) >= N):
+        raise IndexError(f"index_points: index out of range for {N} points")
     M = idx64.numel() // max(B, 1)
     out = torch.empty(tuple(idx64.shape) + (Cc,), dtype=torch.float32, device=points.device)
     L.check(L.lib().papc_gather_f32(L.ptr(points), L.ptr(idx64), B, N, Cc, M, L.ptr(out),
@@ -122,7 +128,12 @@ def _ball_query(radius, nsample, xyz, new_xyz, idx_dtype, check_empty=False):
 
 
 def query_ball_point(radius, nsample, xyz, new_xyz, check_empty=False):
-    """layers.py:98-126.  xyz [B,N,3], new_xyz [B,S,3] -> int64 [B,S,nsample]."""
+    """layers.py:98-126.  xyz [B,N,3], new_xyz [B,S,3] -> int64 [B,S,nsample].
+
+    A query point with no neighbour inside the radius yields index N in every slot (what the
+    reference's sort leaves there, :115-117); the reference then fails with IndexError in
+    ``index_points``.  ``check_empty=True`` reproduces that error (one device synchronisation);
+    the default keeps the call asynchronous and downstream gathers clamp N to N-1."""
     L.require_cuda(xyz, new_xyz)
     return _ball_query(radius, nsample, L.f32c(xyz), L.f32c(new_xyz), torch.int64, check_empty)
 
@@ -189,15 +200,21 @@ def _sample(xyz, ready, npoint, start_idx, queries):
     """FPS + one ball query per (radius, nsample) in ``queries`` -> (new_xyz, [idx int32...], event
     recorded right after the FPS).  Runs on the side stream when ``ready`` (the producer's event) is set.
 
-    Buffers allocated under the side stream come from that stream's pool of the caching allocator and
-    are consumed on the main stream.  No ``record_stream`` is needed (and it is expensive: deferred
-    frees): a freed block can only be handed to a LATER side-stream allocation, whose kernels wait for
-    a later layer's ``ready`` event, and that event is recorded on the main stream after every
-    main-stream consumer of the block was enqueued."""
+    Stream safety.  The side stream first waits for an event recorded on the main stream at entry, so
+    (a) a caller-supplied ``start_idx`` (or any other main-stream tensor) is complete before the side
+    stream reads it, and (b) every buffer the side stream's allocator pool hands out again was last
+    used by main-stream work enqueued before this point.  The buffers allocated here are consumed by
+    main-stream kernels after this call returns, so they are ``record_stream``-ed to the main stream:
+    the caching allocator then defers their reuse until that work has run (three or more chained
+    sampled layers, or repeated calls, would otherwise let a later side-stream allocation overwrite
+    indices an earlier layer's MLP is still reading)."""
     dev = xyz.device
     main = torch.cuda.current_stream(dev)
     if ready is not None and OVERLAP_SAMPLING:
         side = _side_stream(dev)
+        entry = torch.cuda.Event()
+        entry.record(main)
+        side.wait_event(entry)
         side.wait_event(ready)
         with torch.cuda.stream(side):
             _, new_xyz = farthest_point_sample_idx(xyz, npoint, start_idx, return_xyz=True)
@@ -207,6 +224,9 @@ def _sample(xyz, ready, npoint, start_idx, queries):
             done = torch.cuda.Event()
             done.record(side)
         main.wait_event(done)
+        if not torch.cuda.is_current_stream_capturing():
+            for t in [new_xyz] + idxs:
+                t.record_stream(main)
         return new_xyz, idxs, ev
     _, new_xyz = farthest_point_sample_idx(xyz, npoint, start_idx, return_xyz=True)
     ev = torch.cuda.Event()
@@ -292,8 +312,8 @@ class _MlpRunner:
                 stats.append((bm, bv))
         return mlp, keep, stats
 
-    def run(self, src, keep_src, cin, B, S, bn_mode, device, update_running=False, sync_group=None):
-        """-> [B,S,cout] channels-last."""
+    def run(self, src, keep_src, cin, B, S, bn_mode, device, update_running=False, sync=(False, None)):
+        """-> [B,S,cout] channels-last.  ``sync`` = (enabled, process group) from ``_SAMixin._sync_group``."""
         if bn_mode not in ("batch", "running"):
             raise ValueError("bn_mode must be 'batch' or 'running'")
         if any(c.weight.device != device for c in self.convs):
@@ -302,9 +322,8 @@ class _MlpRunner:
         out = torch.empty((B, S, cout), dtype=torch.float32, device=device)
         lib = L.lib()
         st = L.stream_ptr(device)
-        world = dist.get_world_size(sync_group) if (sync_group is not None and dist.is_initialized()) else 1
-        if bn_mode == "batch" and world > 1:
-            self._run_stepwise_synced(src, cin, B, S, out, device, sync_group, update_running)
+        if bn_mode == "batch" and sync[0]:
+            self._run_stepwise_synced(src, cin, B, S, out, device, sync[1], update_running)
             return out
         mlp, keep, stats = self._mlp_struct(cin, bn_mode, device, update_running)
         wsb = lib.papc_sa_mlp_workspace_bytes(C.byref(src), C.byref(mlp))
@@ -407,7 +426,19 @@ class _SAMixin(torch.nn.Module):
 
     bn_mode = "batch"
     update_running_stats = False
-    sync_bn_group = None  # a torch.distributed process group -> SyncBN over the batch shards
+    # SyncBN over the batch shards: ``sync_bn = True`` all-reduces the per-layer statistics over
+    # ``sync_bn_group`` (None = the default / world group).  papc_b200.dist.set_sync_bn sets both.
+    sync_bn = False
+    sync_bn_group = None
+
+    def _sync_group(self):
+        """(enabled, group) -- enabled only when torch.distributed runs with more than one rank."""
+        if not (self.sync_bn or self.sync_bn_group is not None):
+            return False, None
+        if not dist.is_initialized():
+            return False, None
+        group = self.sync_bn_group if self.sync_bn_group is not None else dist.group.WORLD
+        return dist.get_world_size(group) > 1, group
 
     def _holders(self):
         raise NotImplementedError
@@ -466,7 +497,7 @@ class PointNetSetAbstraction(_SAMixin):
             src = _make_src(xyz, new_xyz, feats, idx, B, N, S, self.nsample, L.XYZ_FIRST)
             keep = (xyz, feats, new_xyz, idx)
         out = _MlpRunner(self.mlp_convs, self.mlp_bns).run(                # :214-219
-            src, keep, 3 + D, B, S, self.bn_mode, dev, self.update_running_stats, self.sync_bn_group)
+            src, keep, 3 + D, B, S, self.bn_mode, dev, self.update_running_stats, self._sync_group())
         out_xyz = new_xyz.transpose(1, 2)
         if not self.group_all:
             _tag_ready(out_xyz, ev)
@@ -519,7 +550,7 @@ class PointNetSetAbstractionMsg(_SAMixin):
             src = _make_src(xyz, new_xyz, feats, idx, B, N, S, K, L.FEATS_FIRST)     # :263-267
             outs.append(_MlpRunner(self.conv_blocks[i], self.bn_blocks[i]).run(     # :271-276
                 src, (xyz, feats, new_xyz, idx), 3 + D, B, S, self.bn_mode, dev,
-                self.update_running_stats, self.sync_bn_group))
+                self.update_running_stats, self._sync_group()))
         new_points_concat = torch.cat(outs, dim=2)                                   # :280 (channels-last)
         return _tag_ready(new_xyz.transpose(1, 2), ev), new_points_concat.transpose(1, 2)
 
@@ -535,6 +566,33 @@ class Conv1D(Conv2D):
 
 class BatchNorm1D(BatchNorm2D):
     """Parameter holder mirroring ``paddle.nn.BatchNorm1D(c)`` (epsilon 1e-5, momentum 0.9)."""
+
+
+class Conv1DLayer(torch.nn.Module):
+    """REGISTERED form of ``Conv1D`` (weight / bias are parameters, so they appear in ``parameters()`` and
+    ``state_dict()`` under Paddle's names) for sublayers the reference assigns as attributes, e.g. the
+    segmentation head's ``conv1`` / ``conv2`` (segment/pointnet2/pointnet2.py:21-24)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=1):
+        super().__init__()
+        h = Conv1D(in_channels, out_channels, kernel_size)
+        self.weight = torch.nn.Parameter(h.weight, requires_grad=False)
+        self.bias = torch.nn.Parameter(h.bias, requires_grad=False)
+
+
+class BatchNorm1DLayer(torch.nn.Module):
+    """REGISTERED form of ``BatchNorm1D``: weight / bias parameters, ``_mean`` / ``_variance`` buffers
+    (Paddle's state_dict keys), so running statistics can be saved, loaded and mapped from a reference
+    checkpoint."""
+
+    def __init__(self, num_features, momentum=0.9, epsilon=1e-5):
+        super().__init__()
+        self.weight = torch.nn.Parameter(torch.ones(num_features), requires_grad=False)
+        self.bias = torch.nn.Parameter(torch.zeros(num_features), requires_grad=False)
+        self.register_buffer("_mean", torch.zeros(num_features))
+        self.register_buffer("_variance", torch.ones(num_features))
+        self._momentum = momentum
+        self._epsilon = epsilon
 
 
 def feature_interpolate(xyz1, xyz2, points1, points2, pad_to=8):
@@ -557,7 +615,51 @@ def feature_interpolate(xyz1, xyz2, points1, points2, pad_to=8):
     return out, D1 + D2
 
 
-def pointwise_mlp_rows(rows, cin, convs, bns, bn_mode="batch", update_running=False):
+def _pointwise_mlp_rows_synced(rows, cin, convs, bns, group, update_running):
+    """Batch-sharded form of ``pointwise_mlp_rows`` with BatchNorm statistics summed over the ranks of
+    ``group``: step-wise C ABI, one all-reduce of [2,cout] fp64 sums per layer."""
+    lib = L.lib()
+    dev = rows.device
+    st = L.stream_ptr(dev)
+    M, ld = rows.shape
+    total = float(M) * dist.get_world_size(group)   # equal shards (papc_b200.dist.shard_range)
+    prows = lib.papc_mlp_stats_partial_rows(M)
+    x, c_in = rows, ld
+    scale = shift = None
+    stats = []
+    for l, (conv, bn) in enumerate(zip(convs, bns)):
+        w = L.f32c(conv.weight.reshape(conv.weight.shape[0], -1))
+        if l == 0 and ld != cin:   # the rows are zero-padded to ld columns: pad the first weight alike
+            w = torch.nn.functional.pad(w, (0, ld - cin)).contiguous()
+        cout = w.shape[0]
+        y = torch.empty((M, cout), dtype=torch.float32, device=dev)
+        partial = torch.empty((prows, 2, cout), dtype=torch.float64, device=dev)
+        bias = L.f32c(conv.bias) if conv.bias is not None else None
+        lwsb = lib.papc_mlp_layer_workspace_bytes(c_in, cout)
+        lws = _ws(lwsb, dev)
+        L.check(lib.papc_mlp_layer_forward_f32(None, L.ptr(x), L.ptr(scale), L.ptr(shift), M, c_in, cout, 1,
+                                               L.ptr(w), L.ptr(bias), L.ptr(y), None, None, L.ptr(partial),
+                                               L.ptr(lws), lwsb, st), "mlp_layer_forward")
+        sums = torch.empty((2, cout), dtype=torch.float64, device=dev)
+        L.check(lib.papc_mlp_stats_reduce_f64(L.ptr(partial), prows, cout, L.ptr(sums), st), "mlp_stats_reduce")
+        dist.all_reduce(sums, group=group)
+        scale = torch.empty((cout,), dtype=torch.float32, device=dev)
+        shift = torch.empty((cout,), dtype=torch.float32, device=dev)
+        bm = torch.empty((cout,), dtype=torch.float32, device=dev)
+        bv = torch.empty((cout,), dtype=torch.float32, device=dev)
+        L.check(lib.papc_bn_scale_shift_f32(L.ptr(sums), total, L.ptr(L.f32c(bn.weight)), L.ptr(L.f32c(bn.bias)),
+                                            float(bn._epsilon), cout, L.ptr(scale), L.ptr(shift), L.ptr(bm),
+                                            L.ptr(bv), st), "bn_scale_shift")
+        stats.append((bm, bv))
+        x, c_in = y, cout
+    out = torch.empty_like(x)
+    L.check(lib.papc_bn_relu_apply_f32(L.ptr(x), L.ptr(scale), L.ptr(shift), M, c_in, L.ptr(out), st), "bn_relu_apply")
+    if update_running:
+        _MlpRunner(convs, bns)._update_running(stats)
+    return out
+
+
+def pointwise_mlp_rows(rows, cin, convs, bns, bn_mode="batch", update_running=False, sync=(False, None)):
     """(1x1 conv -> BatchNorm -> ReLU) x len(convs) over channels-last rows [M, ld] (ld >= cin, ld % 4 == 0,
     columns >= cin ignored) -> [M, cout], on the tcgen05 layer kernels (``papc_pointwise_mlp_f32``).
     ``bn_mode`` 'batch' normalises with the statistics of the M rows, 'running' with the holders'
@@ -569,6 +671,8 @@ def pointwise_mlp_rows(rows, cin, convs, bns, bn_mode="batch", update_running=Fa
     dev = rows.device
     if any(c.weight.device != dev for c in convs):
         raise L.PapcError("layer parameters are not on the input's device; call .to(device)")
+    if bn_mode == "batch" and sync[0]:
+        return _pointwise_mlp_rows_synced(rows, cin, convs, bns, sync[1], update_running)
     runner = _MlpRunner(convs, bns)
     mlp, keep, stats = runner._mlp_struct(cin, bn_mode, dev, update_running)
     lib = L.lib()
@@ -618,5 +722,5 @@ class PointNetFeaturePropagation(_SAMixin):
         if cin != self.in_channel:
             raise ValueError(f"in_channel={self.in_channel} but the concatenated input has {cin} channels")
         out = pointwise_mlp_rows(rows, cin, self.mlp_convs, self.mlp_bns, self.bn_mode,   # :332-335
-                                 update_running=self.update_running_stats)
+                                 update_running=self.update_running_stats, sync=self._sync_group())
         return out.reshape(B, N, -1).transpose(1, 2)

@@ -27,7 +27,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib as L
-from .layers import (BatchNorm1D, Conv1D, PointNetFeaturePropagation, PointNetSetAbstraction,
+from .layers import (BatchNorm1DLayer, Conv1DLayer, PointNetFeaturePropagation, PointNetSetAbstraction,
                      PointNetSetAbstractionMsg, _SAMixin, pointwise_mlp_rows)
 
 
@@ -135,19 +135,22 @@ class _SegHead(_SAMixin):
     library's parameter holders (they feed the pointwise-MLP kernel); bn1 follows train()/eval()."""
 
     def _make_head(self, num_parts):
-        self.conv1 = Conv1D(128, 128, 1)
-        self.bn1 = BatchNorm1D(128)
+        # registered sublayers, as in the reference (:21-24): their tensors are in state_dict() under
+        # Paddle's keys (conv1.weight, bn1._mean, ...) and move with .to() like any module
+        self.conv1 = Conv1DLayer(128, 128, 1)
+        self.bn1 = BatchNorm1DLayer(128)
         self.drop1 = torch.nn.Dropout(0.5)
-        self.conv2 = Conv1D(128, num_parts, 1)
+        self.conv2 = Conv1DLayer(128, num_parts, 1)
 
     def _holders(self):
-        return [self.conv1, self.bn1, self.conv2]
+        return []
 
     def _head(self, l0_points):
         B, C, N = l0_points.shape
         rows = L.f32c(l0_points.transpose(1, 2)).reshape(B * N, C)          # fp1's own buffer, no copy
         feat = pointwise_mlp_rows(rows, C, [self.conv1], [self.bn1],       # :45 relu(bn1(conv1(.)))
-                                  "batch" if self.training else "running", update_running=self.training)
+                                  "batch" if self.training else "running", update_running=self.training,
+                                  sync=self._sync_group())
         x = self.drop1(feat)                                                # :46
         w2 = self.conv2.weight.reshape(self.conv2.weight.shape[0], -1)
         x = torch.addmm(self.conv2.bias, x, w2.t())                         # :47

@@ -150,22 +150,26 @@ class PillarFeatureNet(torch.nn.Module):
         super().__init__()
         self.name = "PillarFeatureNet"
         assert len(num_filters) > 0
-        if with_distance:
-            raise NotImplementedError("with_distance=True is not on the accelerated path "
-                                      "(the reference config uses False, yaml:57)")
-        if len(num_filters) != 1:
-            raise NotImplementedError("only a single (last) PFNLayer is accelerated "
-                                      "(the reference config uses num_filters=[64], yaml:56)")
         num_input_features += 5
+        if with_distance:
+            num_input_features += 1
         self._with_distance = with_distance
         num_filters = [num_input_features] + list(num_filters)
-        self.pfn_layers = torch.nn.ModuleList(
-            [PFNLayer(num_filters[0], num_filters[1], use_norm, last_layer=True)])
+        layers_ = []
+        for i in range(len(num_filters) - 1):                                      # :62-70
+            last_layer = not (i < len(num_filters) - 2)
+            layers_.append(PFNLayer(num_filters[i], num_filters[i + 1], use_norm, last_layer=last_layer))
+        self.pfn_layers = torch.nn.ModuleList(layers_)
         self.vx = voxel_size[0]
         self.vy = voxel_size[1]
         self.x_offset = self.vx / 2 + pc_range[0]
         self.y_offset = self.vy / 2 + pc_range[1]
         self.update_running_stats = False
+
+    def _bn_mode(self, pfn):
+        if not pfn.use_norm:
+            return L.BN_NONE
+        return L.BN_BATCH if self.training else L.BN_RUNNING
 
     def forward(self, features, num_voxels, coors, num_valid=None):
         L.require_cuda(features, num_voxels, coors)
@@ -175,35 +179,60 @@ class PillarFeatureNet(torch.nn.Module):
         coors = coors.to(torch.int32).contiguous()
         if coors.shape != (P, 4):
             raise ValueError("coors must be [P,4] (batch, z, y, x)")
-        pfn = self.pfn_layers[0]
-        if pfn.weight.shape[0] != F + 5:
-            raise ValueError(f"PFN expects {pfn.weight.shape[0] - 5} point features, got {F}")
+        extra = 5 + (1 if self._with_distance else 0)
+        if self.pfn_layers[0].weight.shape[0] != F + extra:
+            raise ValueError(f"PFN expects {self.pfn_layers[0].weight.shape[0] - extra} point features, got {F}")
         dev = features.device
-        cout = pfn.units
-        out = torch.empty((P, cout), dtype=torch.float32, device=dev)
-        if pfn.use_norm:
-            mode = L.BN_BATCH if self.training else L.BN_RUNNING
-        else:
-            mode = L.BN_NONE
-        want = self.update_running_stats and mode == L.BN_BATCH
-        bm = torch.empty((cout,), dtype=torch.float32, device=dev) if want else None
-        bv = torch.empty((cout,), dtype=torch.float32, device=dev) if want else None
         lib = L.lib()
-        wsb = lib.papc_pfn_workspace_bytes(P, cout)
-        ws = _ws(wsb, dev)
         f32 = np.float32
-        L.check(lib.papc_pfn_f32(L.ptr(features), L.ptr(num_voxels), L.ptr(coors), P, T, F,
-                                 float(f32(self.vx)), float(f32(self.vy)), float(f32(self.x_offset)),
-                                 float(f32(self.y_offset)), L.ptr(L.f32c(pfn.weight)),
-                                 L.ptr(L.f32c(pfn.bias)) if pfn.bias is not None else None,
-                                 L.ptr(L.f32c(pfn.bn_weight)), L.ptr(L.f32c(pfn.bn_bias)),
-                                 L.ptr(pfn._mean), L.ptr(pfn._variance), mode, float(pfn.epsilon), cout,
-                                 L.ptr(num_valid), L.ptr(out), L.ptr(bm), L.ptr(bv), L.ptr(ws), wsb,
-                                 L.stream_ptr(dev)), "PillarFeatureNet")
-        if want:
-            pfn._mean.mul_(pfn.momentum).add_(bm, alpha=1 - pfn.momentum)
-            pfn._variance.mul_(pfn.momentum).add_(bv, alpha=1 - pfn.momentum)
-        return out.squeeze()                                                  # :108
+        geom = (float(f32(self.vx)), float(f32(self.vy)), float(f32(self.x_offset)), float(f32(self.y_offset)))
+        if len(self.pfn_layers) == 1 and not self._with_distance:
+            # the yaml shape (num_filters=[64]): decoration + Linear + BatchNorm + ReLU + max in one fused pass
+            pfn = self.pfn_layers[0]
+            cout = pfn.units
+            out = torch.empty((P, cout), dtype=torch.float32, device=dev)
+            mode = self._bn_mode(pfn)
+            want = self.update_running_stats and mode == L.BN_BATCH
+            bm = torch.empty((cout,), dtype=torch.float32, device=dev) if want else None
+            bv = torch.empty((cout,), dtype=torch.float32, device=dev) if want else None
+            wsb = lib.papc_pfn_workspace_bytes(P, cout)
+            ws = _ws(wsb, dev)
+            L.check(lib.papc_pfn_f32(L.ptr(features), L.ptr(num_voxels), L.ptr(coors), P, T, F, *geom,
+                                     L.ptr(L.f32c(pfn.weight)),
+                                     L.ptr(L.f32c(pfn.bias)) if pfn.bias is not None else None,
+                                     L.ptr(L.f32c(pfn.bn_weight)), L.ptr(L.f32c(pfn.bn_bias)),
+                                     L.ptr(pfn._mean), L.ptr(pfn._variance), mode, float(pfn.epsilon), cout,
+                                     L.ptr(num_valid), L.ptr(out), L.ptr(bm), L.ptr(bv), L.ptr(ws), wsb,
+                                     L.stream_ptr(dev)), "PillarFeatureNet")
+            if want:
+                pfn._mean.mul_(pfn.momentum).add_(bm, alpha=1 - pfn.momentum)
+                pfn._variance.mul_(pfn.momentum).add_(bv, alpha=1 - pfn.momentum)
+            return out.squeeze()                                                  # :108
+        # general chain (the reference's default num_filters=(64,128), with_distance, ...): one generic
+        # PFNLayer launch group per layer, the intermediate [P,T,2u] tensors materialised as in the reference
+        x, cin, decorate = features, F, 1
+        for pfn in self.pfn_layers:                                               # :105-106
+            u = pfn.units
+            last = 1 if pfn.last_vfe else 0
+            out = torch.empty((P, u) if last else (P, T, 2 * u), dtype=torch.float32, device=dev)
+            mode = self._bn_mode(pfn)
+            want = self.update_running_stats and mode == L.BN_BATCH
+            bm = torch.empty((u,), dtype=torch.float32, device=dev) if want else None
+            bv = torch.empty((u,), dtype=torch.float32, device=dev) if want else None
+            wsb = lib.papc_pfn_layer_workspace_bytes(P, T, u)
+            ws = _ws(wsb, dev)
+            L.check(lib.papc_pfn_layer_f32(L.ptr(x), decorate, 1 if self._with_distance else 0, L.ptr(num_voxels),
+                                           L.ptr(coors), P, T, cin, *geom, L.ptr(L.f32c(pfn.weight)),
+                                           L.ptr(L.f32c(pfn.bias)) if pfn.bias is not None else None,
+                                           L.ptr(L.f32c(pfn.bn_weight)), L.ptr(L.f32c(pfn.bn_bias)),
+                                           L.ptr(pfn._mean), L.ptr(pfn._variance), mode, float(pfn.epsilon), u, last,
+                                           L.ptr(num_valid), L.ptr(out), L.ptr(bm), L.ptr(bv), L.ptr(ws), wsb,
+                                           L.stream_ptr(dev)), "PFNLayer")
+            if want:
+                pfn._mean.mul_(pfn.momentum).add_(bm, alpha=1 - pfn.momentum)
+                pfn._variance.mul_(pfn.momentum).add_(bv, alpha=1 - pfn.momentum)
+            x, cin, decorate = out, 2 * u, 0
+        return x.squeeze()                                                        # :108
 
 
 class PointPillarsScatter(torch.nn.Module):

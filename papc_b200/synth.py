@@ -22,7 +22,7 @@ def clouds(B, N, seed=0):
     pc = rng.uniform(-1.0, 1.0, (B, N, 3)).astype(np.float32)
     pc = pc - pc.mean(axis=1, keepdims=True)
     m = np.sqrt((pc ** 2).sum(-1)).max(axis=1)
-    pc = pc / m[:, None, None]
+    pc = pc / np.where(m > 0, m, 1.0).astype(np.float32)[:, None, None]   # N = 1: the single point is the centroid
     return np.ascontiguousarray(pc.transpose(0, 2, 1)).astype(np.float32)
 
 

@@ -63,17 +63,18 @@ def _randomise_and_copy(prod, orc, seed):
                     ob.weight, ob.bias = b.weight.detach().cpu().numpy(), b.bias.detach().cpu().numpy()
                     ob._mean, ob._variance = b._mean.cpu().numpy(), b._variance.cpu().numpy()
     else:
-        for cname in ("conv1", "conv2"):
-            conv, oconv = getattr(prod, cname), getattr(orc, cname)
-            cout = conv.weight.shape[0]
-            conv.bias = u(cout, -0.1, 0.1)
-            oconv.weight = conv.weight.reshape(cout, -1, 1, 1).cpu().numpy()
-            oconv.bias = conv.bias.cpu().numpy()
-        b, ob = prod.bn1, orc.bn1
-        b.weight, b.bias = u(128, 0.5, 1.5), u(128, -0.2, 0.2)
-        b._mean, b._variance = u(128, -0.1, 0.1), u(128, 0.5, 1.5)
-        ob.weight, ob.bias = b.weight.cpu().numpy(), b.bias.cpu().numpy()
-        ob._mean, ob._variance = b._mean.cpu().numpy(), b._variance.cpu().numpy()
+        with torch.no_grad():   # registered sublayers (as in the reference): parameters / buffers, set in place
+            for cname in ("conv1", "conv2"):
+                conv, oconv = getattr(prod, cname), getattr(orc, cname)
+                cout = conv.weight.shape[0]
+                conv.bias.copy_(u(cout, -0.1, 0.1))
+                oconv.weight = conv.weight.detach().reshape(cout, -1, 1, 1).cpu().numpy()
+                oconv.bias = conv.bias.detach().cpu().numpy()
+            b, ob = prod.bn1, orc.bn1
+            b.weight.copy_(u(128, 0.5, 1.5)); b.bias.copy_(u(128, -0.2, 0.2))
+            b._mean.copy_(u(128, -0.1, 0.1)); b._variance.copy_(u(128, 0.5, 1.5))
+            ob.weight, ob.bias = b.weight.detach().cpu().numpy(), b.bias.detach().cpu().numpy()
+            ob._mean, ob._variance = b._mean.cpu().numpy(), b._variance.cpu().numpy()
 
 
 def _inputs(B, N, normal_channel, seed):

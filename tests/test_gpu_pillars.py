@@ -125,6 +125,57 @@ def test_pfn_vs_oracle(mode):
     np.testing.assert_allclose(out.cpu().numpy(), exp, **TOL)
 
 
+@pytest.mark.parametrize("tag,filters,dist", [("one", (64,), False), ("two", (32, 64), False), ("dist", (16,), True)])
+def test_pfn_vs_reference_executed_classes(tag, filters, dist):
+    """PillarFeatureNet against the outputs of the REFERENCE'S OWN classes (tests/golden/pillars_ref.npz, made by
+    tests/golden/make_golden_pillars.py): single last layer, two layers (max-repeat-concat, pillars.py:36-41)
+    and with_distance (:92-94)."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "pillars_ref.npz"))
+    net = pillars.PillarFeatureNet(4, True, filters, dist, synth.KITTI_VOXEL_SIZE, synth.KITTI_PC_RANGE)
+    for i, pfn in enumerate(net.pfn_layers):
+        pfn.weight.data = torch.from_numpy(g[f"{tag}_w{i}"])
+        pfn.bn_weight.data = torch.from_numpy(g[f"{tag}_gamma{i}"])
+        pfn.bn_bias.data = torch.from_numpy(g[f"{tag}_beta{i}"])
+    net.to(DEV).train()
+    out = net(_cu(g["features"]), _cu(g["num_voxels"]), _cu(g["coors"]))
+    assert tuple(out.shape) == g[f"{tag}_out"].shape
+    np.testing.assert_allclose(out.cpu().numpy(), g[f"{tag}_out"], **TOL)
+
+
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_pfn_default_constructor_two_layers_vs_oracle(mode):
+    """The reference's DEFAULT constructor num_filters=(64,128) (pillars.py:47) at a KITTI-sized frame: 9 -> 32
+    (non-last, concat to 64) -> 128, batch statistics and running statistics, incl. the running-stat update."""
+    pts = synth.lidar_frame(6000, 7)
+    v, c, n = capi.points_to_voxel(pts, synth.KITTI_VOXEL_SIZE, synth.KITTI_PC_RANGE, 100, True, 12000)
+    coors = pillars_np.merge_coordinates([c])
+    rng = np.random.default_rng(17)
+    gpu = pillars.PillarFeatureNet(voxel_size=synth.KITTI_VOXEL_SIZE, pc_range=synth.KITTI_PC_RANGE)
+    ref = pillars_np.PillarFeatureNet(voxel_size=synth.KITTI_VOXEL_SIZE, pc_range=synth.KITTI_PC_RANGE)
+    assert [p.units for p in gpu.pfn_layers] == [32, 128] and not gpu.pfn_layers[0].last_vfe
+    for gp, rp in zip(gpu.pfn_layers, ref.pfn_layers):
+        w = (rng.standard_normal(tuple(gp.weight.shape)) / 3.0).astype(np.float32)
+        gam = rng.uniform(0.5, 1.5, gp.units).astype(np.float32); gam[::7] *= -1
+        bet = rng.uniform(-0.2, 0.2, gp.units).astype(np.float32)
+        gp.weight.data, gp.bn_weight.data, gp.bn_bias.data = torch.from_numpy(w), torch.from_numpy(gam), torch.from_numpy(bet)
+        rp.weight, rp.gamma, rp.beta = w, gam, bet
+        if mode == "eval":
+            m = rng.uniform(-1, 1, gp.units).astype(np.float32); var = rng.uniform(5, 40, gp.units).astype(np.float32)
+            gp._mean.copy_(torch.from_numpy(m)); gp._variance.copy_(torch.from_numpy(var))
+            rp._mean, rp._variance, rp.training = m, var, False
+    gpu.to(DEV)
+    gpu.train(mode == "train")
+    gpu.update_running_stats = True
+    out = gpu(_cu(v), _cu(n), _cu(coors))
+    exp = ref(v, n, coors)
+    assert tuple(out.shape) == exp.shape == (v.shape[0], 128)
+    np.testing.assert_allclose(out.cpu().numpy(), exp, rtol=1e-5, atol=2e-5)
+    if mode == "train":
+        for gp, rp in zip(gpu.pfn_layers, ref.pfn_layers):
+            np.testing.assert_allclose(gp._mean.cpu().numpy(), rp._mean, rtol=1e-4, atol=1e-5)
+            np.testing.assert_allclose(gp._variance.cpu().numpy(), rp._variance, rtol=1e-4, atol=1e-5)
+
+
 def test_scatter_bit_exact_and_fused_device_path():
     frames = [synth.lidar_frame(20000, 0), synth.lidar_frame(20000, 5, shuffle=True)]
     vox = [capi.points_to_voxel(f, synth.KITTI_VOXEL_SIZE, synth.KITTI_PC_RANGE, 100, True, 12000) for f in frames]

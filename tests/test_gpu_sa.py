@@ -291,6 +291,32 @@ def test_sampling_overlap_is_transparent(monkeypatch):
     assert torch.equal(outs[True], outs[False])
 
 
+def test_sampling_overlap_three_sampled_layers(monkeypatch):
+    """Three consecutive SAMPLED layers (the shipped models have two) plus a caller-produced start_idx: the
+    side stream's buffers must not be recycled while an earlier layer's MLP still reads them.
+    Overlap on == off, bit for bit, over repeated calls."""
+    B, N = 4, 1024
+    xyz = _cu(synth.clouds(B, N, seed=11))
+    cfgs = [(512, 0.2, 32, 3, [32, 32, 64]), (256, 0.3, 32, 64 + 3, [64, 64, 64]), (64, 0.5, 32, 64 + 3, [64, 64, 128])]
+    sas = []
+    for i, c in enumerate(cfgs):
+        sa = layers.PointNetSetAbstraction(c[0], c[1], c[2], c[3], c[4], False).to(DEV)
+        from papc_b200 import sa_stack
+        sa_stack.load_conv_bn(sa.mlp_convs, sa.mlp_bns, synth.mlp_params(c[3], c[4], seed=20 + i))
+        sas.append(sa)
+    outs = {}
+    for flag in (True, False):
+        monkeypatch.setattr(layers, "OVERLAP_SAMPLING", flag)
+        for rep in range(4):
+            st = (torch.arange(B, device=DEV) * 7 + rep * 0) % N       # produced on the main stream right here
+            x, p = xyz, None
+            for sa in sas:
+                x, p = sa(x, p, start_idx=st if sa is sas[0] else torch.zeros(B, dtype=torch.int64, device=DEV))
+        torch.cuda.synchronize()
+        outs[flag] = p.clone()
+    assert torch.equal(outs[True], outs[False])
+
+
 def test_launch_profiler_records_kernels():
     """papc_prof_*: every instrumented launch yields one record with a positive duration and the
     algorithmic work of the launch (what bench.py's roofline block is built from)."""

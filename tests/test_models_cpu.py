@@ -63,6 +63,20 @@ def test_product_models_mirror_reference_attributes():
     assert tuple(m.conv2.weight.shape) == (50, 128, 1) and tuple(m.bn1._mean.shape) == (128,)
 
 
+def test_seg_head_is_registered_like_the_reference():
+    """segment/pointnet2/pointnet2.py:21-24 assigns conv1 / bn1 / conv2 as attributes, so Paddle registers them:
+    their tensors must be in parameters() / state_dict() under Paddle's key names."""
+    m = models.PointNet2_SSG_Seg()
+    keys = set(m.state_dict().keys())
+    assert {"conv1.weight", "conv1.bias", "bn1.weight", "bn1.bias", "bn1._mean", "bn1._variance",
+            "conv2.weight", "conv2.bias"} <= keys
+    sd = {k: v.clone() + 1.0 for k, v in m.state_dict().items()}
+    m.load_state_dict(sd)
+    assert float(m.bn1._mean[0]) == 1.0 and float(m.conv2.bias[0]) == 1.0
+    c = models.PointNet2_SSG_Clas()
+    assert {"fc1.weight", "bn1.weight", "fc3.bias"} <= set(c.state_dict().keys())
+
+
 def test_product_models_have_no_cpu_fallback():
     m = models.PointNet2_SSG_Clas()
     with pytest.raises(_lib.PapcError):
