@@ -108,6 +108,26 @@ int papc_ball_query_f32(const float *xyz, const float *new_xyz, int B, int N, in
                         float radius2, int nsample, void *out_idx, int idx_bits,
                         int32_t *empty_count, papc_stream_t stream);
 
+/* A4 (several radii)  the per-radius query_ball_point calls of PointNetSetAbstractionMsg   layers.py:258-267
+ *     One pass over the cloud per centroid evaluates every distance once and fills R (<= 4) index lists:
+ *     out_idx_host[r] -> [B,S,nsample_host[r]] with radius2_host[r]; results identical to R calls of
+ *     papc_ball_query_f32.  radius2_host / nsample_host / out_idx_host are HOST arrays of length R (the
+ *     entries of out_idx_host are device pointers); empty_count (nullable) is a device int32 [R].
+ */
+int papc_ball_query_multi_f32(const float *xyz, const float *new_xyz, int B, int N, int S, int R,
+                              const float *radius2_host, const int32_t *nsample_host,
+                              void *const *out_idx_host, int idx_bits, int32_t *empty_count,
+                              papc_stream_t stream);
+
+/* kNN  the k nearest points of every query under square_distance (A1's arithmetic): ascending distance,
+ *     ties to the lower index -- a stable argsort of a square_distance row cut at k (what
+ *     PointNetFeaturePropagation takes its three neighbours from, layers.py:316-318).  1 <= k <= 32.
+ *     out_idx [B,S,k] int64 / int32 (idx_bits); out_dist [B,S,k] nullable.  Fewer than k points: index N,
+ *     distance +inf in the unused slots.
+ */
+int papc_knn_f32(const float *xyz, const float *query, int B, int N, int S, int k, void *out_idx,
+                 int idx_bits, float *out_dist, papc_stream_t stream);
+
 /* A5  the gather+centre+concat of sample_and_group                 layers.py:146-151, 263-267
  *     out [B,S,K,3+D]: PAPC_XYZ_FIRST  -> [xyz[idx]-new_xyz, feats[idx]]  (SSG, :151)
  *                      PAPC_FEATS_FIRST-> [feats[idx], xyz[idx]-new_xyz]  (MSG, :267)

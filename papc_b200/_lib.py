@@ -66,6 +66,9 @@ _SIGNATURES = {
     "papc_fps_workspace_bytes": (_SZ, [_I, _I]),
     "papc_fps_f32": (_I, [_vp, _I, _I, _I, _vp, _F, _vp, _vp, _vp, _SZ, _vp]),
     "papc_ball_query_f32": (_I, [_vp, _vp, _I, _I, _I, _F, _I, _vp, _I, _vp, _vp]),
+    "papc_ball_query_multi_f32": (_I, [_vp, _vp, _I, _I, _I, _I, C.POINTER(_F), C.POINTER(C.c_int32),
+                                        C.POINTER(C.c_void_p), _I, _vp, _vp]),
+    "papc_knn_f32": (_I, [_vp, _vp, _I, _I, _I, _I, _vp, _I, _vp, _vp]),
     "papc_group_gather_f32": (_I, [_vp, _vp, _vp, _vp, _I, _I, _I, _I, _I, _I, _vp, _vp]),
     "papc_sa_mlp_workspace_bytes": (_SZ, [C.POINTER(GroupSource), C.POINTER(Mlp)]),
     "papc_sa_mlp_f32": (_I, [C.POINTER(GroupSource), C.POINTER(Mlp), _vp, _I, _vp, _SZ, _vp]),

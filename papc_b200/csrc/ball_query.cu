@@ -198,6 +198,180 @@ ball_query_kernel(const float *__restrict__ xyz, const float *__restrict__ new_x
     }
 }
 
+
+// ------------------------------------------------------------------ query_ball_point, several radii at once
+// PointNetSetAbstractionMsg (layers.py:258-267) runs query_ball_point once per radius over the SAME centroids:
+// three (two) full distance passes per layer.  Here one pass evaluates every (query, point) distance once and
+// compacts into up to kBqMaxR index lists (one ballot per radius on the same distance register); the cloud is
+// staged once.  Results are identical to R separate papc_ball_query_f32 calls.
+constexpr int kBqMaxR = 4;
+struct BqMultiArgs {
+    float r2[kBqMaxR];
+    int K[kBqMaxR];
+    void *out[kBqMaxR];
+    int32_t *empty;   // [R] or null
+    int R;
+};
+
+template <typename IdxT>
+__global__ void __launch_bounds__(kBqWarps * 32)
+ball_query_multi_kernel(const float *__restrict__ xyz, const float *__restrict__ new_xyz, int N, int S,
+                        const BqMultiArgs a) {
+    extern __shared__ __align__(128) float s_dyn[];
+    const int chunk = N < kBqChunk ? ((N + 3) & ~3) : kBqChunk;
+    float4 *s_q = reinterpret_cast<float4 *>(s_dyn);
+    float *s_p = s_dyn + chunk * 4;
+    __shared__ __align__(8) uint64_t s_bar;
+    const int b = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int s = blockIdx.x * kBqWarps + warp;
+    const float *cloud = xyz + (size_t)b * N * 3;
+    float qx = 0.f, qy = 0.f, qz = 0.f, qn = 0.f;
+    if (s < S) {
+        const float *q = new_xyz + ((size_t)b * S + s) * 3;
+        qx = q[0]; qy = q[1]; qz = q[2];
+        qn = sq3(qx, qy, qz);
+    }
+    int cnt[kBqMaxR], first[kBqMaxR];
+#pragma unroll
+    for (int r = 0; r < kBqMaxR; ++r) { cnt[r] = 0; first[r] = -1; }
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    uint32_t phase = 0;
+    for (int base = 0; base < N; base += chunk) {
+        const int n = min(chunk, N - base);
+        const float *gsrc = cloud + (size_t)base * 3;
+        const uint32_t bytes = (uint32_t)n * 12u;
+        const bool tma_ok = ((reinterpret_cast<uintptr_t>(gsrc) & 15u) == 0) && ((bytes & 15u) == 0);
+        if (tma_ok) {
+            if (tid == 0) {
+                mbar_expect_tx(&s_bar, bytes);
+                bulk_g2s(s_p, gsrc, bytes, &s_bar);
+            }
+            mbar_wait(&s_bar, phase);
+            phase ^= 1;
+        } else {
+            for (int i = tid; i < n * 3; i += kBqWarps * 32) s_p[i] = gsrc[i];
+            __syncthreads();
+        }
+        for (int j = tid; j < n; j += kBqWarps * 32) {
+            const float x = s_p[j * 3 + 0], y = s_p[j * 3 + 1], z = s_p[j * 3 + 2];
+            s_q[j] = make_float4(x, y, z, sq3(x, y, z));
+        }
+        __syncthreads();
+        if (s < S) {
+            for (int j0 = 0; j0 < n; j0 += 32) {
+                bool open = false;   // any list still short?
+#pragma unroll
+                for (int r = 0; r < kBqMaxR; ++r) open = open || (r < a.R && cnt[r] < a.K[r]);
+                if (!open) break;
+                const int j = j0 + lane;
+                float d = INFINITY;
+                if (j < n) {
+                    const float4 p = s_q[j];
+                    d = sqdist_expanded(qx, qy, qz, qn, p.x, p.y, p.z, p.w);
+                }
+#pragma unroll
+                for (int r = 0; r < kBqMaxR; ++r) {
+                    if (r >= a.R || cnt[r] >= a.K[r]) continue;
+                    const bool in = (j < n) && !(d > a.r2[r]);   // layers.py:112 masks "> r^2" OUT
+                    const unsigned m = __ballot_sync(0xffffffffu, in);
+                    if (m) {
+                        if (first[r] < 0) first[r] = base + j0 + __ffs(m) - 1;
+                        const int pos = cnt[r] + __popc(m & ((1u << lane) - 1u));
+                        IdxT *out = reinterpret_cast<IdxT *>(a.out[r]) + ((size_t)b * S + s) * a.K[r];
+                        if (in && pos < a.K[r]) out[pos] = (IdxT)(base + j);
+                        cnt[r] += __popc(m);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (s >= S) return;
+#pragma unroll
+    for (int r = 0; r < kBqMaxR; ++r) {
+        if (r >= a.R) continue;
+        IdxT *out = reinterpret_cast<IdxT *>(a.out[r]) + ((size_t)b * S + s) * a.K[r];
+        const IdxT pad = (IdxT)(cnt[r] > 0 ? first[r] : N);
+        for (int k = min(cnt[r], a.K[r]) + lane; k < a.K[r]; k += 32) out[k] = pad;
+        if (cnt[r] == 0 && lane == 0 && a.empty != nullptr) atomicAdd(a.empty + r, 1);
+    }
+}
+
+// ------------------------------------------------------------------ k nearest neighbours
+// The k (<= 32) nearest points of every query under square_distance (expansion form, as A1), ascending
+// distance, ties -> the lower index (a stable argsort of the distance row, what layers.py:316-318 takes its
+// first three columns from).  One warp per query; lane i holds the i-th best (distance, index) so far, a
+// candidate that beats the k-th is inserted with one ballot + two shuffles.
+template <typename IdxT>
+__global__ void __launch_bounds__(kBqWarps * 32)
+knn_kernel(const float *__restrict__ xyz, const float *__restrict__ query, int N, int S, int k,
+           IdxT *__restrict__ out_idx, float *__restrict__ out_dist) {
+    extern __shared__ __align__(128) float s_dyn[];
+    const int chunk = N < kBqChunk ? ((N + 3) & ~3) : kBqChunk;
+    float4 *s_q = reinterpret_cast<float4 *>(s_dyn);
+    const int b = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int s = blockIdx.x * kBqWarps + warp;
+    const float *cloud = xyz + (size_t)b * N * 3;
+    float qx = 0.f, qy = 0.f, qz = 0.f, qn = 0.f;
+    if (s < S) {
+        const float *q = query + ((size_t)b * S + s) * 3;
+        qx = q[0]; qy = q[1]; qz = q[2];
+        qn = sq3(qx, qy, qz);
+    }
+    float bd = INFINITY;      // lane i: i-th best distance (lanes >= k stay at +inf and never matter)
+    int bi = 0x7fffffff;
+    for (int base = 0; base < N; base += chunk) {
+        const int n = min(chunk, N - base);
+        __syncthreads();
+        for (int j = tid; j < n; j += kBqWarps * 32) {
+            const float *g = cloud + (size_t)(base + j) * 3;
+            const float x = g[0], y = g[1], z = g[2];
+            s_q[j] = make_float4(x, y, z, sq3(x, y, z));
+        }
+        __syncthreads();
+        if (s >= S) continue;
+        for (int j0 = 0; j0 < n; j0 += 32) {
+            const int j = j0 + lane;
+            float d = INFINITY;
+            if (j < n) {
+                const float4 p = s_q[j];
+                d = sqdist_expanded(qx, qy, qz, qn, p.x, p.y, p.z, p.w);
+            }
+            const int gj = base + j;
+            float thr_d = __shfl_sync(0xffffffffu, bd, k - 1);
+            int thr_i = __shfl_sync(0xffffffffu, bi, k - 1);
+            unsigned m = __ballot_sync(0xffffffffu, (j < n) && (d < thr_d || (d == thr_d && gj < thr_i)));
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const float cd = __shfl_sync(0xffffffffu, d, src);
+                const int ci = __shfl_sync(0xffffffffu, gj, src);
+                if (!(cd < thr_d || (cd == thr_d && ci < thr_i))) continue;   // the threshold moved meanwhile
+                // position = entries that sort before the candidate
+                const bool before = bd < cd || (bd == cd && bi < ci);
+                const int pos = __popc(__ballot_sync(0xffffffffu, before));
+                const float ud = __shfl_up_sync(0xffffffffu, bd, 1);
+                const int ui = __shfl_up_sync(0xffffffffu, bi, 1);
+                if (lane == pos) { bd = cd; bi = ci; }
+                else if (lane > pos) { bd = ud; bi = ui; }
+                thr_d = __shfl_sync(0xffffffffu, bd, k - 1);
+                thr_i = __shfl_sync(0xffffffffu, bi, k - 1);
+            }
+        }
+    }
+    if (s < S && lane < k) {
+        const size_t o = ((size_t)b * S + s) * k + lane;
+        out_idx[o] = (IdxT)(bi == 0x7fffffff ? N : bi);   // fewer than k points: N, like an exhausted sort
+        if (out_dist != nullptr) out_dist[o] = bd;
+    }
+}
+
 // ------------------------------------------------------------------ group gather (A5)
 __global__ void __launch_bounds__(256)
 group_gather_kernel(const float *__restrict__ xyz, const float *__restrict__ new_xyz,
@@ -292,6 +466,64 @@ extern "C" int papc_ball_query_f32(const float *xyz, const float *new_xyz, int B
     else
         ball_query_kernel<int32_t><<<grid, kBqWarps * 32, smem, as_stream(stream)>>>(
             xyz, new_xyz, N, S, radius2, nsample, reinterpret_cast<int32_t *>(out_idx), empty_count);
+    PAPC_LAUNCH_CHECK();
+    return PAPC_OK;
+}
+
+
+extern "C" int papc_ball_query_multi_f32(const float *xyz, const float *new_xyz, int B, int N, int S, int R,
+                                         const float *radius2_host, const int32_t *nsample_host,
+                                         void *const *out_idx_host, int idx_bits, int32_t *empty_count,
+                                         papc_stream_t stream) {
+    if (B < 0 || N <= 0 || S < 0 || R < 1 || R > kBqMaxR || !radius2_host || !nsample_host || !out_idx_host)
+        return PAPC_EINVAL;
+    if (idx_bits != 32 && idx_bits != 64) return PAPC_EINVAL;
+    BqMultiArgs a{};
+    a.R = R;
+    a.empty = empty_count;
+    double out_bytes = 0.0;
+    for (int r = 0; r < R; ++r) {
+        if (nsample_host[r] <= 0 || nsample_host[r] > N) return PAPC_EINVAL;
+        if (!out_idx_host[r] && B * S > 0) return PAPC_EINVAL;
+        a.r2[r] = radius2_host[r];
+        a.K[r] = nsample_host[r];
+        a.out[r] = out_idx_host[r];
+        out_bytes += (idx_bits / 8.0) * B * S * nsample_host[r];
+    }
+    if (B == 0 || S == 0) return PAPC_OK;
+    if (!xyz || !new_xyz) return PAPC_EINVAL;
+    if (B > 65535) return PAPC_EUNSUPPORTED;
+    cudaStream_t st = as_stream(stream);
+    dim3 grid(ceil_div(S, kBqWarps), B);
+    ProfScope prof(st, "ball_query_multi", (long long)B * S, N, R, 0.0, 12.0 * B * (N + S) + out_bytes);
+    const int chunk = N < kBqChunk ? ((N + 3) & ~3) : kBqChunk;
+    const size_t smem = (size_t)chunk * 7 * sizeof(float);
+    if (smem > 48 * 1024) {
+        PAPC_CUDA_TRY(cudaFuncSetAttribute(ball_query_multi_kernel<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PAPC_CUDA_TRY(cudaFuncSetAttribute(ball_query_multi_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    if (idx_bits == 64) ball_query_multi_kernel<int64_t><<<grid, kBqWarps * 32, smem, st>>>(xyz, new_xyz, N, S, a);
+    else ball_query_multi_kernel<int32_t><<<grid, kBqWarps * 32, smem, st>>>(xyz, new_xyz, N, S, a);
+    PAPC_LAUNCH_CHECK();
+    return PAPC_OK;
+}
+
+extern "C" int papc_knn_f32(const float *xyz, const float *query, int B, int N, int S, int k, void *out_idx,
+                            int idx_bits, float *out_dist, papc_stream_t stream) {
+    if (B < 0 || N <= 0 || S < 0 || k < 1 || k > 32) return PAPC_EINVAL;
+    if (idx_bits != 32 && idx_bits != 64) return PAPC_EINVAL;
+    if (B == 0 || S == 0) return PAPC_OK;
+    if (!xyz || !query || !out_idx) return PAPC_EINVAL;
+    if (B > 65535) return PAPC_EUNSUPPORTED;
+    cudaStream_t st = as_stream(stream);
+    dim3 grid(ceil_div(S, kBqWarps), B);
+    ProfScope prof(st, "knn", (long long)B * S, N, k, 0.0, 12.0 * B * (N + S) + (idx_bits / 8.0 + 4.0) * B * S * k);
+    const int chunk = N < kBqChunk ? ((N + 3) & ~3) : kBqChunk;
+    const size_t smem = (size_t)chunk * 4 * sizeof(float);
+    if (idx_bits == 64)
+        knn_kernel<int64_t><<<grid, kBqWarps * 32, smem, st>>>(xyz, query, N, S, k, reinterpret_cast<int64_t *>(out_idx), out_dist);
+    else
+        knn_kernel<int32_t><<<grid, kBqWarps * 32, smem, st>>>(xyz, query, N, S, k, reinterpret_cast<int32_t *>(out_idx), out_dist);
     PAPC_LAUNCH_CHECK();
     return PAPC_OK;
 }

@@ -138,6 +138,51 @@ def query_ball_point(radius, nsample, xyz, new_xyz, check_empty=False):
     return _ball_query(radius, nsample, L.f32c(xyz), L.f32c(new_xyz), torch.int64, check_empty)
 
 
+def _ball_query_multi(queries, xyz, new_xyz, idx_dtype):
+    """All (radius, nsample) pairs of an MSG layer in ONE pass over the distances (papc_ball_query_multi_f32);
+    same results as one ``_ball_query`` per pair."""
+    B, N, _ = xyz.shape
+    S = new_xyz.shape[1]
+    R = len(queries)
+    if R == 1 or R > 4:
+        return [_ball_query(r, k, xyz, new_xyz, idx_dtype) for r, k in queries]
+    for _, k in queries:
+        if k > N:
+            raise ValueError(f"query_ball_point: nsample ({k}) > N ({N})")
+    outs = [torch.empty((B, S, k), dtype=idx_dtype, device=xyz.device) for _, k in queries]
+    r2 = (C.c_float * R)(*[radius2_f32(r) for r, _ in queries])
+    ks = (C.c_int32 * R)(*[int(k) for _, k in queries])
+    ptrs = (C.c_void_p * R)(*[o.data_ptr() for o in outs])
+    L.check(L.lib().papc_ball_query_multi_f32(L.ptr(xyz), L.ptr(new_xyz), B, N, S, R, r2, ks, ptrs,
+                                              64 if idx_dtype == torch.int64 else 32, None,
+                                              L.stream_ptr(xyz.device)), "query_ball_point (multi-radius)")
+    return outs
+
+
+def query_ball_point_multi(radius_list, nsample_list, xyz, new_xyz):
+    """The per-radius ``query_ball_point`` calls of PointNetSetAbstractionMsg.forward (layers.py:258-267) as one
+    kernel: -> list of int64 [B,S,nsample_i]."""
+    L.require_cuda(xyz, new_xyz)
+    return _ball_query_multi(list(zip(radius_list, nsample_list)), L.f32c(xyz), L.f32c(new_xyz), torch.int64)
+
+
+def knn_points(k, xyz, new_xyz, return_dist=False):
+    """k nearest neighbours of every ``new_xyz`` point in ``xyz`` under ``square_distance`` (stable order:
+    ascending distance, ties to the lower index).  xyz [B,N,3], new_xyz [B,S,3] -> int64 [B,S,k]
+    (+ fp32 distances).  The neighbour search inside PointNetFeaturePropagation (layers.py:316-318), standalone."""
+    L.require_cuda(xyz, new_xyz)
+    xyz, new_xyz = L.f32c(xyz), L.f32c(new_xyz)
+    B, N, _ = xyz.shape
+    S = new_xyz.shape[1]
+    if not 1 <= k <= 32:
+        raise ValueError("knn_points: 1 <= k <= 32")
+    idx = torch.empty((B, S, k), dtype=torch.int64, device=xyz.device)
+    dist_ = torch.empty((B, S, k), dtype=torch.float32, device=xyz.device) if return_dist else None
+    L.check(L.lib().papc_knn_f32(L.ptr(xyz), L.ptr(new_xyz), B, N, S, k, L.ptr(idx), 64, L.ptr(dist_),
+                                 L.stream_ptr(xyz.device)), "knn_points")
+    return (idx, dist_) if return_dist else idx
+
+
 def _group_gather(xyz, new_xyz, feats, idx64, order):
     B, N, _ = xyz.shape
     _, S, K = idx64.shape
@@ -220,7 +265,7 @@ def _sample(xyz, ready, npoint, start_idx, queries):
             _, new_xyz = farthest_point_sample_idx(xyz, npoint, start_idx, return_xyz=True)
             ev = torch.cuda.Event()
             ev.record(side)
-            idxs = [_ball_query(r, k, xyz, new_xyz, torch.int32) for r, k in queries]
+            idxs = _ball_query_multi(queries, xyz, new_xyz, torch.int32)
             done = torch.cuda.Event()
             done.record(side)
         main.wait_event(done)
@@ -231,7 +276,7 @@ def _sample(xyz, ready, npoint, start_idx, queries):
     _, new_xyz = farthest_point_sample_idx(xyz, npoint, start_idx, return_xyz=True)
     ev = torch.cuda.Event()
     ev.record(main)
-    idxs = [_ball_query(r, k, xyz, new_xyz, torch.int32) for r, k in queries]
+    idxs = _ball_query_multi(queries, xyz, new_xyz, torch.int32)
     return new_xyz, idxs, ev
 
 

@@ -381,3 +381,42 @@ def test_msg_sa1_c3_shapes_vs_oracle():
     assert tuple(gp.shape) == rp.shape == (B, 320, 512)
     np.testing.assert_array_equal(gx.cpu().numpy(), rx)
     np.testing.assert_allclose(gp.cpu().numpy(), rp, **TOL)
+
+
+# ------------------------------------------------------------------ multi-radius ball query, kNN
+@pytest.mark.parametrize("B,N,S,radii,ks", [(16, 2048, 512, (0.1, 0.2, 0.4), (32, 64, 128)),   # BASELINE config 3, sa1
+                                            (16, 512, 128, (0.4, 0.8), (64, 128)),               # config 3, sa2
+                                            (3, 5000, 70, (0.05, 0.3, 0.5, 2.0), (8, 40, 17, 64)),
+                                            (2, 33, 9, (0.2, 10.0), (33, 5))])
+def test_ball_query_multi_equals_separate_queries(B, N, S, radii, ks):
+    """One distance pass, R index lists (papc_ball_query_multi_f32) == R calls of query_ball_point, bit for bit,
+    and both == the oracle (layers.py:258-267)."""
+    xyz = _xyz(B, N, seed=N + S)
+    fps = capi.farthest_point_sample(xyz, S, synth.fps_start(B, N))
+    new_xyz = layers_np.index_points(xyz, fps)
+    outs = layers.query_ball_point_multi(radii, ks, _cu(xyz), _cu(new_xyz))
+    assert len(outs) == len(radii)
+    for r, k, o in zip(radii, ks, outs):
+        assert o.dtype == torch.int64 and tuple(o.shape) == (B, S, k)
+        ref, _ = capi.query_ball_point(r, k, xyz, new_xyz)
+        np.testing.assert_array_equal(o.cpu().numpy(), ref)
+        np.testing.assert_array_equal(layers.query_ball_point(r, k, _cu(xyz), _cu(new_xyz)).cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("B,N,S,k", [(16, 128, 512, 3), (4, 2048, 100, 16), (2, 5000, 33, 32), (3, 7, 5, 3), (2, 2, 4, 3)])
+def test_knn_vs_stable_argsort_of_square_distance(B, N, S, k):
+    """papc_knn_f32 == the first k columns of a STABLE argsort of square_distance(query, xyz) (the oracle's
+    pinned arithmetic), distances bit-exact; fewer than k points -> index N / +inf."""
+    xyz = _xyz(B, N, seed=3 * N + S)
+    q = _xyz(B, S, seed=7 * S + N)
+    if N >= 8:
+        xyz[:, 5] = xyz[:, 2]            # duplicated points: equal distances, the lower index must come first
+    d = capi.square_distance(q, xyz)                               # [B,S,N]
+    order = np.argsort(d, axis=-1, kind="stable")[:, :, :k]
+    idx, dist_ = layers.knn_points(k, _cu(xyz), _cu(q), return_dist=True)
+    idx, dist_ = idx.cpu().numpy(), dist_.cpu().numpy()
+    kk = min(k, N)
+    np.testing.assert_array_equal(idx[:, :, :kk], order[:, :, :kk])
+    np.testing.assert_array_equal(dist_[:, :, :kk], np.take_along_axis(d, order[:, :, :kk], -1))
+    if kk < k:
+        assert (idx[:, :, kk:] == N).all() and np.isinf(dist_[:, :, kk:]).all()
