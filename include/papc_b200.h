@@ -323,6 +323,28 @@ int papc_pillar_scatter_f32(const float *voxel_features, const int32_t *coords, 
                             int batch, int ny, int nx, const int32_t *num_valid, float *canvas,
                             void *workspace, size_t workspace_bytes, papc_stream_t stream);
 
+/* ----------------------------------------------------------------------------------------
+ * N3  detector post-processing      pp/libs/ops/non_max_suppression/nms_gpu.py
+ *
+ *   papc_nms_f32: nms_gpu (:133-164, box_dim 5: x1, y1, x2, y2, score) and rotate_nms_gpu (:453-488, box_dim 6:
+ *     cx, cy, w, h, angle, score).  Boxes are visited by descending score (ties: higher index first, numpy's
+ *     stable argsort reversed, :147); a box is kept unless a kept box before it has IoU > thresh (:64, :98, :445).
+ *     keep_out [n] int32 receives the ORIGINAL indices of the kept boxes in visiting order (what the reference
+ *     returns as list(order[keep])), -1 beyond *num_out (device int32).  Everything stays on the device: no
+ *     host sort, no mask round trip, no host suppress loop (cc/nms/nms_kernel.cu.cc:100-157).  n <= 65536.
+ *   papc_rotate_iou_f32: rotate_iou_gpu (:518-553, criterion -1) / rotate_iou_gpu_eval (:603-653, criterion
+ *     -1 IoU, 0 inter / area(query), 1 inter / area(box), 2 inter): boxes [N,5], query_boxes [K,5] (cx, cy, w, h,
+ *     angle clockwise) -> out [N,K].
+ *   Arithmetic: fp32 in the reference's operation order, no FMA contraction, cos / sin evaluated in double.
+ *   Reference quirk, reproduced: two IDENTICAL rotated boxes do not score IoU 1 (all eight corners enter the
+ *   clipped polygon, which then holds every vertex twice: IoU 1/3 or 0, see tests/test_nms_oracle.py).
+ */
+size_t papc_nms_workspace_bytes(int n);
+int papc_nms_f32(const float *dets, int n, int box_dim, float thresh, int32_t *keep_out, int32_t *num_out,
+                 void *workspace, size_t workspace_bytes, papc_stream_t stream);
+int papc_rotate_iou_f32(const float *boxes, int N, const float *query_boxes, int K, int criterion, float *out,
+                        papc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,15 +12,16 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "papc_oracle.c")
+SRCS = [SRC, os.path.join(HERE, "nms_oracle.c")]
 OUT = os.path.join(HERE, "libpapc_oracle.so")
 
 
 def build(force=False, verbose=False):
     if (not force and os.path.exists(OUT)
-            and os.path.getmtime(OUT) >= os.path.getmtime(SRC)):
+            and all(os.path.getmtime(OUT) >= os.path.getmtime(f) for f in SRCS)):
         return OUT
     cmd = ["gcc", "-O2", "-fPIC", "-shared", "-std=c11", "-ffp-contract=off",
-           "-fno-fast-math", "-Wall", "-o", OUT, SRC, "-lm"]
+           "-fno-fast-math", "-Wall", "-o", OUT, *SRCS, "-lm"]
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)

@@ -12,8 +12,8 @@ def lib():
     global _LIB
     if _LIB is None:
         path = os.path.join(_HERE, "libpapc_oracle.so")
-        if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(
-                os.path.join(_HERE, "papc_oracle.c")):
+        if not os.path.exists(path) or any(os.path.getmtime(path) < os.path.getmtime(os.path.join(_HERE, f))
+                                           for f in ("papc_oracle.c", "nms_oracle.c")):
             from . import build as _b
             _b.build()
         _LIB = C.CDLL(path)
@@ -90,3 +90,24 @@ def points_to_voxel(points, voxel_size, coors_range, max_points=35, reverse_inde
                                   C.c_int(max_points), C.c_int(1 if reverse_index else 0),
                                   C.c_int(max_voxels), _p(voxels), _p(coors), _p(num))
     return voxels[:n], coors[:n], num[:n]
+
+
+def nms(dets, thresh, rotated=False):
+    """nms_gpu (nms_gpu.py:133-164) / rotate_nms_gpu (:453-488): kept ORIGINAL indices in kept order."""
+    dets = _f32(dets)
+    n = dets.shape[0]
+    assert dets.shape[1] == (6 if rotated else 5)
+    keep = np.zeros(max(n, 1), np.int32)
+    lib().oracle_nms_f32.restype = C.c_int
+    num = lib().oracle_nms_f32(_p(dets), C.c_int(n), C.c_float(thresh), C.c_int(1 if rotated else 0), _p(keep))
+    return keep[:num].copy()
+
+
+def rotate_iou(boxes, query_boxes, criterion=-1):
+    """rotate_iou_gpu_eval (nms_gpu.py:603-653); criterion -1 is rotate_iou_gpu (:518-553)."""
+    boxes, query_boxes = _f32(boxes), _f32(query_boxes)
+    N, K = boxes.shape[0], query_boxes.shape[0]
+    out = np.zeros((N, K), np.float32)
+    if N and K:
+        lib().oracle_rotate_iou_f32(_p(boxes), C.c_int(N), _p(query_boxes), C.c_int(K), C.c_int(criterion), _p(out))
+    return out

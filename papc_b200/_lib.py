@@ -97,6 +97,9 @@ _SIGNATURES = {
                                  _F, _I, _I, _vp, _vp, _vp, _vp, _vp, _SZ, _vp]),
     "papc_pillar_scatter_workspace_bytes": (_SZ, [_I, _I, _I]),
     "papc_pillar_scatter_f32": (_I, [_vp, _vp, _I, _I, _I, _I, _I, _vp, _vp, _vp, _SZ, _vp]),
+    "papc_nms_workspace_bytes": (_SZ, [_I]),
+    "papc_nms_f32": (_I, [_vp, _I, _I, _F, _vp, _vp, _vp, _SZ, _vp]),
+    "papc_rotate_iou_f32": (_I, [_vp, _I, _vp, _I, _I, _vp, _vp]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
