@@ -345,6 +345,45 @@ int papc_nms_f32(const float *dets, int n, int box_dim, float thresh, int32_t *k
 int papc_rotate_iou_f32(const float *boxes, int N, const float *query_boxes, int K, int criterion, float *out,
                         papc_stream_t stream);
 
+/* ----------------------------------------------------------------------------------------
+ * N4  the steps either side of the pillar encode
+ *
+ *   papc_voxelize_batch_f32: points_to_voxel (pc_ops.py:106-166) over a whole batch of frames plus the merged
+ *     layout of merge_second_batch (pp/data/preprocess.py:16-42).  points [total,F] = the frames back to back,
+ *     frame_offsets_host [batch+1] (HOST, offsets[0] = 0); every frame is voxelised exactly as papc_voxelize_f32
+ *     does (first-come numbering, max_points cap, the max_voxels break per frame) and the rows of all frames are
+ *     written back to back: voxels [batch*max_voxels,max_points,F], coors4 [batch*max_voxels,4] int32
+ *     (b, z, y, x) = np.pad(coors, ((0,0),(1,0)), constant_values=b) (:31-36), num_points [batch*max_voxels],
+ *     frame_voxels [batch] int32 (the 'num_voxels' entry), *total_voxels int32 (device); rows >= *total_voxels
+ *     are zero.  batch <= 32.
+ *   papc_anchors_mask_f32: sparse_sum_for_anchors_mask (pp/libs/ops/box_np_ops.py:772-777) -> dense_map [ny,nx]
+ *     (+1 at (coors[i,-2], coors[i,-1]) of every pillar; coor_dim 3 = (z,y,x), 4 = (b,z,y,x)); when n_anchors > 0
+ *     the map is then turned into its inclusive 2-D prefix sum in place (the cumsum(0).cumsum(1) the caller of
+ *     fused_get_anchors_area applies) and anchors_area [n_anchors] = fused_get_anchors_area(dense_map, anchors_bv
+ *     [n_anchors,4] (x1,y1,x2,y2), stride, offset, grid_size) (:781-806).  stride/offset [2], grid_size [2] HOST.
+ *   papc_points_to_bev_f32: points_to_bev (pp/libs/ops/point_cloud/bev_ops.py:6-103): bev_map
+ *     [D + 1 (+1 with reflectivity), H, W]: per height slice the maximum normalised height, (the intensity of the
+ *     last point that raised a maximum of its column), the point count.  height_lowers_host [D] = the reference's
+ *     np.linspace(lo_z, hi_z, D, endpoint=False) (:89-90), computed by the caller.  The sequential loop's break at
+ *     the first new cell once max_voxels cells exist (:44-46) is reproduced.
+ */
+size_t papc_voxelize_batch_workspace_bytes(int total_points, int batch, const float *voxel_size_host,
+                                           const float *coors_range_host, int max_voxels);
+int papc_voxelize_batch_f32(const float *points, const int32_t *frame_offsets_host, int batch, int F,
+                            const float *voxel_size_host, const float *coors_range_host, int max_points,
+                            int reverse_index, int max_voxels, float *voxels, int32_t *coors4,
+                            int32_t *num_points, int32_t *frame_voxels, int32_t *total_voxels,
+                            void *workspace, size_t workspace_bytes, papc_stream_t stream);
+int papc_anchors_mask_f32(const int32_t *coors, int P, int coor_dim, const int32_t *num_valid, int ny, int nx,
+                          const float *anchors_bv, int n_anchors, const float *stride_host, const float *offset_host,
+                          const int32_t *grid_size_host, float *dense_map, float *anchors_area,
+                          papc_stream_t stream);
+size_t papc_points_to_bev_workspace_bytes(int N, const float *voxel_size_host, const float *coors_range_host);
+int papc_points_to_bev_f32(const float *points, int N, int F, const float *voxel_size_host,
+                           const float *coors_range_host, const float *height_lowers_host,
+                           int with_reflectivity, int max_voxels, float *bev_map, void *workspace,
+                           size_t workspace_bytes, papc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,6 +7,8 @@ Follows (paths under /root/reference/PAPC/models/detect/pointpillars/):
   models/bones/pillars.py:9-41, 43-108, 110-142   PFNLayer, PillarFeatureNet, PointPillarsScatter
   libs/functional.py:21-38                        mask_select, select_change
   data/preprocess.py:16-42                        merge_second_batch ('coordinates' branch)
+  libs/ops/box_np_ops.py:772-806                  sparse_sum_for_anchors_mask, fused_get_anchors_area (N4)
+  libs/ops/point_cloud/bev_ops.py:6-103           points_to_bev (N4)
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
 may import this module.
@@ -17,7 +19,9 @@ its outputs (tests/golden/make_golden.py).  PillarFeatureNet / PointPillarsScatt
 is pinned to vectors produced by executing the reference's own classes over a NumPy stand-in for
 paddle (tests/golden/make_golden_pillars.py -> pillars_ref.npz; decoration and canvas bit-exact,
 tests/test_oracle_vs_reference_source.py); the Linear / BatchNorm1D arithmetic remains "parity
-unpinned" (it executes inside PaddlePaddle, absent here; no reference tests).
+unpinned" (it executes inside PaddlePaddle, absent here; no reference tests).  The N4 pieces are PINNED: the
+reference's own functions (plain NumPy / numba) run as they are in tests/golden/make_golden_pillar_batch.py ->
+pillar_batch_ref.npz.
 """
 from __future__ import annotations
 
@@ -220,3 +224,84 @@ class PointPillarsScatter:
         return batch_canvas.reshape(batch_size, self.nchannels, self.ny, self.nx)        # :140
 
     __call__ = forward
+
+
+# ------------------------------------------------------------------ N4: either side of the encode
+def merge_second_batch_voxels(points_list, voxel_size, coors_range, max_points=35, reverse_index=True,
+                              max_voxels=20000):
+    """points_to_voxel per frame (what the dataset's prep function does) followed by the 'voxels' /
+    'num_points' / 'coordinates' branches of merge_second_batch (data/preprocess.py:16-42; 'num_voxels' is popped
+    there, :20 -- returned here beside the dict as the per-frame counts)."""
+    vox, num, coors, nv = [], [], [], []
+    for i, pts in enumerate(points_list):
+        v, c, n = points_to_voxel(pts, voxel_size, coors_range, max_points, reverse_index, max_voxels)
+        vox.append(v)
+        num.append(n)
+        coors.append(np.pad(c, ((0, 0), (1, 0)), mode="constant", constant_values=i))   # :33-36
+        nv.append(v.shape[0])
+    return {"voxels": np.concatenate(vox, axis=0), "num_points": np.concatenate(num, axis=0),
+            "coordinates": np.concatenate(coors, axis=0)}, np.array(nv, np.int32)
+
+
+def sparse_sum_for_anchors_mask(coors, shape):
+    """box_np_ops.py:772-777."""
+    ret = np.zeros(shape, dtype=np.float32)
+    for i in range(coors.shape[0]):
+        ret[coors[i, 1], coors[i, 2]] += 1
+    return ret
+
+
+def fused_get_anchors_area(dense_map, anchors_bv, stride, offset, grid_size):
+    """box_np_ops.py:781-806 (dense_map is the 2-D inclusive prefix sum of the occupancy map); fp32 arithmetic,
+    i.e. what the reference computes for float32 anchors / voxel_size / pc_range."""
+    anchors_bv = np.asarray(anchors_bv, F32)
+    stride = np.asarray(stride, F32)
+    offset = np.asarray(offset, F32)
+    gx, gy = int(grid_size[0]) - 1, int(grid_size[1]) - 1
+    ret = np.zeros((anchors_bv.shape[0],), dtype=dense_map.dtype)
+    for i in range(anchors_bv.shape[0]):
+        c0 = int(np.floor((anchors_bv[i, 0] - offset[0]) / stride[0]))
+        c1 = int(np.floor((anchors_bv[i, 1] - offset[1]) / stride[1]))
+        c2 = int(np.floor((anchors_bv[i, 2] - offset[0]) / stride[0]))
+        c3 = int(np.floor((anchors_bv[i, 3] - offset[1]) / stride[1]))
+        c0, c1, c2, c3 = max(c0, 0), max(c1, 0), min(c2, gx), min(c3, gy)
+        ret[i] = dense_map[c3, c2] - dense_map[c3, c0] - dense_map[c1, c2] + dense_map[c1, c0]
+    return ret
+
+
+def points_to_bev(points, voxel_size, coors_range, with_reflectivity=False, density_norm_num=16, max_voxels=40000):
+    """bev_ops.py:6-103, the sequential loop restated (fp32 throughout, like the jitted kernel on float32 input)."""
+    points = np.asarray(points, F32)
+    voxel_size = np.asarray(voxel_size, dtype=F32)
+    coors_range = np.asarray(coors_range, dtype=F32)
+    shape = tuple(np.round((coors_range[3:] - coors_range[:3]) / voxel_size).astype(np.int32).tolist())[::-1]
+    grid = shape[::-1]
+    seen = -np.ones(shape, np.int32)
+    D = shape[0]
+    lowers = np.linspace(coors_range[2], coors_range[5], D, endpoint=False).astype(F32)
+    bev = np.zeros((D + 1 + (1 if with_reflectivity else 0),) + shape[1:], F32)
+    slice_h = voxel_size[2]
+    voxel_num = 0
+    for i in range(points.shape[0]):
+        coor = [0, 0, 0]
+        failed = False
+        for j in range(3):
+            c = np.floor((points[i, j] - coors_range[j]) / voxel_size[j])
+            if c < 0 or c >= grid[j]:
+                failed = True
+                break
+            coor[2 - j] = int(c)
+        if failed:
+            continue
+        if seen[coor[0], coor[1], coor[2]] == -1:
+            if voxel_num >= max_voxels:
+                break
+            seen[coor[0], coor[1], coor[2]] = voxel_num
+            voxel_num += 1
+        bev[-1, coor[1], coor[2]] += 1
+        h = F32(F32(points[i, 2] - lowers[coor[0]]) / slice_h)
+        if h > bev[coor[0], coor[1], coor[2]]:
+            bev[coor[0], coor[1], coor[2]] = h
+            if with_reflectivity:
+                bev[-2, coor[1], coor[2]] = points[i, 3]
+    return bev

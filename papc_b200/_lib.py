@@ -97,6 +97,14 @@ _SIGNATURES = {
                                  _F, _I, _I, _vp, _vp, _vp, _vp, _vp, _SZ, _vp]),
     "papc_pillar_scatter_workspace_bytes": (_SZ, [_I, _I, _I]),
     "papc_pillar_scatter_f32": (_I, [_vp, _vp, _I, _I, _I, _I, _I, _vp, _vp, _vp, _SZ, _vp]),
+    "papc_voxelize_batch_workspace_bytes": (_SZ, [_I, _I, C.POINTER(_F), C.POINTER(_F), _I]),
+    "papc_voxelize_batch_f32": (_I, [_vp, C.POINTER(C.c_int32), _I, _I, C.POINTER(_F), C.POINTER(_F), _I, _I, _I,
+                                      _vp, _vp, _vp, _vp, _vp, _vp, _SZ, _vp]),
+    "papc_anchors_mask_f32": (_I, [_vp, _I, _I, _vp, _I, _I, _vp, _I, C.POINTER(_F), C.POINTER(_F),
+                                    C.POINTER(C.c_int32), _vp, _vp, _vp]),
+    "papc_points_to_bev_workspace_bytes": (_SZ, [_I, C.POINTER(_F), C.POINTER(_F)]),
+    "papc_points_to_bev_f32": (_I, [_vp, _I, _I, C.POINTER(_F), C.POINTER(_F), C.POINTER(_F), _I, _I, _vp, _vp,
+                                     _SZ, _vp]),
     "papc_nms_workspace_bytes": (_SZ, [_I]),
     "papc_nms_f32": (_I, [_vp, _I, _I, _F, _vp, _vp, _vp, _SZ, _vp]),
     "papc_rotate_iou_f32": (_I, [_vp, _I, _vp, _I, _I, _vp, _vp]),

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 OUT_DIR = os.path.join(os.path.dirname(HERE), "lib")
 OUT = os.path.join(OUT_DIR, "libpapc_b200.so")
-SOURCES = ["capi.cu", "fps.cu", "ball_query.cu", "sa_mlp.cu", "sa_mlp_tc.cu", "sa_mlp_tt.cu", "sa_chain.cu", "pillars.cu", "feature_prop.cu", "nms.cu"]
+SOURCES = ["capi.cu", "fps.cu", "ball_query.cu", "sa_mlp.cu", "sa_mlp_tc.cu", "sa_mlp_tt.cu", "sa_chain.cu", "pillars.cu", "pillar_batch.cu", "feature_prop.cu", "nms.cu"]
 # per-file flags.  fps.cu: the distance is pinned as separately rounded multiplies and adds.
 EXTRA = {"fps.cu": ["-fmad=false"], "nms.cu": ["-fmad=false"]}   # nms.cu: IoU arithmetic pinned like oracle/nms_oracle.c
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -275,3 +275,121 @@ def merge_coordinates(coors_list):
         pad = torch.full((c.shape[0], 1), i, dtype=c.dtype, device=c.device)
         out.append(torch.cat([pad, c], dim=1))
     return torch.cat(out, dim=0)
+
+
+# ------------------------------------------------------------------ N4: the steps either side of the encode
+def points_to_voxel_batch_device(points_list, voxel_size, coors_range, max_points=35, reverse_index=True,
+                                 max_voxels=20000):
+    """``points_to_voxel`` over a list of frames + the merged batch layout of ``merge_second_batch``
+    (pp/data/preprocess.py:16-42), device resident, no host sync: returns
+    ``(voxels [B*max_voxels,T,F], coordinates [B*max_voxels,4] int32 (b,z,y,x), num_points [B*max_voxels] int32,
+    num_voxels [B] int32, total int32[1])``; rows >= total are zero.  Feeds ``PillarFeatureNet`` /
+    ``PointPillarsScatter`` through ``num_valid=total``."""
+    if len(points_list) < 1:
+        raise ValueError("points_to_voxel_batch: empty batch")
+    L.require_cuda(*points_list)
+    pts = [L.f32c(p) for p in points_list]
+    F = pts[0].shape[1]
+    for p in pts:
+        if p.dim() != 2 or p.shape[1] != F or F < 3:
+            raise ValueError("every frame must be [N_i, F>=3] with the same F")
+    dev = pts[0].device
+    B = len(pts)
+    offs = np.zeros(B + 1, np.int32)
+    offs[1:] = np.cumsum([p.shape[0] for p in pts])
+    allp = torch.cat(pts, dim=0) if B > 1 else pts[0]
+    vs_c, cr_c, _, _ = _geom(voxel_size, coors_range)
+    lib = L.lib()
+    rows = B * max_voxels
+    voxels = torch.empty((rows, max_points, F), dtype=torch.float32, device=dev)
+    coors = torch.empty((rows, 4), dtype=torch.int32, device=dev)
+    num = torch.empty((rows,), dtype=torch.int32, device=dev)
+    fv = torch.empty((B,), dtype=torch.int32, device=dev)
+    total = torch.empty((1,), dtype=torch.int32, device=dev)
+    wsb = lib.papc_voxelize_batch_workspace_bytes(int(offs[-1]), B, vs_c, cr_c, max_voxels)
+    if wsb == 0:
+        raise ValueError("points_to_voxel_batch: bad voxel_size / coors_range / max_voxels / batch (<= 32)")
+    ws = _ws(wsb, dev)
+    offs_c = (C.c_int32 * (B + 1))(*offs.tolist())
+    L.check(lib.papc_voxelize_batch_f32(L.ptr(allp), offs_c, B, F, vs_c, cr_c, int(max_points),
+                                        1 if reverse_index else 0, int(max_voxels), L.ptr(voxels), L.ptr(coors),
+                                        L.ptr(num), L.ptr(fv), L.ptr(total), L.ptr(ws), wsb, L.stream_ptr(dev)),
+            "points_to_voxel_batch")
+    return voxels, coors, num, fv, total
+
+
+def merge_second_batch_voxels(points_list, voxel_size, coors_range, max_points=35, reverse_index=True,
+                              max_voxels=20000):
+    """The 'voxels' / 'num_points' / 'coordinates' entries of ``merge_second_batch`` (pp/data/preprocess.py:16-42;
+    'num_voxels' is popped there, :20) for a list of point clouds: NumPy in -> (dict of NumPy arrays with the
+    reference's shapes, per-frame voxel counts); this form reads the total back, as the reference's return
+    shapes require."""
+    is_np = isinstance(points_list[0], np.ndarray)
+    pl = [torch.from_numpy(np.ascontiguousarray(p, dtype=np.float32)).cuda() if is_np else p for p in points_list]
+    v, c, n, fv, total = points_to_voxel_batch_device(pl, voxel_size, coors_range, max_points, reverse_index, max_voxels)
+    m = int(total.item())
+    out = {"voxels": v[:m], "num_points": n[:m], "coordinates": c[:m]}
+    if is_np:
+        return {k: t.cpu().numpy() for k, t in out.items()}, fv.cpu().numpy()
+    return out, fv
+
+
+def sparse_sum_for_anchors_mask(coors, shape, num_valid=None):
+    """box_np_ops.py:772-777: ``ret[coors[i,1], coors[i,2]] += 1`` over (z,y,x) rows -> float32 [ny,nx].
+    Also accepts merged (b,z,y,x) rows (the last two columns are used).  torch CUDA in / out, or NumPy in / out."""
+    is_np = isinstance(coors, np.ndarray)
+    c = torch.from_numpy(np.ascontiguousarray(coors, dtype=np.int32)).cuda() if is_np else coors
+    L.require_cuda(c)
+    c = c.to(torch.int32).contiguous()
+    ny, nx = int(shape[0]), int(shape[1])
+    dense = torch.empty((ny, nx), dtype=torch.float32, device=c.device)
+    L.check(L.lib().papc_anchors_mask_f32(L.ptr(c), c.shape[0], c.shape[1], L.ptr(num_valid), ny, nx, None, 0, None, None,
+                                          None, L.ptr(dense), None, L.stream_ptr(c.device)), "sparse_sum_for_anchors_mask")
+    return dense.cpu().numpy() if is_np else dense
+
+
+def anchors_area_from_coors(coors, shape, anchors_bv, stride, offset, grid_size, num_valid=None):
+    """The anchors-mask chain of the reference's target assigner in one call:
+    ``dense = sparse_sum_for_anchors_mask(coors, shape).cumsum(0).cumsum(1)`` then
+    ``fused_get_anchors_area(dense, anchors_bv, stride, offset, grid_size)`` (box_np_ops.py:772-806).
+    Returns (dense cumulative map [ny,nx], anchors_area [N])."""
+    is_np = isinstance(coors, np.ndarray)
+    c = torch.from_numpy(np.ascontiguousarray(coors, dtype=np.int32)).cuda() if is_np else coors
+    a = torch.from_numpy(np.ascontiguousarray(anchors_bv, dtype=np.float32)).cuda() if isinstance(anchors_bv, np.ndarray) else anchors_bv
+    L.require_cuda(c, a)
+    c = c.to(torch.int32).contiguous()
+    a = L.f32c(a)
+    ny, nx = int(shape[0]), int(shape[1])
+    dense = torch.empty((ny, nx), dtype=torch.float32, device=c.device)
+    area = torch.empty((a.shape[0],), dtype=torch.float32, device=c.device)
+    st = (C.c_float * 2)(float(stride[0]), float(stride[1]))
+    of = (C.c_float * 2)(float(offset[0]), float(offset[1]))
+    gs = (C.c_int32 * 2)(int(grid_size[0]), int(grid_size[1]))
+    L.check(L.lib().papc_anchors_mask_f32(L.ptr(c), c.shape[0], c.shape[1], L.ptr(num_valid), ny, nx, L.ptr(a), a.shape[0],
+                                          st, of, gs, L.ptr(dense), L.ptr(area), L.stream_ptr(c.device)),
+            "fused_get_anchors_area")
+    if is_np:
+        return dense.cpu().numpy(), area.cpu().numpy()
+    return dense, area
+
+
+def points_to_bev(points, voxel_size, coors_range, with_reflectivity=False, density_norm_num=16, max_voxels=40000):
+    """bev_ops.py:61-103: points [N,4] -> bev map [D+1(+1), H, W] (per-slice maximum normalised height,
+    optional intensity map, point-count map).  NumPy in -> NumPy out or torch CUDA in -> out."""
+    is_np = isinstance(points, np.ndarray)
+    p = torch.from_numpy(np.ascontiguousarray(points, dtype=np.float32)).cuda() if is_np else points
+    L.require_cuda(p)
+    p = L.f32c(p)
+    vs_c, cr_c, vs, cr = _geom(voxel_size, coors_range)
+    shape = tuple(np.round((cr[3:] - cr[:3]) / vs).astype(np.int32).tolist())[::-1]   # DHW (:84-86)
+    D, H, W = shape
+    lowers = np.linspace(cr[2], cr[5], D, endpoint=False).astype(np.float32)            # (:89-90)
+    hl = (C.c_float * D)(*lowers.tolist())
+    nm = D + 1 + (1 if with_reflectivity else 0)
+    bev = torch.empty((nm, H, W), dtype=torch.float32, device=p.device)
+    lib = L.lib()
+    wsb = lib.papc_points_to_bev_workspace_bytes(p.shape[0], vs_c, cr_c)
+    ws = _ws(wsb, p.device)
+    L.check(lib.papc_points_to_bev_f32(L.ptr(p), p.shape[0], p.shape[1], vs_c, cr_c, hl, 1 if with_reflectivity else 0,
+                                       int(max_voxels), L.ptr(bev), L.ptr(ws), wsb, L.stream_ptr(p.device)), "points_to_bev")
+    return bev.cpu().numpy() if is_np else bev

@@ -200,3 +200,88 @@ def test_scatter_bit_exact_and_fused_device_path():
     cc = pillars_np.merge_coordinates([c])
     exp = pillars_np.PointPillarsScatter([1, 1, 496, 432], 64)(ref_pfn(v, n, cc), cc, 1)
     np.testing.assert_allclose(canvas.cpu().numpy(), exp, **TOL)
+
+
+# ---- N4: batched voxelisation + merged layout, anchors mask, BEV map -- vs the reference's own outputs
+def _n4(golden_dir):
+    return np.load(os.path.join(golden_dir, "pillar_batch_ref.npz"))
+
+
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_voxelize_batch_merged_golden(golden_dir, case):
+    """points_to_voxel per frame + merge_second_batch (data/preprocess.py:16-42) in one device call: ragged frames,
+    an empty frame, frames that hit the max_voxels break; bit-exact vs the reference's own output."""
+    g = _n4(golden_dir)
+    frames = [g[f"{case}_points{i}"] for i in range(len(g[f"{case}_sizes"]))]
+    mp, mv = [int(x) for x in g[f"{case}_cfg"]]
+    merged, fv = pillars.merge_second_batch_voxels(frames, g["voxel_size"], g["range"], mp, True, mv)
+    np.testing.assert_array_equal(fv, g[f"{case}_frame_voxels"])
+    for k in ("coordinates", "num_points", "voxels"):
+        assert merged[k].dtype == g[f"{case}_{k}"].dtype, k
+        np.testing.assert_array_equal(merged[k], g[f"{case}_{k}"], err_msg=k)
+    # rows past the total are zero on the device form
+    v, c, n, fvd, tot = pillars.points_to_voxel_batch_device([_cu(f) for f in frames], g["voxel_size"], g["range"], mp, True, mv)
+    m = int(tot.item())
+    assert m == int(fv.sum())
+    assert not v[m:].any() and not c[m:].any() and not n[m:].any()
+
+
+def test_voxelize_batch_k5_matches_single_frame():
+    """BASELINE config 4 (20 000-point frames), batch of 3: every frame's rows equal the single-frame voxeliser's
+    (itself pinned to the reference's numba kernel) and the merged coordinates carry the frame index."""
+    frames = [synth.lidar_frame(20000, s, s == 1) for s in range(3)]
+    v, c, n, fv, tot = pillars.points_to_voxel_batch_device([_cu(f) for f in frames], synth.KITTI_VOXEL_SIZE,
+                                                            synth.KITTI_PC_RANGE, synth.KITTI_MAX_POINTS, True,
+                                                            synth.KITTI_MAX_VOXELS)
+    fv = fv.cpu().numpy()
+    assert int(tot.item()) == int(fv.sum())
+    r0 = 0
+    for b, f in enumerate(frames):
+        v1, c1, n1 = pillars.points_to_voxel(f, synth.KITTI_VOXEL_SIZE, synth.KITTI_PC_RANGE, synth.KITTI_MAX_POINTS,
+                                             True, synth.KITTI_MAX_VOXELS)
+        m = v1.shape[0]
+        assert fv[b] == m
+        np.testing.assert_array_equal(v[r0:r0 + m].cpu().numpy(), v1)
+        np.testing.assert_array_equal(n[r0:r0 + m].cpu().numpy(), n1)
+        cc = c[r0:r0 + m].cpu().numpy()
+        assert (cc[:, 0] == b).all()
+        np.testing.assert_array_equal(cc[:, 1:], c1)
+        r0 += m
+
+
+def test_anchors_mask_golden(golden_dir):
+    g = _n4(golden_dir)
+    grid = g["am_grid"]
+    shape = tuple(int(x) for x in grid[::-1][1:])
+    dense = pillars.sparse_sum_for_anchors_mask(g["am_coors"], shape)
+    np.testing.assert_array_equal(dense, g["am_dense"])
+    cum, area = pillars.anchors_area_from_coors(g["am_coors"], shape, g["am_anchors_bv"], g["voxel_size"], g["range"], grid)
+    np.testing.assert_array_equal(cum, g["am_cum"])
+    np.testing.assert_array_equal(area, g["am_area"])
+    # merged (b,z,y,x) rows and a device-side count
+    c4 = np.pad(g["am_coors"], ((0, 5), (1, 0)))
+    nv = torch.tensor([g["am_coors"].shape[0]], dtype=torch.int32, device=DEV)
+    d2 = pillars.sparse_sum_for_anchors_mask(_cu(c4), shape, num_valid=nv)
+    np.testing.assert_array_equal(d2.cpu().numpy(), g["am_dense"])
+
+
+@pytest.mark.parametrize("key,refl,mv", [("bev_plain", False, 40000), ("bev_refl", True, 40000), ("bev_refl_break", True, 700)])
+def test_points_to_bev_golden(golden_dir, key, refl, mv):
+    g = _n4(golden_dir)
+    bev = pillars.points_to_bev(g["bev_points"], g["bev_voxel_size"], g["range"], refl, max_voxels=mv)
+    assert bev.shape == g[key].shape
+    np.testing.assert_array_equal(bev, g[key])
+
+
+def test_points_to_bev_random_vs_oracle():
+    rng = np.random.default_rng(3)
+    pts = rng.uniform(-1, 1, (6000, 4)).astype(np.float32)
+    pts[:, 0] = pts[:, 0] * 6 + 5
+    pts[:, 1] *= 5
+    pts[:, 2] = np.round(pts[:, 2] * 10) / 4 - 1
+    vs, rg = np.array([0.25, 0.5, 0.5], np.float32), np.array([0, -4, -3, 10, 4, 1], np.float32)
+    for refl in (False, True):
+        for mv in (40000, 900):
+            want = pillars_np.points_to_bev(pts, vs, rg, refl, max_voxels=mv)
+            got = pillars.points_to_bev(pts, vs, rg, refl, max_voxels=mv)
+            np.testing.assert_array_equal(got, want)

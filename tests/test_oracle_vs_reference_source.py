@@ -254,3 +254,41 @@ def test_c_oracle_indices_at_baseline_config_3(golden_dir):
     l2 = layers_np.index_points(l1, f2)
     for r, k in ((0.4, 64), (0.8, 128)):
         assert _digest(capi.query_ball_point(r, k, l1, l2)[0]) == str(gc[f"sa2_ball_r{r}_k{k}:sha256"]), (r, k)
+
+
+# ---- N4: batched voxelisation layout, anchors mask, BEV map (tests/golden/make_golden_pillar_batch.py)
+def _n4():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pillar_batch_ref.npz"))
+
+
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_n4_merged_voxel_batch_oracle(case):
+    from oracle import pillars_np
+    g = _n4()
+    frames = [g[f"{case}_points{i}"] for i in range(len(g[f"{case}_sizes"]))]
+    mp, mv = [int(x) for x in g[f"{case}_cfg"]]
+    merged, fv = pillars_np.merge_second_batch_voxels(frames, g["voxel_size"], g["range"], mp, True, mv)
+    for k in ("voxels", "num_points", "coordinates"):
+        np.testing.assert_array_equal(merged[k], g[f"{case}_{k}"], err_msg=k)
+    np.testing.assert_array_equal(fv, g[f"{case}_frame_voxels"])
+
+
+def test_n4_anchors_mask_oracle():
+    from oracle import pillars_np
+    g = _n4()
+    grid = g["am_grid"]
+    dense = pillars_np.sparse_sum_for_anchors_mask(g["am_coors"], tuple(grid[::-1][1:]))
+    np.testing.assert_array_equal(dense, g["am_dense"])
+    cum = dense.cumsum(0).cumsum(1)
+    np.testing.assert_array_equal(cum, g["am_cum"])
+    area = pillars_np.fused_get_anchors_area(cum, g["am_anchors_bv"], g["voxel_size"], g["range"], grid)
+    np.testing.assert_array_equal(area, g["am_area"])
+
+
+@pytest.mark.parametrize("key,refl,mv", [("bev_plain", False, 40000), ("bev_refl", True, 40000), ("bev_refl_break", True, 700)])
+def test_n4_points_to_bev_oracle(key, refl, mv):
+    from oracle import pillars_np
+    g = _n4()
+    bev = pillars_np.points_to_bev(g["bev_points"], g["bev_voxel_size"], g["range"], refl, max_voxels=mv)
+    np.testing.assert_array_equal(bev, g[key])
