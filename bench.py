@@ -138,9 +138,7 @@ def cpu_reference_step(xyz, starts, params, acc):
     return p
 
 
-def time_cpu_baseline(steps, warmup, batch):
-    """Oracle on the host cores: returns (points/s, ms/step, cores, sample description)."""
-    from papc_b200 import synth
+def _host_threads():
     cores = os.cpu_count() or 1
     try:
         import torch
@@ -152,20 +150,66 @@ def time_cpu_baseline(steps, warmup, batch):
         threadpool_limits(limits=cores)
     except Exception:
         pass
-    xyz = synth.clouds(batch, N_POINTS, seed=0)
-    starts = [synth.fps_start(batch, N_POINTS, seed=1), np.zeros(batch, np.int64), None]
+    return cores
+
+
+def cpu_reference_factory(batch, cfgs=None, n_points=N_POINTS, msg=False):
+    """-> (step_fn, kind, description).  Preferred: the reference's OWN layers file
+    (PAPC/models/layers/pointnet2_basic_layers.py, staged unmodified under oracle/_ref/ by oracle/build.py)
+    executed over the torch-CPU paddle facade (papc_b200/compat) -- kind "reference".  Fallback when oracle/_ref
+    is absent: the NumPy oracle port -- kind "port".  Both run train-mode BatchNorm over the whole batch."""
+    from oracle import build as oracle_build
+    from papc_b200 import synth
+    xyz = synth.clouds(batch, n_points, seed=0)
+    st = [synth.fps_start(batch, n_points, seed=1), np.zeros(batch, np.int64)]
+    ref_layers = oracle_build.ref_file("pointnet2_basic_layers.py")
+    if ref_layers is not None:
+        import torch
+        from papc_b200 import compat
+        m = compat.install(layers_file=ref_layers, device="cpu", force=True)
+        if msg:   # BASELINE configs[2]: the MSG segment SetAbstraction stack (segment/pointnet2/pointnet2.py:62-64)
+            sas = [m.PointNetSetAbstractionMsg(512, [0.1, 0.2, 0.4], [32, 64, 128], 3, [[32, 32, 64], [64, 64, 128], [64, 96, 128]]),
+                   m.PointNetSetAbstractionMsg(128, [0.4, 0.8], [64, 128], 128 + 128 + 64, [[128, 128, 256], [128, 196, 256]]),
+                   m.PointNetSetAbstraction(None, None, None, 512 + 3, [256, 512, 1024], True)]
+        else:
+            sas = [m.PointNetSetAbstraction(*c) for c in SA_CFG]
+
+        def step():
+            compat.paddle_torch.queue_randint([s.copy() for s in st])
+            with torch.no_grad():
+                x = compat.paddle_torch.to_tensor(xyz)
+                p = x if msg else None
+                for sa in sas:
+                    x, p = sa(x, p)
+            return p
+        return step, "reference", ("the reference's own pointnet2_basic_layers.py (unmodified, oracle/_ref) over the "
+                                   "torch-CPU paddle facade (papc_b200/compat)")
+    if msg:
+        raise RuntimeError("MSG reference sample needs oracle/_ref")
     params = [synth.mlp_params(c[3], c[4], seed=2 + i) for i, c in enumerate(SA_CFG)]
+    starts = st + [None]
+    return (lambda: cpu_reference_step(xyz, starts, params, np.float32)), "port", "NumPy/BLAS oracle port (oracle/layers_np.py)"
+
+
+def time_cpu_baseline(steps, warmup, batch, budget_s=None):
+    """The reference path on the host cores: returns dict(value points/s, ms, cores, kind, sample, steps)."""
+    cores = _host_threads()
+    step, kind, what = cpu_reference_factory(batch)
+    t_all = time.perf_counter()
     for _ in range(warmup):
-        cpu_reference_step(xyz, starts, params, np.float32)
+        step()
     t = []
-    for _ in range(steps):
+    for i in range(steps):
         t0 = time.perf_counter()
-        cpu_reference_step(xyz, starts, params, np.float32)
+        step()
         t.append(time.perf_counter() - t0)
+        if budget_s is not None and i + 1 < steps and (time.perf_counter() - t_all) + 1.5 * t[-1] > budget_s:
+            break   # bounded sample: stop before the run exceeds its time budget (reported in `steps`)
     ms = 1e3 * float(np.mean(t))
-    sample = (f"{steps} timed passes (after {warmup} warm-up) of the full sa1+sa2+sa3 oracle over "
-              f"{batch} clouds x {N_POINTS} points, fp32 NumPy/BLAS with {cores} threads")
-    return batch * N_POINTS / (ms / 1e3), ms, cores, sample
+    sample = (f"{len(t)} timed passes (after {warmup} warm-up) of sa1+sa2+sa3 over {batch} clouds x {N_POINTS} "
+              f"points, train-mode BatchNorm, fp32, {cores} host threads: {what}")
+    return {"value": batch * N_POINTS / (ms / 1e3), "ms": ms, "cores": cores, "kind": kind, "sample": sample,
+            "steps": len(t)}
 
 
 WORKLOAD = ("PointNet++SSG classify SetAbstraction stack sa1+sa2+sa3, 1024-pt clouds, "
@@ -173,26 +217,29 @@ WORKLOAD = ("PointNet++SSG classify SetAbstraction stack sa1+sa2+sa3, 1024-pt cl
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path.  PaddlePaddle cannot
-    be installed here (no wheel, no network), so this is the oracle port -- the line-by-line NumPy
-    restatement of pointnet2_basic_layers.py -- on all host cores."""
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores, the FULL
+    per-GPU batch (32 clouds) per step, --steps / --warmup honoured (a 240 s budget stops a slow box early and
+    the line says how many steps ran).  PaddlePaddle itself cannot be installed (no wheel, no network): the
+    reference's layers file runs unmodified over the torch-CPU paddle facade."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    batch = 8  # bounded sample: 8 of the 32 clouds per pass keeps K+W passes within a few minutes
-    steps, warmup = min(args.steps, 5), min(args.warmup, 1)
-    value, ms, cores, sample = time_cpu_baseline(steps, warmup, batch)
+    batch = B_PER_GPU
+    r = time_cpu_baseline(args.steps, args.warmup, batch, budget_s=240.0)
+    world = max(1, args.gpus)
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch": B_PER_GPU * max(1, args.gpus), "n_points": N_POINTS,
-                   "bn": "train-mode batch statistics, as the reference's unregistered SA layers run",
-                   "sample": f"{batch} of the {B_PER_GPU} clouds per step (points/s is per point, so the "
-                             "rate is that of the full batch on the same cores)",
-                   "note": "Paddle unavailable: CPU restatement of the reference path (oracle port), rank 0 only"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": WORKLOAD, "global_batch": B_PER_GPU * world, "n_points": N_POINTS,
+                   "parallelism": f"batch-shard x{world}",
+                   "bn": "train-mode batch statistics (per shard), as the reference's unregistered SA layers run",
+                   "sample": (f"every step = one full pass over {batch} clouds" +
+                              ("" if world == 1 else f" (one rank's shard of the {B_PER_GPU * world}-cloud batch; "
+                               "points/s is per point, CPU time scales linearly in the batch)")),
+                   "note": "CPU arm: " + r["sample"]},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -239,22 +286,39 @@ def run_ours(args):
 
     # The step as the library's public graph API runs it: the whole sa1 -> sa2 -> sa3 forward captured
     # once (papc_b200.sa_stack.GraphedForward) and replayed; --no-graph times the eager calls instead.
-    graphed = None
-    if not args.no_graph:
-        graphed = sa_stack.GraphedForward(lambda x: model(x, None, start_idx=(st1, st2)), xyz_d)
-
-    def forward(x=None):
-        if graphed is None:
-            _, l3 = model(xyz_d if x is None else x, None, start_idx=(st1, st2))
-        else:
-            _, l3 = graphed.replay() if x is None else graphed(x)
-        return l3.reshape(B, 1024)
-
-    def step_device():
-        feats = forward()
+    def fwd_gather(x):
+        """The step: sa1 -> sa2 -> sa3 on this rank's shard, then (N > 1) the ONE all-gather of the l3 features."""
+        _, l3 = model(x, None, start_idx=(st1, st2))
+        feats = l3.reshape(B, 1024)
         if world > 1:
             feats = pdist.all_gather_features(feats)
         return feats
+
+    graphed = None
+    gather_in_graph = False
+    if not args.no_graph:
+        if world > 1 and os.environ.get("PAPC_GATHER_IN_GRAPH", "1") != "0":
+            try:   # the NCCL all-gather captured as a node of the same graph: no separate launch after the replay
+                graphed = sa_stack.GraphedForward(fwd_gather, xyz_d)
+                gather_in_graph = True
+            except Exception as e:  # noqa: BLE001
+                print(f"[bench] all-gather capture failed ({type(e).__name__}: {e}); gathering after the replay",
+                      file=sys.stderr)
+                torch.cuda.synchronize()
+                graphed = None
+        if graphed is None:
+            graphed = sa_stack.GraphedForward(lambda x: model(x, None, start_idx=(st1, st2))[1].reshape(B, 1024), xyz_d)
+
+    def forward(x=None):
+        if graphed is None:
+            return fwd_gather(xyz_d if x is None else x)
+        feats = graphed.replay() if x is None else graphed(x)
+        if world > 1 and not gather_in_graph:
+            feats = pdist.all_gather_features(feats)
+        return feats
+
+    def step_device():
+        return forward()
 
     def step_e2e():
         if graphed is None:
@@ -262,8 +326,7 @@ def run_ours(args):
         else:
             feats = forward(xyz_h)          # H2D straight into the graph's static input buffer
         if world > 1:
-            g = pdist.all_gather_features(feats)
-            feats = g[lo:hi]
+            feats = feats[lo:hi]
         out_h.copy_(feats, non_blocking=True)
 
     def barrier():
@@ -303,6 +366,10 @@ def run_ours(args):
     e2e_ms, _ = timed(step_e2e, args.steps, args.warmup)
     if sampler:
         sampler.stop()
+
+    extra = {}
+    if not args.no_extra:
+        extra = extra_modes(torch, dist, pdist, sa_stack, synth, model, dev, rank, world, timed, args)
 
     points_per_step = Bg * N_POINTS
     value = points_per_step * args.steps / (total_ms / 1e3)
@@ -366,8 +433,11 @@ def run_ours(args):
         "kernel": sass.get(fam_name, fam_name), "avg_launch_ms": avg_ms, "launches_per_step": fam["launches"],
         "share_of_step": fam["ms"] / step_ms,
         "algorithmic_flops_per_launch": fam["flops"] / fam["launches"],
-        "algorithmic_bytes_per_launch": fam["bytes"] / fam["launches"],
-        "hbm_gbs_algorithmic": fam["bytes"] / (fam["ms"] / 1e3) / 1e9, "hbm_peak_gbs": hbm,
+        # ~800 B of compulsory traffic per point for the whole stack, spread over its launches
+        "algorithmic_bytes_per_launch": algorithmic_bytes_per_cloud() * B / fam["launches"],
+        # what THIS design moves per launch (pre-BatchNorm activations are materialised between layers)
+        "materialised_bytes_per_launch": fam["bytes"] / fam["launches"],
+        "hbm_gbs_materialised": fam["bytes"] / (fam["ms"] / 1e3) / 1e9, "hbm_peak_gbs": hbm,
         "largest_launch": {"name": dom["name"], "M": dom["M"], "cin": dom["cin"], "cout": dom["cout"],
                            "avg_ms": dom["ms"], "tflops": dom["flops"] / (dom["ms"] / 1e3) / 1e12 if dom["flops"] else None,
                            "traffic": lookup_traffic(dom)},
@@ -385,7 +455,7 @@ def run_ours(args):
                        "achieved_hbm_gbs_algorithmic": algorithmic_bytes_per_cloud() * Bg * args.steps / (total_ms / 1e3) / 1e9},
     })
 
-    cpu_v, cpu_ms, cores, sample = time_cpu_baseline(steps=2, warmup=1, batch=8)
+    cpu = time_cpu_baseline(steps=3, warmup=1, batch=B_PER_GPU, budget_s=30.0)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -393,7 +463,9 @@ def run_ours(args):
         "config": {"workload": WORKLOAD,
                    "global_batch": Bg, "n_points": N_POINTS, "parallelism": f"batch-shard x{world}",
                    "bn": "train-mode batch statistics (per shard), as the reference's unregistered SA layers run",
-                   "collective": "one all-gather of l3 features" if world > 1 else "none",
+                   "collective": ("none" if world == 1 else "one NCCL all-gather of the l3 features, " +
+                                  ("captured inside the replayed graph" if gather_in_graph else "launched after the forward")),
+                   "timed_region": f"{args.steps} steps, {total_ms:.1f} ms of device time in total (CUDA events)",
                    "launch": "eager calls" if graphed is None else "CUDA-graph replay of the captured forward "
                              "(sa_stack.GraphedForward); per-kernel times in roofline.kernels come from eager passes",
                    "l2": "256 MiB buffer rewritten between timed iterations (outside the timed interval)"},
@@ -401,13 +473,186 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(out_h.numel() * 4), "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches),
         "roofline": roofline,
-        "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                         "ms_per_step": cpu_ms},
+        "cpu_baseline": {"value": cpu["value"], "unit": UNIT, "cores": cpu["cores"], "kind": cpu["kind"],
+                         "sample": cpu["sample"], "ms_per_step": cpu["ms"]},
         "clocks": sampler.summary() if sampler else None,
     }
+    line.update(extra)
+    if world == 1 and not args.no_extra:
+        try:
+            line["other_configs"] = other_configs(torch, dev)
+        except Exception as e:  # noqa: BLE001  (the headline line must still print)
+            line["other_configs"] = {"error": f"{type(e).__name__}: {e}"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def extra_modes(torch, dist, pdist, sa_stack, synth, model, dev, rank, world, timed, args):
+    """Two more modes of the same step, reported beside the weak-scaling headline:
+      strong_scaling: BASELINE configs[4] as written -- a FIXED global batch of 256 clouds, 256/N per GPU,
+                      per-shard BatchNorm, CUDA-graph replay + one all-gather;
+      syncbn:         the weak-scaling step with SyncBN (per-layer all-reduce of the [2,C] fp64 statistics, so the
+                      sharded forward equals the unsharded one) -- eager launches, N > 1 only."""
+    out = {}
+    steps, warm = max(3, min(args.steps, 10)), 3
+    GB = 256
+    if GB % world == 0:
+        Bs = GB // world
+        xs = torch.from_numpy(synth.clouds(GB, N_POINTS, seed=100)[rank * Bs:(rank + 1) * Bs]).to(dev)
+        s1 = torch.from_numpy(synth.fps_start(GB, N_POINTS, seed=101)[rank * Bs:(rank + 1) * Bs]).to(dev)
+        s2 = torch.zeros(Bs, dtype=torch.int64, device=dev)
+
+        def fwd(x):
+            f = model(x, None, start_idx=(s1, s2))[1].reshape(Bs, 1024)
+            return pdist.all_gather_features(f) if world > 1 else f
+        try:
+            g = sa_stack.GraphedForward(fwd, xs)
+            fn, how = g.replay, "CUDA-graph replay (all-gather inside the graph)" if world > 1 else "CUDA-graph replay"
+        except Exception:  # noqa: BLE001
+            torch.cuda.synchronize()
+            fn, how = (lambda: fwd(xs)), "eager launches"
+        ms, _ = timed(fn, steps, warm)
+        out["strong_scaling"] = {"global_batch": GB, "clouds_per_gpu": Bs, "steps": steps, "ms_per_step": ms / steps,
+                                 "value": GB * N_POINTS * steps / (ms / 1e3), "unit": UNIT, "launch": how,
+                                 "bn": "train-mode batch statistics per shard"}
+        del xs
+    if world > 1:
+        B = B_PER_GPU
+        xs = torch.from_numpy(synth.clouds(B * world, N_POINTS, seed=0)[rank * B:(rank + 1) * B]).to(dev)
+        s1 = torch.from_numpy(synth.fps_start(B * world, N_POINTS, seed=1)[rank * B:(rank + 1) * B]).to(dev)
+        s2 = torch.zeros(B, dtype=torch.int64, device=dev)
+        pdist.set_sync_bn(model)
+        try:
+            def fwd_sync():
+                f = model(xs, None, start_idx=(s1, s2))[1].reshape(B, 1024)
+                return pdist.all_gather_features(f)
+            ms, _ = timed(fwd_sync, steps, warm)
+            out["syncbn"] = {"global_batch": B * world, "clouds_per_gpu": B, "steps": steps, "ms_per_step": ms / steps,
+                             "value": B * world * N_POINTS * steps / (ms / 1e3), "unit": UNIT,
+                             "launch": "eager launches; 9 all-reduces of [2,C] fp64 sums + one all-gather per step",
+                             "bn": "train-mode statistics of the WHOLE batch (sharded == unsharded, tests/test_gpu_dist.py)"}
+        finally:
+            pdist.set_sync_bn(model, enabled=False)
+    return out
+
+
+def other_configs(torch, dev):
+    """The other single-GPU BASELINE configurations, measured in the same process (N = 1, rank 0) so the driver
+    sees them: C3 = configs[2] (MSG segment SetAbstraction stack, B = 16 x 2048, 3-radius ball query; plus the
+    FeaturePropagation decoder), C4 = configs[3] (PointPillars pillar encode: voxelise -> PillarFeatureNet ->
+    scatter on 20 000-point KITTI-shaped frames).  Device time by CUDA events over back-to-back passes; the CPU
+    figures are the reference's own code on this box's host cores (bounded samples)."""
+    from oracle import build as oracle_build
+    from papc_b200 import pillars, sa_stack, synth
+    out = {}
+
+    def timeit(fn, reps=20, warm=4):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    # ---- C3
+    B, N = 16, 2048
+    xyz = torch.from_numpy(synth.clouds(B, N, seed=0)).to(dev)
+    st1 = torch.from_numpy(synth.fps_start(B, N, seed=1)).to(dev)
+    st2 = torch.zeros(B, dtype=torch.int64, device=dev)
+    msg = sa_stack.MSGSegSetAbstractionStack().to(dev)
+    try:
+        g = sa_stack.GraphedForward(lambda x: msg(x, x, start_idx=(st1, st2))[1], xyz)
+        ms, how = timeit(g.replay), "CUDA-graph replay"
+    except Exception:  # noqa: BLE001
+        torch.cuda.synchronize()
+        ms, how = timeit(lambda: msg(xyz, xyz, start_idx=(st1, st2))), "eager launches"
+    c3 = {"workload": "PointNet++MSG segment SetAbstraction stack sa1+sa2+sa3, B=16 x 2048 points (BASELINE configs[2])",
+          "ms_per_forward": ms, "value": B * N / (ms / 1e3), "unit": UNIT, "launch": how,
+          "algorithmic_gflop": 142.6, "tflops": 142.6e9 / (ms / 1e3) / 1e12}
+    seg = sa_stack.MSGSegEncoderDecoder().to(dev)
+    onehot = torch.zeros((B, 16, N), device=dev)
+    onehot[:, 3, :] = 1.0
+    ms2 = timeit(lambda: seg(xyz, onehot, start_idx=(st1, st2)), reps=10)
+    c3["with_feature_propagation_decoder"] = {"ms_per_forward": ms2, "value": B * N / (ms2 / 1e3), "unit": UNIT,
+                                              "launch": "eager launches"}
+    try:
+        _host_threads()
+        step, kind, what = cpu_reference_factory(2, n_points=N, msg=True)
+        step()
+        t0 = time.perf_counter()
+        step()
+        dt = time.perf_counter() - t0
+        c3["cpu_baseline"] = {"value": 2 * N / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": kind,
+                              "sample": f"1 timed pass (after 1 warm-up) over 2 of the 16 clouds: {what}"}
+    except Exception as e:  # noqa: BLE001
+        c3["cpu_baseline"] = {"error": f"{type(e).__name__}: {e}"}
+    out["C3_msg_segment"] = c3
+    del msg, seg, xyz, onehot
+
+    # ---- C4
+    NF, PTS = 4, 20000
+    frames_np = [synth.lidar_frame(PTS, seed=s) for s in range(NF)]
+    frames = [torch.from_numpy(f).to(dev) for f in frames_np]
+    vs, rg, T, MV = synth.KITTI_VOXEL_SIZE, synth.KITTI_PC_RANGE, synth.KITTI_MAX_POINTS, synth.KITTI_MAX_VOXELS
+    pfn = pillars.PillarFeatureNet(num_input_features=4, use_norm=True, num_filters=(64,), with_distance=False,
+                                   voxel_size=vs, pc_range=rg).to(dev)
+    scatter = pillars.PointPillarsScatter(output_shape=[1, 1, 496, 432], num_input_features=64)
+
+    def encode_batch():   # one device call voxelises the whole batch into the merged layout, then PFN + scatter
+        v, c, n, fv, total = pillars.points_to_voxel_batch_device(frames, vs, rg, T, True, MV)
+        feats = pfn(v, n, c, num_valid=total)
+        return scatter(feats, c, NF, num_valid=total)
+
+    def encode_frame():
+        v, c, n, vn = pillars.points_to_voxel_device(frames[0], vs, rg, T, True, MV)
+        return v, c, n, vn
+
+    c4 = {"workload": f"PointPillars pillar encode, {PTS}-point KITTI-shaped frames, yaml geometry 0.16 m pillars, "
+                      f"max {T} points x {MV} pillars (BASELINE configs[3])"}
+    try:
+        try:
+            g = sa_stack.GraphedForward(lambda *_: encode_batch(), frames[0])
+            ms, how = timeit(g.replay), "CUDA-graph replay"
+        except Exception:  # noqa: BLE001
+            torch.cuda.synchronize()
+            ms, how = timeit(encode_batch), "eager launches"
+        bytes_frame = 4.0 * PTS * 4 + 12000 * (T * 4 * 4 + 16 + 4) + 12000 * 64 * 4 + 64 * 496 * 432 * 4
+        c4["encode_voxelise_pfn_scatter"] = {"frames_per_call": NF, "ms_per_frame": ms / NF, "value": PTS * NF / (ms / 1e3),
+                                             "unit": UNIT, "launch": how,
+                                             "hbm_gbs_algorithmic": bytes_frame * NF / (ms / 1e3) / 1e9,
+                                             "algorithmic_bytes_per_frame": bytes_frame}
+    except Exception as e:  # noqa: BLE001
+        torch.cuda.synchronize()
+        c4["encode_voxelise_pfn_scatter"] = {"error": f"{type(e).__name__}: {e}"}
+    msv = timeit(encode_frame)
+    c4["voxelise_single_frame_call"] = {"ms_per_frame": msv, "value": PTS / (msv / 1e3), "unit": UNIT}
+    ref = oracle_build.ref_file("point_cloud_ops.py")
+    if ref is not None:
+        try:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("papc_ref_point_cloud_ops", ref)
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            mod.points_to_voxel(frames_np[0], vs, rg, T, True, MV)   # numba JIT
+            t = []
+            for f in frames_np:
+                t0 = time.perf_counter()
+                mod.points_to_voxel(f, vs, rg, T, True, MV)
+                t.append(time.perf_counter() - t0)
+            c4["cpu_baseline"] = {"value": PTS / float(np.mean(t)), "unit": UNIT, "cores": 1, "kind": "reference",
+                                  "ms_per_frame": 1e3 * float(np.mean(t)),
+                                  "sample": f"{NF} frames through the reference's own numba points_to_voxel "
+                                            "(point_cloud_ops.py, unmodified, oracle/_ref), after the JIT warm-up; "
+                                            "voxelisation only (its PFN / scatter are Paddle ops)"}
+        except Exception as e:  # noqa: BLE001
+            c4["cpu_baseline"] = {"error": f"{type(e).__name__}: {e}"}
+    out["C4_pillar_encode"] = c4
+    return out
 
 
 def profile_kernels(torch, lib, L, step_fn, flush, steps):
@@ -535,6 +780,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="time eager calls instead of CUDA-graph replays")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="skip the strong-scaling / SyncBN / other-config blocks (headline numbers only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -177,6 +177,8 @@ def f32c(t):
     """Contiguous float32 view/copy of a CUDA tensor."""
     if t is None:
         return None
+    if type(t) is not torch.Tensor:   # e.g. the paddle facade's Tensor subclass (papc_b200.compat): plain view
+        t = t.as_subclass(torch.Tensor)
     if t.dtype != torch.float32:
         t = t.float()
     return t.contiguous()

@@ -70,7 +70,12 @@ def index_points(points, idx, strict=False):
     return out
 
 
+_START_QUEUE = []   # seeded draws for layers called WITHOUT start_idx (papc_b200.compat.queue_fps_starts)
+
+
 def _draw_start(B, N, device, start_idx):
+    if start_idx is None and _START_QUEUE:
+        start_idx = _START_QUEUE.pop(0)
     if start_idx is None:
         return torch.randint(0, N, (B,), device=device, dtype=torch.int64)  # layers.py:76
     s = torch.as_tensor(start_idx, device=device).to(torch.int64).reshape(B).contiguous()
@@ -295,12 +300,16 @@ def _ready_event(t):
     return ev if t._version == version else None
 
 
+DEFAULT_DEVICE = None   # device of freshly built parameter holders (None = CPU until .to(); compat.install sets cuda)
+
+
 class Conv2D:
     """Parameter holder mirroring ``paddle.nn.Conv2D(cin, cout, 1)``: weight [cout,cin,1,1], bias
     [cout].  Default init as Paddle: Normal(0, sqrt(2/fan_in)) weight, zero bias."""
 
     def __init__(self, in_channels, out_channels, kernel_size=1, device=None, generator=None):
         assert kernel_size == 1
+        device = DEFAULT_DEVICE if device is None else device
         std = math.sqrt(2.0 / in_channels)
         self.weight = (torch.randn((out_channels, in_channels, 1, 1), generator=generator) * std).to(device)
         self.bias = torch.zeros((out_channels,), device=device)
@@ -314,6 +323,7 @@ class BatchNorm2D:
     weight/bias and the running ``_mean`` / ``_variance`` under Paddle's attribute names."""
 
     def __init__(self, num_features, momentum=0.9, epsilon=1e-5, device=None):
+        device = DEFAULT_DEVICE if device is None else device
         self.weight = torch.ones((num_features,), device=device)
         self.bias = torch.zeros((num_features,), device=device)
         self._mean = torch.zeros((num_features,), device=device)

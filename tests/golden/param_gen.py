@@ -52,6 +52,10 @@ def install(model, prefix, wrap=lambda a: a):
         for name, sub in list(vars(obj).items()):
             if name.startswith("_sub"):
                 continue
+            if name == "_modules" and isinstance(sub, dict):              # torch.nn.Module registry (the facade)
+                for k, m in sub.items():
+                    visit(m, f"{path}.{k}")
+                continue
             if isinstance(sub, (type, types.FunctionType, types.MethodType, types.BuiltinFunctionType)):
                 continue                                                  # dtypes, functions
             if isinstance(sub, (list, tuple)) or (hasattr(sub, "__dict__") and not isinstance(sub, np.ndarray)
