@@ -379,10 +379,17 @@ def run_ours(args):
     #      its launching stream by the library's launch profiler (papc_prof_*), same step function
     kernels = profile_kernels(torch, lib, _lib, step_eager, flush, min(args.steps, 10))
 
+    if world > 1:
+        # Leave together and WITHOUT destroy_process_group: tearing the communicator down while captured graphs
+        # still hold NCCL nodes hung the 2-GPU run (the line was printed, the process never exited).
+        graphed = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
     peaks = {}
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -485,7 +492,9 @@ def run_ours(args):
             line["other_configs"] = {"error": f"{type(e).__name__}: {e}"}
     print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def extra_modes(torch, dist, pdist, sa_stack, synth, model, dev, rank, world, timed, args):
