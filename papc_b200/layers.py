@@ -246,26 +246,49 @@ def _side_stream(device):
     return _SIDE_STREAMS[key]
 
 
+_KEEPALIVE = {}    # device -> buffers of the most recent side-stream sampling (see _sample)
+
+
+def precede(t):
+    """Mark a CUDA tensor (e.g. a ``start_idx``) as complete at THIS point of the current stream: an event is
+    recorded and attached, and an overlapped layer waits for exactly that event instead of for everything the
+    main stream has been given so far (which would include the previous layer's MLP and undo the overlap)."""
+    if isinstance(t, torch.Tensor) and t.is_cuda:
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(t.device))
+        t._papc_ev = ev
+    return t
+
+
 def _sample(xyz, ready, npoint, start_idx, queries):
     """FPS + one ball query per (radius, nsample) in ``queries`` -> (new_xyz, [idx int32...], event
-    recorded right after the FPS).  Runs on the side stream when ``ready`` (the producer's event) is set.
+    recorded right after the FPS).  Runs on the side stream when ``ready`` -- the producer layer's
+    (FPS-done event, entry event) pair -- is set, so that the sampling of layer n+1 overlaps the MLP of layer n.
 
-    Stream safety.  The side stream first waits for an event recorded on the main stream at entry, so
-    (a) a caller-supplied ``start_idx`` (or any other main-stream tensor) is complete before the side
-    stream reads it, and (b) every buffer the side stream's allocator pool hands out again was last
-    used by main-stream work enqueued before this point.  The buffers allocated here are consumed by
-    main-stream kernels after this call returns, so they are ``record_stream``-ed to the main stream:
-    the caching allocator then defers their reuse until that work has run (three or more chained
-    sampled layers, or repeated calls, would otherwise let a later side-stream allocation overwrite
-    indices an earlier layer's MLP is still reading)."""
+    Stream safety without giving the overlap up:
+      * the side stream waits for the producer's FPS (``ready[0]``) and for the producer layer's ENTRY event
+        (``ready[1]``, recorded on the main stream before the producer enqueued its MLP): everything the main
+        stream did before the producer layer is complete, the producer's own MLP is not waited for;
+      * a CUDA ``start_idx`` is waited for through the event ``precede()`` attached to it (the stacks / models
+        attach one at their entry); an unmarked one falls back to waiting for the main stream as it is now;
+      * buffers allocated here are read by main-stream kernels after this call returns: outside a capture
+        they are ``record_stream``-ed to the main stream (the allocator defers their reuse); in every mode the
+        most recent sampling's buffers are also kept alive until the NEXT overlapped sampling has made its
+        allocations, and that one waits for this layer's entry event, i.e. for the MLP that read them."""
     dev = xyz.device
     main = torch.cuda.current_stream(dev)
     if ready is not None and OVERLAP_SAMPLING:
         side = _side_stream(dev)
-        entry = torch.cuda.Event()
-        entry.record(main)
-        side.wait_event(entry)
-        side.wait_event(ready)
+        ready_ev, entry_ev = ready
+        if entry_ev is not None:
+            side.wait_event(entry_ev)
+        if isinstance(start_idx, torch.Tensor) and start_idx.is_cuda:
+            ev0 = getattr(start_idx, "_papc_ev", None)
+            if ev0 is None:
+                ev0 = torch.cuda.Event()
+                ev0.record(main)           # conservative: everything enqueued on main so far
+            side.wait_event(ev0)
+        side.wait_event(ready_ev)
         with torch.cuda.stream(side):
             _, new_xyz = farthest_point_sample_idx(xyz, npoint, start_idx, return_xyz=True)
             ev = torch.cuda.Event()
@@ -277,6 +300,7 @@ def _sample(xyz, ready, npoint, start_idx, queries):
         if not torch.cuda.is_current_stream_capturing():
             for t in [new_xyz] + idxs:
                 t.record_stream(main)
+        _KEEPALIVE[dev] = [new_xyz] + idxs
         return new_xyz, idxs, ev
     _, new_xyz = farthest_point_sample_idx(xyz, npoint, start_idx, return_xyz=True)
     ev = torch.cuda.Event()
@@ -285,10 +309,17 @@ def _sample(xyz, ready, npoint, start_idx, queries):
     return new_xyz, idxs, ev
 
 
-def _tag_ready(t, ev):
-    """Attach the producer's event (and the tensor's version counter: an in-place modification by the
+def _entry_event(dev):
+    """Recorded on the main stream when a sampled layer is entered (before its MLP is enqueued)."""
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(dev))
+    return ev
+
+
+def _tag_ready(t, ev, entry_ev=None):
+    """Attach the producer's events (and the tensor's version counter: an in-place modification by the
     caller after the layer returned invalidates the tag, see ``_ready_event``)."""
-    t._papc_ready = (ev, t._version)
+    t._papc_ready = (ev, entry_ev, t._version)
     return t
 
 
@@ -296,8 +327,8 @@ def _ready_event(t):
     tag = getattr(t, "_papc_ready", None)
     if tag is None:
         return None
-    ev, version = tag
-    return ev if t._version == version else None
+    ev, entry_ev, version = tag
+    return (ev, entry_ev) if t._version == version else None
 
 
 DEFAULT_DEVICE = None   # device of freshly built parameter holders (None = CPU until .to(); compat.install sets cuda)
@@ -530,6 +561,7 @@ class PointNetSetAbstraction(_SAMixin):
         """xyz [B,3,N], points [B,D,N] | None -> (new_xyz [B,3,S], new_points [B,D',S])."""
         L.require_cuda(xyz, points)
         ready = _ready_event(xyz)
+        entry_ev = _entry_event(xyz.device) if not self.group_all else None
         xyz = L.f32c(xyz.transpose(1, 2))                                  # :203
         feats = L.f32c(points.transpose(1, 2)) if points is not None else None  # :205
         B, N, Cc = xyz.shape
@@ -555,7 +587,7 @@ class PointNetSetAbstraction(_SAMixin):
             src, keep, 3 + D, B, S, self.bn_mode, dev, self.update_running_stats, self._sync_group())
         out_xyz = new_xyz.transpose(1, 2)
         if not self.group_all:
-            _tag_ready(out_xyz, ev)
+            _tag_ready(out_xyz, ev, entry_ev)
         return out_xyz, out.transpose(1, 2)                                # :220-221
 
 
@@ -586,6 +618,7 @@ class PointNetSetAbstractionMsg(_SAMixin):
     def forward(self, xyz, points, start_idx=None):
         L.require_cuda(xyz, points)
         ready = _ready_event(xyz)
+        entry_ev = _entry_event(xyz.device)
         xyz = L.f32c(xyz.transpose(1, 2))
         feats = L.f32c(points.transpose(1, 2)) if points is not None else None
         B, N, Cc = xyz.shape
@@ -607,7 +640,7 @@ class PointNetSetAbstractionMsg(_SAMixin):
                 src, (xyz, feats, new_xyz, idx), 3 + D, B, S, self.bn_mode, dev,
                 self.update_running_stats, self._sync_group()))
         new_points_concat = torch.cat(outs, dim=2)                                   # :280 (channels-last)
-        return _tag_ready(new_xyz.transpose(1, 2), ev), new_points_concat.transpose(1, 2)
+        return _tag_ready(new_xyz.transpose(1, 2), ev, entry_ev), new_points_concat.transpose(1, 2)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -28,7 +28,7 @@ import torch
 
 from . import _lib as L
 from .layers import (BatchNorm1DLayer, Conv1DLayer, PointNetFeaturePropagation, PointNetSetAbstraction,
-                     PointNetSetAbstractionMsg, _SAMixin, pointwise_mlp_rows)
+                     PointNetSetAbstractionMsg, _SAMixin, pointwise_mlp_rows, precede)
 
 
 def Categorical(y, num_class=16, device=None):
@@ -107,6 +107,7 @@ class PointNet2_SSG_Clas(_ClsHead):
     def forward(self, inputs, start_idx=(None, None)):
         xyz, norm = self._split(inputs)
         B = xyz.shape[0]
+        precede(start_idx[1])
         l1_xyz, l1_points = self.sa1(xyz, norm, start_idx=start_idx[0])
         l2_xyz, l2_points = self.sa2(l1_xyz, l1_points, start_idx=start_idx[1])
         l3_xyz, l3_points = self.sa3(l2_xyz, l2_points)
@@ -169,6 +170,7 @@ class _SegHead(_SAMixin):
 
     def forward(self, inputs, start_idx=(None, None)):
         B, N, l0_xyz, l0_points, cls_label = self._inputs(inputs)
+        precede(start_idx[1])
         l1_xyz, l1_points = self.sa1(l0_xyz, l0_points, start_idx=start_idx[0])
         l2_xyz, l2_points = self.sa2(l1_xyz, l1_points, start_idx=start_idx[1])
         l3_xyz, l3_points = self.sa3(l2_xyz, l2_points)

@@ -8,7 +8,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from .layers import PointNetFeaturePropagation, PointNetSetAbstraction, PointNetSetAbstractionMsg
+from .layers import PointNetFeaturePropagation, PointNetSetAbstraction, PointNetSetAbstractionMsg, precede
 
 
 def load_conv_bn(convs, bns, params):
@@ -37,6 +37,7 @@ class SSGSetAbstractionStack(torch.nn.Module):
         return [self.sa1, self.sa2, self.sa3]
 
     def forward(self, xyz, norm=None, start_idx=(None, None)):
+        precede(start_idx[1])   # ready here, before sa1 is enqueued: sa2's overlapped sampling waits for this only
         l1_xyz, l1_points = self.sa1(xyz, norm, start_idx=start_idx[0])
         l2_xyz, l2_points = self.sa2(l1_xyz, l1_points, start_idx=start_idx[1])
         l3_xyz, l3_points = self.sa3(l2_xyz, l2_points)
@@ -56,6 +57,7 @@ class MSGSegSetAbstractionStack(torch.nn.Module):
                                           mlp=[256, 512, 1024], group_all=True)
 
     def forward(self, xyz, points, start_idx=(None, None)):
+        precede(start_idx[1])
         l1_xyz, l1_points = self.sa1(xyz, points, start_idx=start_idx[0])
         l2_xyz, l2_points = self.sa2(l1_xyz, l1_points, start_idx=start_idx[1])
         l3_xyz, l3_points = self.sa3(l2_xyz, l2_points)
@@ -77,6 +79,7 @@ class MSGSegEncoderDecoder(torch.nn.Module):
 
     def forward(self, xyz, cls_one_hot, start_idx=(None, None)):
         l0_xyz, l0_points = xyz, xyz
+        precede(start_idx[1])
         l1_xyz, l1_points = self.enc.sa1(l0_xyz, l0_points, start_idx=start_idx[0])
         l2_xyz, l2_points = self.enc.sa2(l1_xyz, l1_points, start_idx=start_idx[1])
         l3_xyz, l3_points = self.enc.sa3(l2_xyz, l2_points)
