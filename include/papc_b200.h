@@ -108,6 +108,25 @@ int papc_ball_query_f32(const float *xyz, const float *new_xyz, int B, int N, in
                         float radius2, int nsample, void *out_idx, int idx_bits,
                         int32_t *empty_count, papc_stream_t stream);
 
+/* A3 + A4 + the grouping statistics in ONE launch      layers.py:143-146 (sample_and_group's first three calls)
+ *     farthest_point_sample -> index_points -> query_ball_point for one radius, with the ball query of
+ *     centroid i running (on other SMs) while the FPS recurrence is still producing centroid i+1...: results
+ *     are bit-identical to papc_fps_f32 followed by papc_ball_query_f32 (idx_bits 32).  out_fps_idx [B,npoint]
+ *     int64, out_new_xyz [B,npoint,3], out_group_idx [B,npoint,nsample] int32; moments_partial (nullable)
+ *     [papc_sample_group_parts(...) * B][9] doubles for papc_group_source.xyz_moments.
+ *     papc_sample_group_parts returns the number of consumer CTAs per cloud, or 0 when the shape does not run
+ *     fused (256 < N <= 1024 and B + B*parts <= 148 SMs are required: every CTA must be co-resident) -- then
+ *     papc_sample_group_f32 returns PAPC_EUNSUPPORTED and the caller uses the two separate entry points.
+ *     workspace: papc_sample_group_workspace_bytes(B, npoint).
+ */
+int papc_sample_group_parts(int B, int N, int npoint, int nsample);
+size_t papc_sample_group_workspace_bytes(int B, int npoint);
+int papc_sample_group_f32(const float *xyz, int B, int N, int npoint, const int64_t *start_idx,
+                          float init_dist, float radius2, int nsample, int64_t *out_fps_idx,
+                          float *out_new_xyz, int32_t *out_group_idx, int32_t *empty_count,
+                          double *moments_partial, void *workspace, size_t workspace_bytes,
+                          papc_stream_t stream);
+
 /* A4 (several radii)  the per-radius query_ball_point calls of PointNetSetAbstractionMsg   layers.py:258-267
  *     One pass over the cloud per centroid evaluates every distance once and fills R (<= 4) index lists:
  *     out_idx_host[r] -> [B,S,nsample_host[r]] with radius2_host[r]; results identical to R calls of
@@ -162,6 +181,9 @@ typedef struct papc_group_source {
     const int32_t *idx;   /* [B,S,K] int32, or NULL = identity (group_all: row k = point k)  */
     int32_t B, N, S, K, D;
     int32_t order;        /* PAPC_XYZ_FIRST / PAPC_FEATS_FIRST                               */
+    const double *xyz_moments; /* nullable: [xyz_moment_rows][9] partial sums (x, y, z, xx, xy, xz, yy, yz, zz)  */
+    int32_t xyz_moment_rows;   /* of the centred grouped points over all M rows, as papc_sample_group_f32      */
+    int32_t reserved;          /* writes them: the folded first layer (D = 0) then skips its own gather pass    */
 } papc_group_source;
 
 typedef struct papc_mlp_layer {

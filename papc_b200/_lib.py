@@ -29,7 +29,8 @@ _vp = C.c_void_p
 class GroupSource(C.Structure):
     _fields_ = [("grouped", _vp), ("xyz", _vp), ("new_xyz", _vp), ("feats", _vp), ("idx", _vp),
                 ("B", C.c_int32), ("N", C.c_int32), ("S", C.c_int32), ("K", C.c_int32),
-                ("D", C.c_int32), ("order", C.c_int32)]
+                ("D", C.c_int32), ("order", C.c_int32),
+                ("xyz_moments", _vp), ("xyz_moment_rows", C.c_int32), ("reserved", C.c_int32)]
 
 
 class MlpLayer(C.Structure):
@@ -65,6 +66,9 @@ _SIGNATURES = {
     "papc_gather_f32": (_I, [_vp, _vp, _I, _I, _I, _I, _vp, _vp]),
     "papc_fps_workspace_bytes": (_SZ, [_I, _I]),
     "papc_fps_f32": (_I, [_vp, _I, _I, _I, _vp, _F, _vp, _vp, _vp, _SZ, _vp]),
+    "papc_sample_group_parts": (_I, [_I, _I, _I, _I]),
+    "papc_sample_group_workspace_bytes": (_SZ, [_I, _I]),
+    "papc_sample_group_f32": (_I, [_vp, _I, _I, _I, _vp, _F, _F, _I, _vp, _vp, _vp, _vp, _vp, _vp, _SZ, _vp]),
     "papc_ball_query_f32": (_I, [_vp, _vp, _I, _I, _I, _F, _I, _vp, _I, _vp, _vp]),
     "papc_ball_query_multi_f32": (_I, [_vp, _vp, _I, _I, _I, _I, C.POINTER(_F), C.POINTER(C.c_int32),
                                         C.POINTER(C.c_void_p), _I, _vp, _vp]),

@@ -74,11 +74,21 @@ __device__ __forceinline__ uint64_t f2mul(uint64_t a, uint64_t b) {
 
 // DBG (timing experiments only, results are wrong): 1 = no cross-warp exchange, 2 = no warp redux /
 // ballot either, 4 = no centroid LDS dependency
-template <int THREADS, int PPT, int DBG = 0>
-__global__ void __launch_bounds__(THREADS)
-fps_reg_kernel(const float *__restrict__ xyz, int N, int npoint,
-               const int64_t *__restrict__ start_idx, float init_dist,
-               int64_t *__restrict__ out_idx, float *__restrict__ out_new_xyz) {
+// PUB: every pick is also stored to pub[it] (global, relaxed) the moment it is known, so that the consumer
+// CTAs of sample_group_kernel can run the ball query of centroid `it` while the recurrence continues.
+// CTA-wide barrier of the FPS role: the whole CTA, or -- inside sample_group_kernel, whose CTAs carry more
+// warps than the FPS role uses -- named barrier 1 over the role's THREADS threads.
+template <int THREADS, bool NAMED>
+__device__ __forceinline__ void fps_sync() {
+    if (NAMED) asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
+    else __syncthreads();
+}
+
+template <int THREADS, int PPT, int DBG, bool PUB>
+__device__ __forceinline__ void
+fps_reg_body(const int b, const float *__restrict__ xyz, int N, int npoint,
+             const int64_t *__restrict__ start_idx, float init_dist,
+             int64_t *__restrict__ out_idx, float *__restrict__ out_new_xyz, int32_t *__restrict__ pub) {
     static_assert(PPT % 2 == 0, "points are processed in packed pairs");
     extern __shared__ float4 s_xyz4[];  // [N] (x, y, z, 0): one LDS.128 fetches a centroid
     int *s_out = reinterpret_cast<int *>(s_xyz4 + N);  // [min(npoint, kFpsOutCap)] picks awaiting the flush
@@ -87,7 +97,6 @@ fps_reg_kernel(const float *__restrict__ xyz, int N, int npoint,
     constexpr int NWP = NW > 1 ? NW : 2;
     __shared__ __align__(16) int2 s_red[2][NWP];  // per warp: (distance bits, point index)
 
-    const int b = blockIdx.x;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
@@ -95,7 +104,7 @@ fps_reg_kernel(const float *__restrict__ xyz, int N, int npoint,
 
     for (int i = tid; i < N; i += THREADS)
         s_xyz4[i] = make_float4(cloud[i * 3 + 0], cloud[i * 3 + 1], cloud[i * 3 + 2], 0.f);
-    __syncthreads();
+    fps_sync<THREADS, PUB>();
 
     uint64_t px[PP], py[PP], pz[PP];
     float pd[PPT];
@@ -131,7 +140,7 @@ fps_reg_kernel(const float *__restrict__ xyz, int N, int npoint,
         s_addr[1] = fps_smem_u32(&s_red[0][0]);
         s_addr[2] = fps_smem_u32(s_out);
     }
-    __syncthreads();
+    fps_sync<THREADS, PUB>();
     uint32_t xyz_sa, red_sa, out_sa;
     asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(out_sa) : "r"(fps_smem_u32(&s_addr[2])) : "memory");
     asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(xyz_sa) : "r"(fps_smem_u32(&s_addr[0])) : "memory");
@@ -140,7 +149,7 @@ fps_reg_kernel(const float *__restrict__ xyz, int N, int npoint,
     int64_t *out = out_idx + (size_t)b * npoint;
     float *oxyz = out_new_xyz != nullptr ? out_new_xyz + (size_t)b * npoint * 3 : nullptr;
     auto flush = [&](int base, int n) {  // picks [base, base+n) -> global (all threads)
-        __syncthreads();
+        fps_sync<THREADS, PUB>();
         for (int i = tid; i < n; i += THREADS) out[base + i] = s_out[i];
         if (oxyz != nullptr)
             for (int i = tid; i < n * 3; i += THREADS) {
@@ -148,9 +157,11 @@ fps_reg_kernel(const float *__restrict__ xyz, int N, int npoint,
                 const float4 v = s_xyz4[s_out[pt]];
                 oxyz[(size_t)base * 3 + i] = d == 0 ? v.x : (d == 1 ? v.y : v.z);
             }
-        __syncthreads();
+        fps_sync<THREADS, PUB>();
     };
 
+    int32_t *pub_ptr = pub;
+    const uint32_t is_pub = (PUB && tid == THREADS - 1) ? 1u : 0u;
     for (int it = 0; it < npoint; ++it) {
         const float4 c = fps_lds128f(xyz_sa + 16u * (uint32_t)((DBG & 4) ? (it & 1023) : far));
         const uint32_t red_it = red_sa + (uint32_t)(it & 1) * (NWP * 8);
@@ -159,6 +170,14 @@ fps_reg_kernel(const float *__restrict__ xyz, int N, int npoint,
         if (tid == 0)
             asm volatile("st.shared.u32 [%0], %1;" ::"r"(out_sa + 4u * (uint32_t)(it & (kFpsOutCap - 1))), "r"(far)
                          : "memory");
+        // the last warp's spare lane publishes the pick: ONE predicated store through a per-thread running pointer
+        // (an `if` here became a divergent branch with a reconvergence barrier at the head of every iteration and
+        // cost 20 % of the recurrence).  A weak store: the consumers only ever need the 4-byte value itself.
+        if (PUB) {
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.global.s32 [%0], %1;\n\t}"
+                         ::"l"(pub_ptr), "r"(far), "r"(is_pub) : "memory");
+            ++pub_ptr;
+        }
         if (it == npoint - 1) break;  // the reference's last argmax is discarded (:93 after :80)
         if ((it & (kFpsOutCap - 1)) == kFpsOutCap - 1) flush(it + 1 - kFpsOutCap, kFpsOutCap);  // rare
         const uint64_t ncx = f2pack(-c.x, -c.x), ncy = f2pack(-c.y, -c.y), ncz = f2pack(-c.z, -c.z);
@@ -207,7 +226,7 @@ fps_reg_kernel(const float *__restrict__ xyz, int N, int npoint,
         } else {
             if (mine && (ball & lt_mask) == 0u)  // lowest lane holding the warp maximum
                 fps_sts64i(red_it + 8u * warp, wmax, tid * PPT + bi);
-            __syncthreads();
+            fps_sync<THREADS, PUB>();
             if (NW <= 8) {
                 // every thread reduces all warps' candidates itself: broadcast LDS.128 (two
                 // candidates each), fixed tree, the lower warp (= lower indices) wins ties
@@ -237,6 +256,138 @@ fps_reg_kernel(const float *__restrict__ xyz, int N, int npoint,
         }
     }
     flush((npoint - 1) & ~(kFpsOutCap - 1), ((npoint - 1) & (kFpsOutCap - 1)) + 1);
+}
+
+template <int THREADS, int PPT, int DBG = 0>
+__global__ void __launch_bounds__(THREADS)
+fps_reg_kernel(const float *__restrict__ xyz, int N, int npoint,
+               const int64_t *__restrict__ start_idx, float init_dist,
+               int64_t *__restrict__ out_idx, float *__restrict__ out_new_xyz) {
+    fps_reg_body<THREADS, PPT, DBG, false>(blockIdx.x, xyz, N, npoint, start_idx, init_dist, out_idx, out_new_xyz, nullptr);
+}
+
+// ------------------------------------------------------------------ FPS + ball query + moments in ONE launch
+// sample_and_group's three dependent stages (layers.py:143-146) for the SetAbstraction layers: CTAs [0, B) run
+// the FPS recurrence (one per cloud, exactly fps_reg_kernel) and publish every pick as it is made; CTAs
+// [B, B + B*P) are consumers -- P per cloud, the cloud staged once in shared memory as (x, y, z, |p|^2) -- whose
+// warps take the centroids of their cloud round-robin, wait for the pick, and run query_ball_point for it
+// (the same in-order ballot / popcount scan as ball_query_kernel) while the recurrence is still going.  The
+// in-radius points are in registers at that moment, so the nine second-moment sums of the centred neighbours
+// that the folded first MLP layer needs (MomentArgs, sa_mlp_tt.cuh) are accumulated on the way: the separate
+// 15 us gather pass and all but the last few microseconds of the 30 us ball query leave the critical path.
+// All CTAs are co-resident (host: B + B*P <= number of SMs) and the FPS CTAs have the lowest block indices, so
+// the consumers' spin-waits cannot starve a producer.
+constexpr int kSgThreads = 512;   // consumer CTAs: 16 warps hide the scan's shared-memory latency
+constexpr int kSgFpsThreads = 128;  // the FPS role uses the first four warps of its CTA (the rest exit at once)
+
+template <int PPT>
+__global__ void __launch_bounds__(kSgThreads)
+sample_group_kernel(const float *__restrict__ xyz, int B, int N, int npoint, const int64_t *__restrict__ start_idx,
+                    float init_dist, int64_t *__restrict__ out_idx, float *__restrict__ out_new_xyz,
+                    int32_t *__restrict__ pub, int P, float radius2, int K, int32_t *__restrict__ grp_idx,
+                    int32_t *__restrict__ empty_count, double *__restrict__ mom_partial, int dbg) {
+    if ((int)blockIdx.x < B) {
+        if (threadIdx.x >= kSgFpsThreads) return;
+        fps_reg_body<kSgFpsThreads, PPT, 0, true>(blockIdx.x, xyz, N, npoint, start_idx, init_dist, out_idx, out_new_xyz,
+                                               pub + (size_t)blockIdx.x * npoint);
+        return;
+    }
+    extern __shared__ float4 s_q[];   // [N] (x, y, z, |p|^2)
+    __shared__ double s_red[kSgThreads / 32][9];
+    const int c = (int)blockIdx.x - B;
+    const int b = c / P, part = c - b * P;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *cloud = xyz + (size_t)b * N * 3;
+    for (int j = tid; j < N; j += kSgThreads) {
+        const float x = cloud[j * 3 + 0], y = cloud[j * 3 + 1], z = cloud[j * 3 + 2];
+        s_q[j] = make_float4(x, y, z, sq3(x, y, z));
+    }
+    __syncthreads();
+    const int32_t *picks = pub + (size_t)b * npoint;
+    constexpr int NW = kSgThreads / 32;
+#ifdef PAPC_TRIAGE
+    if (dbg & 1) return;   // timing experiment: producers only
+#endif
+    double dacc[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) dacc[i] = 0.0;
+    for (int s = part * NW + warp; s < npoint; s += NW * P) {
+        int pick = 0;
+        if (lane == 0) {
+            for (uint32_t spin = 0;; ++spin) {
+                asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(pick) : "l"(picks + s) : "memory");
+                if (pick >= 0) break;
+                __nanosleep(100);
+                if (spin > (1u << 24)) __trap();   // a lost producer traps instead of hanging the GPU
+            }
+        }
+        pick = __shfl_sync(0xffffffffu, pick, 0);
+#ifdef PAPC_TRIAGE
+        if (dbg & 2) continue;   // timing experiment: wait for the picks, no scan
+#endif
+        const float4 q = s_q[pick];
+        int32_t *out = grp_idx + ((size_t)b * npoint + s) * K;
+        int cnt = 0, first = -1;
+        // in-order scan, 64 points per trip: both loads and both distances are in flight before the first ballot
+        for (int j0 = 0; j0 < N && cnt < K; j0 += 64) {
+            const int ja = j0 + lane, jb = j0 + 32 + lane;
+            const float4 pa = s_q[ja < N ? ja : 0], pb = s_q[jb < N ? jb : 0];
+            const float da = sqdist_expanded(q.x, q.y, q.z, q.w, pa.x, pa.y, pa.z, pa.w);
+            const float db = sqdist_expanded(q.x, q.y, q.z, q.w, pb.x, pb.y, pb.z, pb.w);
+            const bool ina = ja < N && !(da > radius2);   // layers.py:112 masks "> r^2" OUT
+            const bool inb = jb < N && !(db > radius2);
+            const unsigned ma = __ballot_sync(0xffffffffu, ina);
+            const unsigned mb = __ballot_sync(0xffffffffu, inb);
+            if (ma | mb) {
+                if (first < 0) first = ma ? j0 + __ffs(ma) - 1 : j0 + 32 + __ffs(mb) - 1;
+                const unsigned lt = (1u << lane) - 1u;
+                const int posa = cnt + __popc(ma & lt);
+                if (ina && posa < K) out[posa] = ja;
+                cnt += __popc(ma);
+                const int posb = cnt + __popc(mb & lt);
+                if (inb && posb < K) out[posb] = jb;
+                cnt += __popc(mb);
+            }
+        }
+        const int have = min(cnt, K);
+        const int pad = cnt > 0 ? first : N;   // empty ball: N in every slot, as the sort leaves it
+        for (int k = have + lane; k < K; k += 32) out[k] = pad;
+        if (lane == 0 && cnt == 0 && empty_count != nullptr) atomicAdd(empty_count, 1);
+        __syncwarp();   // the warp's own index writes are visible to all of its lanes
+        // second moments of the K centred neighbours (padding rows included; an empty ball's N clamps to N-1
+        // exactly as the MLP's gather does): every lane takes rows lane, lane+32, ...
+        float f[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) f[i] = 0.f;
+        if (mom_partial != nullptr) {
+            for (int k = lane; k < K; k += 32) {
+                const int j = min(out[k], N - 1);
+                const float4 p = s_q[j];
+                const float x = __fsub_rn(p.x, q.x), y = __fsub_rn(p.y, q.y), z = __fsub_rn(p.z, q.z);
+                f[0] += x; f[1] += y; f[2] += z;
+                f[3] = fmaf(x, x, f[3]); f[4] = fmaf(x, y, f[4]); f[5] = fmaf(x, z, f[5]);
+                f[6] = fmaf(y, y, f[6]); f[7] = fmaf(y, z, f[7]); f[8] = fmaf(z, z, f[8]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) dacc[i] += (double)f[i];
+    }
+    if (mom_partial != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            double v = dacc[i];
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) s_red[warp][i] = v;
+        }
+        __syncthreads();
+        if (tid < 9) {
+            double v = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) v += s_red[w][tid];
+            mom_partial[(size_t)c * 9 + tid] = v;
+        }
+    }
 }
 
 // Generic path for N > 8192: running distances in global memory (L2-resident), xyz read through
@@ -326,6 +477,53 @@ static int launch_fps_reg(const float *xyz, int B, int N, int npoint, const int6
 }
 
 }  // namespace papc
+
+extern "C" int papc_sample_group_parts(int B, int N, int npoint, int nsample) {
+    // consumer CTAs per cloud, 0 = this shape does not run fused (use papc_fps_f32 + papc_ball_query_f32)
+    if (B < 1 || N <= 256 || N > 1024 || npoint < 1 || nsample < 1 || nsample > N) return 0;
+    int P = (papc::kNumSMs - B) / B;
+    if (P > 4) P = 4;
+    return P >= 1 ? P : 0;
+}
+extern "C" size_t papc_sample_group_workspace_bytes(int B, int npoint) {
+    return B > 0 && npoint > 0 ? papc::align_up((size_t)B * npoint * sizeof(int32_t), 256) : 0;
+}
+extern "C" int papc_sample_group_f32(const float *xyz, int B, int N, int npoint, const int64_t *start_idx,
+                                     float init_dist, float radius2, int nsample, int64_t *out_fps_idx,
+                                     float *out_new_xyz, int32_t *out_group_idx, int32_t *empty_count,
+                                     double *moments_partial, void *workspace, size_t workspace_bytes,
+                                     papc_stream_t stream) {
+    using namespace papc;
+    const int P = papc_sample_group_parts(B, N, npoint, nsample);
+    if (P == 0) return PAPC_EUNSUPPORTED;
+    if (!(init_dist >= 0.0f) || !xyz || !start_idx || !out_fps_idx || !out_new_xyz || !out_group_idx) return PAPC_EINVAL;
+    const size_t need = papc_sample_group_workspace_bytes(B, npoint);
+    if (!workspace || workspace_bytes < need) return PAPC_EWORKSPACE;
+    cudaStream_t st = as_stream(stream);
+    int32_t *pub = reinterpret_cast<int32_t *>(workspace);
+    PAPC_CUDA_TRY(cudaMemsetAsync(pub, 0xFF, (size_t)B * npoint * sizeof(int32_t), st));   // -1 = not picked yet
+    const size_t smem = (size_t)N * sizeof(float4) + (size_t)(npoint < kFpsOutCap ? npoint : kFpsOutCap) * sizeof(int);
+    ProfScope prof(st, "sample_group", (long long)B * N, npoint, nsample, 0.0,
+                   12.0 * B * N + 20.0 * B * npoint + 4.0 * B * npoint * nsample);
+    const int grid = B + B * P;
+    int dbg = 0;
+#ifdef PAPC_TRIAGE
+    { const char *e = getenv("PAPC_SG_DBG"); dbg = e ? atoi(e) : 0; }
+#endif
+    if (N <= 512) {
+        auto k = sample_group_kernel<4>;
+        if (smem > 48 * 1024) PAPC_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, kSgThreads, smem, st>>>(xyz, B, N, npoint, start_idx, init_dist, out_fps_idx, out_new_xyz, pub, P, radius2,
+                                           nsample, out_group_idx, empty_count, moments_partial, dbg);
+    } else {
+        auto k = sample_group_kernel<8>;
+        if (smem > 48 * 1024) PAPC_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, kSgThreads, smem, st>>>(xyz, B, N, npoint, start_idx, init_dist, out_fps_idx, out_new_xyz, pub, P, radius2,
+                                           nsample, out_group_idx, empty_count, moments_partial, dbg);
+    }
+    PAPC_LAUNCH_CHECK();
+    return PAPC_OK;
+}
 
 extern "C" size_t papc_fps_workspace_bytes(int B, int N) {
     if (N <= papc::kFpsRegMaxN || B <= 0) return 0;

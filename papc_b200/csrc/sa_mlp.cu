@@ -1065,6 +1065,8 @@ static int run_chain(const papc_group_source *src, const papc_mlp *mlp, const Ws
         m.W0 = l1.weight; m.b0 = l1.bias; m.gamma = l1.gamma; m.beta = l1.beta;
         m.eps = mlp->eps; m.c0 = c1; m.sqrt_M = sqrt_m;
         m.partial = reinterpret_cast<double *>(ws + p.mom_partial);
+        m.pre_partial = src->xyz_moments;
+        m.pre_rows = src->xyz_moment_rows;
         m.counter = counters + PAPC_MAX_MLP_LAYERS;
         m.scale = scale[0]; m.shift = shift[0]; m.mean_out = l1.batch_mean; m.var_out = l1.batch_var;
         m.l0_fold = reinterpret_cast<float *>(ws + p.fold);
@@ -1233,6 +1235,8 @@ extern "C" int papc_sa_mlp_f32(const papc_group_source *src, const papc_mlp *mlp
         m.running_var = batch ? nullptr : l0.running_var;
         m.eps = mlp->eps; m.c0 = l0.cout; m.sqrt_M = sqrt_m;
         m.partial = reinterpret_cast<double *>(ws + p.mom_partial);
+        m.pre_partial = src->xyz_moments;
+        m.pre_rows = src->xyz_moment_rows;
         m.counter = counters + PAPC_MAX_MLP_LAYERS;
         m.scale = scale; m.shift = shift; m.mean_out = l0.batch_mean; m.var_out = l0.batch_var;
         m.l0_fold = fold;

@@ -1213,7 +1213,24 @@ point_moments_kernel(const MomentArgs a) {
     __shared__ uint32_t s_islast;
     const int tid = threadIdx.x;
     const bool batch = a.running_mean == nullptr;
-    if (batch) {
+    if (batch && a.pre_partial != nullptr) {
+        // the nine sums were accumulated by the fused sampling kernel: fixed-order reduction of its rows
+        __shared__ double s_sl[28][9];
+        const int q = tid % 9, sl = tid / 9;
+        if (sl < 28) {
+            double v = 0.0;
+            for (int b = sl; b < a.pre_rows; b += 28) v += __ldcg(a.pre_partial + (long long)b * 9 + q);
+            s_sl[sl][q] = v;
+        }
+        __syncthreads();
+        if (tid < 9) {
+            double v = 0.0;
+#pragma unroll
+            for (int k = 0; k < 28; ++k) v += s_sl[k][tid];
+            s_tot[tid] = v / (double)a.M;
+        }
+        __syncthreads();
+    } else if (batch) {
         float acc[9];
 #pragma unroll
         for (int i = 0; i < 9; ++i) acc[i] = 0.f;
@@ -1673,6 +1690,14 @@ int launch_moments(const MomentArgs &a_in, cudaStream_t st) {
     int blocks = a.running_mean != nullptr ? 1 : moment_blocks(a.M);
     size_t smem = 0;
     a.nslice = 0;
+    if (a.running_mean != nullptr) a.pre_partial = nullptr;
+    if (a.pre_partial != nullptr) {
+        if (a.pre_rows < 1) return PAPC_EINVAL;
+        ProfScope prof(st, "point_moments_finish", a.M, 3, a.c0, 0.0, 72.0 * a.pre_rows);
+        point_moments_kernel<<<1, kMomThreads, 0, st>>>(a);
+        PAPC_LAUNCH_CHECK();
+        return PAPC_OK;
+    }
     // one cloud per block, staged in shared memory, when the batch provides enough blocks and the
     // cloud fits; B = M / (S * K)
     const long long rows_per_cloud = (long long)a.S * a.K;

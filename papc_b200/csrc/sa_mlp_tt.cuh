@@ -123,6 +123,8 @@ struct MomentArgs {
     uint32_t kmul, kshr, smul, sshr;  // as TtArgs (filled in by launch_moments)
     int fastgeom;
     int nslice;             // > 0: staged variant, nslice blocks per cloud (filled in by launch_moments)
+    const double *pre_partial;  // non-null: [pre_rows][9] sums already accumulated (papc_sample_group_f32): one block
+    int pre_rows;               //           reduces them in fixed order and finalises -- no pass over the rows
     double *partial;        // [blocks][9]
     unsigned int *counter;
     float *scale, *shift, *mean_out, *var_out;  // [c0] (mean/var nullable)

@@ -246,6 +246,33 @@ def _side_stream(device):
     return _SIDE_STREAMS[key]
 
 
+FUSED_SAMPLING = os.environ.get("PAPC_FUSED_SAMPLING", "1") != "0"
+
+
+def _sample_group_fused(xyz, npoint, start_idx, radius, nsample, want_moments):
+    """FPS + ball query (+ the second moments of the centred neighbours) in ONE launch
+    (``papc_sample_group_f32``): the ball query of centroid i runs on other SMs while the FPS recurrence is
+    still producing the next centroids.  Bit-identical to ``farthest_point_sample_idx`` + ``_ball_query``.
+    Returns None when the shape does not run fused."""
+    B, N, _ = xyz.shape
+    lib = L.lib()
+    P = lib.papc_sample_group_parts(B, N, npoint, nsample)
+    if P == 0:
+        return None
+    dev = xyz.device
+    start = _draw_start(B, N, dev, start_idx)
+    fps = torch.empty((B, npoint), dtype=torch.int64, device=dev)
+    new_xyz = torch.empty((B, npoint, 3), dtype=torch.float32, device=dev)
+    idx = torch.empty((B, npoint, nsample), dtype=torch.int32, device=dev)
+    mom = torch.empty((B * P, 9), dtype=torch.float64, device=dev) if want_moments else None
+    wsb = lib.papc_sample_group_workspace_bytes(B, npoint)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    L.check(lib.papc_sample_group_f32(L.ptr(xyz), B, N, npoint, L.ptr(start), 1.0, radius2_f32(radius), nsample,
+                                      L.ptr(fps), L.ptr(new_xyz), L.ptr(idx), None, L.ptr(mom), L.ptr(ws), wsb,
+                                      L.stream_ptr(dev)), "sample_and_group (fused)")
+    return new_xyz, idx, mom
+
+
 _KEEPALIVE = {}    # device -> buffers of the most recent side-stream sampling (see _sample)
 
 
@@ -260,9 +287,9 @@ def precede(t):
     return t
 
 
-def _sample(xyz, ready, npoint, start_idx, queries):
+def _sample(xyz, ready, npoint, start_idx, queries, want_moments=False):
     """FPS + one ball query per (radius, nsample) in ``queries`` -> (new_xyz, [idx int32...], event
-    recorded right after the FPS).  Runs on the side stream when ``ready`` -- the producer layer's
+    recorded right after the FPS[, moment partials when ``want_moments``: one query, fused launch, else None]).  Runs on the side stream when ``ready`` -- the producer layer's
     (FPS-done event, entry event) pair -- is set, so that the sampling of layer n+1 overlaps the MLP of layer n.
 
     Stream safety without giving the overlap up:
@@ -290,23 +317,37 @@ def _sample(xyz, ready, npoint, start_idx, queries):
             side.wait_event(ev0)
         side.wait_event(ready_ev)
         with torch.cuda.stream(side):
-            _, new_xyz = farthest_point_sample_idx(xyz, npoint, start_idx, return_xyz=True)
-            ev = torch.cuda.Event()
-            ev.record(side)
-            idxs = _ball_query_multi(queries, xyz, new_xyz, torch.int32)
+            # separate small kernels here: the fused launch (512-thread CTAs) cannot co-reside with the
+            # previous layer's MLP kernels, which is the whole point of this branch
+            new_xyz, idxs, ev, mom = _sample_kernels(xyz, npoint, start_idx, queries, False, side, fused=False)
             done = torch.cuda.Event()
             done.record(side)
         main.wait_event(done)
+        bufs = [new_xyz] + idxs + ([mom] if mom is not None else [])
         if not torch.cuda.is_current_stream_capturing():
-            for t in [new_xyz] + idxs:
+            for t in bufs:
                 t.record_stream(main)
-        _KEEPALIVE[dev] = [new_xyz] + idxs
-        return new_xyz, idxs, ev
+        _KEEPALIVE[dev] = bufs
+        return (new_xyz, idxs, ev, mom) if want_moments else (new_xyz, idxs, ev)
+    new_xyz, idxs, ev, mom = _sample_kernels(xyz, npoint, start_idx, queries, want_moments, main)
+    return (new_xyz, idxs, ev, mom) if want_moments else (new_xyz, idxs, ev)
+
+
+def _sample_kernels(xyz, npoint, start_idx, queries, want_moments, stream, fused=True):
+    """The sampling launches on the current stream: the fused kernel for a single-radius layer whose shape
+    qualifies, else FPS followed by the (multi-radius) ball query."""
+    if fused and FUSED_SAMPLING and len(queries) == 1:
+        r = _sample_group_fused(xyz, npoint, start_idx, queries[0][0], queries[0][1], want_moments)
+        if r is not None:
+            new_xyz, idx, mom = r
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            return new_xyz, [idx], ev, mom
     _, new_xyz = farthest_point_sample_idx(xyz, npoint, start_idx, return_xyz=True)
     ev = torch.cuda.Event()
-    ev.record(main)
+    ev.record(stream)
     idxs = _ball_query_multi(queries, xyz, new_xyz, torch.int32)
-    return new_xyz, idxs, ev
+    return new_xyz, idxs, ev, None
 
 
 def _entry_event(dev):
@@ -478,8 +519,11 @@ class _MlpRunner:
             self._update_running(stats)
 
 
-def _make_src(xyz, new_xyz, feats, idx32, B, N, S, K, order):
+def _make_src(xyz, new_xyz, feats, idx32, B, N, S, K, order, moments=None):
     src = L.GroupSource()
+    if moments is not None:   # [rows,9] fp64 partial sums from the fused sampling kernel (D = 0 layers)
+        src.xyz_moments = moments.data_ptr()
+        src.xyz_moment_rows = moments.shape[0]
     src.grouped = None
     src.xyz = xyz.data_ptr()
     src.new_xyz = new_xyz.data_ptr() if new_xyz is not None else None
@@ -580,9 +624,12 @@ class PointNetSetAbstraction(_SAMixin):
             S = self.npoint
             if self.nsample > N:
                 raise ValueError(f"query_ball_point: nsample ({self.nsample}) > N ({N})")
-            new_xyz, (idx,), ev = _sample(xyz, ready, S, start_idx, [(self.radius, self.nsample)])
-            src = _make_src(xyz, new_xyz, feats, idx, B, N, S, self.nsample, L.XYZ_FIRST)
-            keep = (xyz, feats, new_xyz, idx)
+            new_xyz, (idx,), ev, mom = _sample(xyz, ready, S, start_idx, [(self.radius, self.nsample)],
+                                               want_moments=True)
+            if feats is not None or self.bn_mode != "batch":
+                mom = None        # only the folded first layer (features = centred xyz, batch statistics) reads them
+            src = _make_src(xyz, new_xyz, feats, idx, B, N, S, self.nsample, L.XYZ_FIRST, moments=mom)
+            keep = (xyz, feats, new_xyz, idx, mom)
         out = _MlpRunner(self.mlp_convs, self.mlp_bns).run(                # :214-219
             src, keep, 3 + D, B, S, self.bn_mode, dev, self.update_running_stats, self._sync_group())
         out_xyz = new_xyz.transpose(1, 2)

@@ -420,3 +420,48 @@ def test_knn_vs_stable_argsort_of_square_distance(B, N, S, k):
     np.testing.assert_array_equal(dist_[:, :, :kk], np.take_along_axis(d, order[:, :, :kk], -1))
     if kk < k:
         assert (idx[:, :, kk:] == N).all() and np.isinf(dist_[:, :, kk:]).all()
+
+
+# ------------------------------------------------------------------ fused sampling: FPS + ball query + moments
+@pytest.mark.parametrize("B,N,S,K,r", [(32, 1024, 512, 32, 0.2), (32, 512, 128, 64, 0.4), (5, 700, 100, 16, 0.15),
+                                       (74, 300, 40, 8, 0.3), (3, 1000, 64, 48, 0.02)])
+def test_fused_sample_group_bit_exact(B, N, S, K, r):
+    """papc_sample_group_f32 (the ball query of centroid i overlapping the FPS recurrence, one launch) ==
+    papc_fps_f32 + papc_ball_query_f32, bit for bit; its moment partial sums == the sums over the grouped,
+    centred points (fp64 reference from the indices)."""
+    xyz = _xyz(B, N, seed=B * 7 + N)
+    start = synth.fps_start(B, N, seed=3)
+    x = _cu(xyz)
+    assert layers.L.lib().papc_sample_group_parts(B, N, S, K) >= 1
+    got = layers._sample_group_fused(x, S, _cu(start), r, K, True)
+    assert got is not None
+    new_xyz, idx, mom = got
+    fps_ref, nx_ref = layers.farthest_point_sample_idx(x, S, _cu(start), return_xyz=True)
+    idx_ref = layers._ball_query(r, K, x, nx_ref, torch.int32)
+    assert torch.equal(new_xyz, nx_ref)
+    assert torch.equal(idx, idx_ref)
+    # moments: rows = all B*S*K grouped points (padding rows repeat the first neighbour; an empty ball's N clamps)
+    ii = np.minimum(idx.cpu().numpy().astype(np.int64), N - 1)
+    g = np.take_along_axis(xyz[:, None, :, :].astype(np.float32), ii[..., None].repeat(3, -1), axis=2)
+    cen = (g - new_xyz.cpu().numpy()[:, :, None, :]).astype(np.float64).reshape(-1, 3)
+    want = np.array([cen[:, 0].sum(), cen[:, 1].sum(), cen[:, 2].sum(),
+                     (cen[:, 0] ** 2).sum(), (cen[:, 0] * cen[:, 1]).sum(), (cen[:, 0] * cen[:, 2]).sum(),
+                     (cen[:, 1] ** 2).sum(), (cen[:, 1] * cen[:, 2]).sum(), (cen[:, 2] ** 2).sum()])
+    np.testing.assert_allclose(mom.cpu().numpy().sum(0), want, rtol=2e-6, atol=1e-6 * cen.shape[0] ** 0.5)
+
+
+def test_fused_sampling_layer_equals_unfused(monkeypatch):
+    """A SetAbstraction layer with the fused sampling launch == the same layer on the separate kernels:
+    coordinates bit-exact, features within fp32 rounding of the two moment summation orders."""
+    B, N = 8, 1024
+    xyz = _cu(synth.clouds(B, N, seed=17))
+    st = _cu(synth.fps_start(B, N, seed=18))
+    sa = layers.PointNetSetAbstraction(512, 0.2, 32, 3, [64, 64, 128], False).to(DEV)
+    outs = {}
+    for flag in (True, False):
+        monkeypatch.setattr(layers, "FUSED_SAMPLING", flag)
+        ox, op = sa(xyz, None, start_idx=st)
+        outs[flag] = (ox.clone(), op.clone())
+    assert torch.equal(outs[True][0], outs[False][0])
+    assert float((outs[True][1] - outs[False][1]).abs().max()) <= 1e-5
+    assert layers.L.lib().papc_sample_group_parts(200, 1024, 512, 32) == 0   # too many clouds to be co-resident
