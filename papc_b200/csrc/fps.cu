@@ -224,8 +224,12 @@ fps_reg_body(const int b, const float *__restrict__ xyz, int N, int npoint,
             const int src = __ffs(ball) - 1;  // lowest lane == lowest index
             far = __shfl_sync(0xffffffffu, tid * PPT + bi, src);
         } else {
-            if (mine && (ball & lt_mask) == 0u)  // lowest lane holding the warp maximum
-                fps_sts64i(red_it + 8u * warp, wmax, tid * PPT + bi);
+            {   // lowest lane holding the warp maximum publishes it: a PREDICATED store, not a branch (a divergent
+                // branch + reconvergence barrier in front of the bar.sync sits on every iteration's critical path)
+                const uint32_t wr = (mine && (ball & lt_mask) == 0u) ? 1u : 0u;
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p st.shared.v2.b32 [%0], {%1, %2};\n\t}"
+                             ::"r"(red_it + 8u * warp), "r"(wmax), "r"(tid * PPT + bi), "r"(wr) : "memory");
+            }
             fps_sync<THREADS, PUB>();
             if (NW <= 8) {
                 // every thread reduces all warps' candidates itself: broadcast LDS.128 (two
