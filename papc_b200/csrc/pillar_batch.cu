@@ -25,7 +25,20 @@ struct BatchGeom {
     int reverse;
     int B;
     int off[kMaxFrames + 1];   // point offsets of the frames in the concatenated cloud
+    uint32_t mul2, shr2, mul1, shr1;   // division by shape[2] / shape[1] (cells < 2^31): q = umulhi(x, mul) >> shr
 };
+__device__ __forceinline__ uint32_t vb_div(uint32_t x, uint32_t mul, uint32_t shr) {
+    return mul == 0u ? x : (__umulhi(x, mul) >> shr);
+}
+// cell -> (c0, c1, c2) of the [shape0, shape1, shape2] grid without integer divisions (12 000 openers x 5
+// runtime div / mod were most of the opener scan's 49 us)
+__device__ __forceinline__ void vb_cell_coords(const BatchGeom &g, int cell, int &c0, int &c1, int &c2) {
+    const uint32_t q2 = vb_div((uint32_t)cell, g.mul2, g.shr2);
+    c2 = cell - (int)q2 * g.shape[2];
+    const uint32_t q1 = vb_div(q2, g.mul1, g.shr1);
+    c1 = (int)q2 - (int)q1 * g.shape[1];
+    c0 = (int)q1;
+}
 __device__ __forceinline__ int frame_of(const BatchGeom &g, int i) {
     int b = 0;
     while (b + 1 < g.B && i >= g.off[b + 1]) ++b;
@@ -37,8 +50,9 @@ __global__ void vb_init_kernel(int32_t *cell_first, size_t cells_total, int32_t 
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     if (i < (size_t)g.B) {
-        meta[2 * i] = g.off[i + 1] - g.off[i];   // cutoff (local point index): no break
-        meta[2 * i + 1] = 0;
+        meta[3 * i] = g.off[i + 1] - g.off[i];   // cutoff (local point index): no break
+        meta[3 * i + 1] = 0;                     // openers found by the scan
+        meta[3 * i + 2] = 0;                     // segment cursor of the bucket list (vb_alloc_kernel)
     }
     for (size_t j = i; j < cells_total; j += stride) cell_first[j] = INT_MAX;
     for (size_t j = i; j < vox_total; j += stride) {
@@ -131,11 +145,13 @@ vb_scan_kernel(const int32_t *__restrict__ pt_cell, const int32_t *__restrict__ 
                 if ((flags >> e) & 1u) {
                     if (vid < max_voxels) {
                         if (coors3 == nullptr) { ++vid; continue; }
-                        co[vid * 3 + 0] = cell[e] / (g.shape[2] * g.shape[1]);
-                        co[vid * 3 + 1] = (cell[e] / g.shape[2]) % g.shape[1];
-                        co[vid * 3 + 2] = cell[e] % g.shape[2];
+                        int c0, c1, c2;
+                        vb_cell_coords(g, cell[e], c0, c1, c2);
+                        co[vid * 3 + 0] = c0;
+                        co[vid * 3 + 1] = c1;
+                        co[vid * 3 + 2] = c2;
                     } else if (vid == max_voxels) {
-                        meta[2 * b] = i;   // the reference breaks here (point_cloud_ops.py:44-45)
+                        meta[3 * b] = i;   // the reference breaks here (point_cloud_ops.py:44-45)
                     }
                     ++vid;
                 }
@@ -143,7 +159,7 @@ vb_scan_kernel(const int32_t *__restrict__ pt_cell, const int32_t *__restrict__ 
         }
         carry += total;
     }
-    if (tid == 0) meta[2 * b + 1] = carry;
+    if (tid == 0) meta[3 * b + 1] = carry;
 }
 
 __global__ void __launch_bounds__(256)
@@ -156,42 +172,39 @@ vb_count_kernel(int32_t *__restrict__ pt_cell, const int32_t *__restrict__ cell_
     const int li = i - g.off[b];
     const int cell = pt_cell[i];
     int v = -1;
-    if (cell >= 0 && li < meta[2 * b]) {
+    if (cell >= 0 && li < meta[3 * b]) {
         v = pt_vid[g.off[b] + cell_first[(size_t)b * cells + cell]];
         atomicAdd(cnt + (size_t)b * max_voxels + v, 1);
     }
     pt_cell[i] = v;   // from here on: voxel id (inside its frame) of the point, -1 = dropped
 }
 
-// one CTA per frame: bucket offsets (relative to the frame's point range) and the frame's voxel count
-__global__ void __launch_bounds__(1024)
-vb_offsets_kernel(const int32_t *__restrict__ cnt, const int32_t *__restrict__ meta, int max_voxels,
-                  int32_t *__restrict__ off, int32_t *__restrict__ frame_voxels) {
-    __shared__ int s_warp[32];
-    const int b = blockIdx.x, tid = threadIdx.x;
-    const int vnum = min(meta[2 * b + 1], max_voxels);
-    if (tid == 0) frame_voxels[b] = vnum;
-    const int32_t *c_in = cnt + (size_t)b * max_voxels;
-    int32_t *o = off + (size_t)b * max_voxels;
-    int carry = 0;
-    for (int base = 0; base < max_voxels; base += 1024 * kVbEPT) {
-        const int v0 = base + tid * kVbEPT;
-        int c[kVbEPT];
-        int local = 0;
+// bucket segments of the frame's point list: one atomic cursor per frame hands every voxel a contiguous
+// segment of cnt[v] slots (the ORDER of the segments is irrelevant -- the writer sorts each voxel's points and
+// addresses them through off[] -- so no scan over the 12 000 counts is needed); also the frame's voxel count
+__global__ void __launch_bounds__(256)
+vb_alloc_kernel(const int32_t *__restrict__ cnt, int32_t *__restrict__ meta, int batch, int max_voxels,
+                int32_t *__restrict__ off, int32_t *__restrict__ frame_voxels) {
+    // grid.y = frame; one atomicAdd per WARP (the warp's 32 counts are scanned with shuffles first): 12 000
+    // single-thread atomics on one cursor serialise to ~35 us
+    const int b = blockIdx.y;
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int vnum = min(meta[3 * b + 1], max_voxels);
+    if (v == 0) frame_voxels[b] = vnum;
+    const size_t i = (size_t)b * max_voxels + v;
+    const int c = (v < vnum) ? cnt[i] : 0;
+    int incl = c;
 #pragma unroll
-        for (int e = 0; e < kVbEPT; ++e) {
-            c[e] = (v0 + e < vnum) ? c_in[v0 + e] : 0;
-            local += c[e];
-        }
-        int total;
-        int run = carry + vb_block_excl_scan_1024(local, s_warp, &total);
-#pragma unroll
-        for (int e = 0; e < kVbEPT; ++e) {
-            if (v0 + e < max_voxels) o[v0 + e] = run;
-            run += c[e];
-        }
-        carry += total;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
     }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    int base = 0;
+    if (lane == 0 && total > 0) base = atomicAdd(meta + 3 * b + 2, total);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (v < max_voxels) off[i] = base + incl - c;
 }
 
 __global__ void __launch_bounds__(256)
@@ -272,10 +285,11 @@ vb_write_kernel(const float *__restrict__ points, int F, const int32_t *__restri
             coors4[row * 4 + 3] = c3[2];
             num_points[row] = min(n, max_points);
         }
-    } else if (lane == 0) {
-        coors4[row * 4 + 0] = 0; coors4[row * 4 + 1] = 0; coors4[row * 4 + 2] = 0; coors4[row * 4 + 3] = 0;
-        num_points[row] = 0;
+    } else {
+        return;   // rows past the batch total stay zero (the launcher clears the three outputs first)
     }
+    // only the real rows are written: the zero padding (98 % of the 19.2 MB per frame) comes from one memset at
+    // full HBM write rate instead of from 48 000 latency-bound warps
     float *vout = voxels + (size_t)row * max_points * F;
     const bool vec = (F % 4 == 0) && ((reinterpret_cast<uintptr_t>(points) & 15u) == 0) &&
                      ((reinterpret_cast<uintptr_t>(voxels) & 15u) == 0);
@@ -283,14 +297,14 @@ vb_write_kernel(const float *__restrict__ points, int F, const int32_t *__restri
         const int F4 = F / 4;
         const float4 *pin = reinterpret_cast<const float4 *>(points);
         float4 *po = reinterpret_cast<float4 *>(vout);
-        for (int e = lane; e < max_points * F4; e += 32) {
+        for (int e = lane; e < nsel * F4; e += 32) {
             const int r = e / F4, c = e - r * F4;
-            po[e] = (r < nsel) ? pin[(size_t)s_sorted[r] * F4 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
+            po[e] = pin[(size_t)s_sorted[r] * F4 + c];
         }
     } else {
-        for (int e = lane; e < max_points * F; e += 32) {
+        for (int e = lane; e < nsel * F; e += 32) {
             const int r = e / F, c = e - r * F;
-            vout[e] = (r < nsel) ? points[(size_t)s_sorted[r] * F + c] : 0.f;
+            vout[e] = points[(size_t)s_sorted[r] * F + c];
         }
     }
 }
@@ -355,7 +369,8 @@ bev_accumulate_kernel(const float *__restrict__ points, int N, int F, const Batc
     const int cell = pt_cell[i];
     if (cell < 0 || i >= meta[0]) return;
     const int D = g.shape[0], H = g.shape[1], W = g.shape[2];
-    const int x = cell % W, y = (cell / W) % H, z = cell / (W * H);
+    int x, y, z;
+    vb_cell_coords(g, cell, z, y, x);
     const size_t plane = (size_t)H * W;
     const int nmaps = D + 1 + (with_refl ? 1 : 0);
     atomicAdd(bev + (size_t)(nmaps - 1) * plane + (size_t)y * W + x, 1.0f);
@@ -414,7 +429,7 @@ static void plan_vb(int Ntot, size_t cells, int B, int max_voxels, VbWs *w) {
     w->fillc = take(vt * 4);
     w->list = take(n * 4);
     w->coors3 = take(vt * 3 * 4);
-    w->meta = take((size_t)B * 8 + 16);
+    w->meta = take((size_t)B * 12 + 16);
     w->total = off;
 }
 static bool make_batch_geom(const float *vs, const float *cr, int reverse, BatchGeom *g) {
@@ -428,6 +443,16 @@ static bool make_batch_geom(const float *vs, const float *cr, int reverse, Batch
     }
     for (int j = 0; j < 3; ++j) g->shape[j] = reverse ? g->grid[2 - j] : g->grid[j];
     g->reverse = reverse;
+    auto magic = [](uint32_t d, uint32_t *mul, uint32_t *shr) {   // as tt::make_fastdiv: dividends < 2^31
+        if (d <= 1u) { *mul = 0u; *shr = 0u; return; }
+        uint32_t lg = 0;
+        while ((1ull << lg) < d) ++lg;
+        const uint32_t p = 31u + lg;
+        *mul = (uint32_t)(((1ull << p) + d - 1ull) / d);
+        *shr = p - 32u;
+    };
+    magic((uint32_t)g->shape[2], &g->mul2, &g->shr2);
+    magic((uint32_t)g->shape[1], &g->mul1, &g->shr1);
     return true;
 }
 
@@ -491,12 +516,16 @@ extern "C" int papc_voxelize_batch_f32(const float *points, const int32_t *frame
         vb_count_kernel<<<ceil_div(Ntot, 256), 256, 0, st>>>(pt_cell, cell_first, pt_vid, meta, Ntot, g, cells, max_voxels, cnt);
         PAPC_LAUNCH_CHECK();
     }
-    vb_offsets_kernel<<<batch, 1024, 0, st>>>(cnt, meta, max_voxels, off, frame_voxels);
+    vb_alloc_kernel<<<dim3((unsigned)ceil_div(max_voxels, 256), (unsigned)batch), 256, 0, st>>>(cnt, meta, batch, max_voxels, off,
+                                                                                                frame_voxels);
     PAPC_LAUNCH_CHECK();
     if (Ntot > 0) {
         vb_bucket_kernel<<<ceil_div(Ntot, 256), 256, 0, st>>>(pt_cell, off, Ntot, g, max_voxels, fillc, list);
         PAPC_LAUNCH_CHECK();
     }
+    PAPC_CUDA_TRY(cudaMemsetAsync(voxels, 0, vt * (size_t)max_points * F * sizeof(float), st));
+    PAPC_CUDA_TRY(cudaMemsetAsync(coors4, 0, vt * 4 * sizeof(int32_t), st));
+    PAPC_CUDA_TRY(cudaMemsetAsync(num_points, 0, vt * sizeof(int32_t), st));
     if (smem > 48 * 1024)
         PAPC_CUDA_TRY(cudaFuncSetAttribute(vb_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     vb_write_kernel<<<(unsigned)ceil_div<long long>((long long)vt, kVbWarps), kVbWarps * 32, smem, st>>>(
