@@ -661,6 +661,70 @@ def other_configs(torch, dev):
         except Exception as e:  # noqa: BLE001
             c4["cpu_baseline"] = {"error": f"{type(e).__name__}: {e}"}
     out["C4_pillar_encode"] = c4
+    try:
+        out["N3_nms"] = nms_block(torch, dev, timeit)
+    except Exception as e:  # noqa: BLE001
+        out["N3_nms"] = {"error": f"{type(e).__name__}: {e}"}
+    return out
+
+
+def nms_block(torch, dev, timeit):
+    """rotated / axis-aligned NMS of 1000 / 4096 boxes (PointPillars keeps nms_pre_max_size =
+    1000 boxes per frame) on the device-resident kernels, beside the reference's own numba.cuda path
+    (nms_gpu.py, unmodified, oracle/_ref) on the same boxes when numba.cuda runs on this box."""
+    from oracle import build as oracle_build
+    from papc_b200 import nms as pnms
+    rng = np.random.default_rng(5)
+
+    def rdets(n):
+        c = rng.uniform(0, 70.0, (n, 2))
+        wh = rng.uniform(1.5, 4.5, (n, 2))
+        a = rng.uniform(-np.pi, np.pi, (n, 1))
+        s = rng.uniform(0.05, 1.0, (n, 1))
+        return np.concatenate([c, wh, a, s], 1).astype(np.float32)
+
+    def adets(n):
+        c = rng.uniform(0, 200.0, (n, 2))
+        wh = rng.uniform(2.0, 12.0, (n, 2))
+        s = rng.uniform(0.05, 1.0, (n, 1))
+        return np.concatenate([c - wh / 2, c + wh / 2, s], 1).astype(np.float32)
+
+    cases = {"rotate_nms_1000": (rdets(1000), 0.5), "rotate_nms_4096": (rdets(4096), 0.5), "nms_4096": (adets(4096), 0.5)}
+    out = {}
+    ref = None
+    path = oracle_build.ref_file("nms_gpu.py")
+    if path is not None:
+        try:
+            from numba import cuda as ncuda
+            if ncuda.is_available():
+                from oracle import ref_nms
+                ref = ref_nms.load(path)
+        except Exception as e:  # noqa: BLE001
+            out["reference_note"] = f"numba.cuda unavailable here: {type(e).__name__}: {e}"
+    for name, (d, thr) in cases.items():
+        dd = torch.from_numpy(d).to(dev)
+        ms = timeit(lambda: pnms.nms_device(dd, thr), reps=20)
+        keep, num = pnms.nms_device(dd, thr)
+        k = int(num.item())
+        blk = {"boxes": int(d.shape[0]), "kept": k, "ms": ms, "value": d.shape[0] / (ms / 1e3), "unit": "boxes/s",
+               "note": "device-resident: boxes in HBM, keep list + count left on the device"}
+        if ref is not None:
+            try:
+                fn = ref["rotate_nms_gpu"] if d.shape[1] == 6 else ref["nms_gpu"]
+                r = fn(d, np.float32(thr))                     # numba JIT + warm-up
+                t = []
+                for _ in range(3):
+                    t0 = time.perf_counter()
+                    r = fn(d, np.float32(thr))
+                    t.append(time.perf_counter() - t0)
+                mine = keep[:k].cpu().numpy().tolist()
+                blk["reference"] = {"ms": 1e3 * float(np.median(t)), "kind": "reference",
+                                    "same_keep_list": bool(list(map(int, r)) == mine),
+                                    "sample": "the reference's own numba.cuda kernels + host suppress loop (nms_gpu.py, "
+                                              "unmodified, oracle/_ref), NumPy in -> list out, median of 3 calls"}
+            except Exception as e:  # noqa: BLE001
+                blk["reference"] = {"error": f"{type(e).__name__}: {e}"}
+        out[name] = blk
     return out
 
 

@@ -39,6 +39,7 @@ REF_FILES = {   # destination under oracle/_ref/ -> source under /root/reference
     "pointnet2_basic_layers.py": "layers/pointnet2_basic_layers.py",
     "classify_pointnet2.py": "classify/pointnet2/pointnet2.py",
     "segment_pointnet2.py": "segment/pointnet2/pointnet2.py",
+    "nms_gpu.py": "detect/pointpillars/libs/ops/non_max_suppression/nms_gpu.py",
 }
 
 
