@@ -286,23 +286,50 @@ def run_ours(args):
 
     # The step as the library's public graph API runs it: the whole sa1 -> sa2 -> sa3 forward captured
     # once (papc_b200.sa_stack.GraphedForward) and replayed; --no-graph times the eager calls instead.
+    # The step's one exchange: peer-memory stores + signal-pad barrier (papc_b200.dist.PeerAllGather) when torch
+    # symmetric memory works on this box, else the NCCL all-gather.  PAPC_P2P_GATHER=0 forces NCCL (A/B).
+    peer_ag, side_ag, gather_kind = None, None, "none"
+    if world > 1:
+        gather_kind = "NCCL all-gather"
+        if os.environ.get("PAPC_P2P_GATHER", "1") != "0":
+            try:
+                peer_ag = pdist.PeerAllGather(B, 1024, dev)
+                side_ag = torch.cuda.Stream()
+                gather_kind = "peer-memory stores (papc_p2p_allgather_f32) + signal-pad barrier over symmetric memory"
+            except Exception as e:  # noqa: BLE001
+                print(f"[bench] symmetric memory unavailable ({type(e).__name__}: {e}); using the NCCL all-gather",
+                      file=sys.stderr)
+                peer_ag = None
+
+    def gather(feats):
+        if world == 1:
+            return feats
+        if peer_ag is not None:
+            return peer_ag.gather(feats)
+        return pdist.all_gather_features(feats)
+
     def fwd_gather(x):
-        """The step: sa1 -> sa2 -> sa3 on this rank's shard, then (N > 1) the ONE all-gather of the l3 features."""
+        """The step: sa1 -> sa2 -> sa3 on this rank's shard, then (N > 1) the ONE exchange of the l3 features."""
+        cur = torch.cuda.current_stream()
+        if peer_ag is not None:      # "peers are done with the previous result": no data dependency on the forward,
+            side_ag.wait_stream(cur)  # so it runs on a parallel branch and is off the critical path
+            with torch.cuda.stream(side_ag):
+                peer_ag.pre()
         _, l3 = model(x, None, start_idx=(st1, st2))
         feats = l3.reshape(B, 1024)
-        if world > 1:
-            feats = pdist.all_gather_features(feats)
-        return feats
+        if peer_ag is not None:
+            cur.wait_stream(side_ag)
+        return gather(feats)
 
     graphed = None
     gather_in_graph = False
     if not args.no_graph:
         if world > 1 and os.environ.get("PAPC_GATHER_IN_GRAPH", "1") != "0":
-            try:   # the NCCL all-gather captured as a node of the same graph: no separate launch after the replay
+            try:   # the exchange captured as nodes of the same graph: no separate launches after the replay
                 graphed = sa_stack.GraphedForward(fwd_gather, xyz_d)
                 gather_in_graph = True
             except Exception as e:  # noqa: BLE001
-                print(f"[bench] all-gather capture failed ({type(e).__name__}: {e}); gathering after the replay",
+                print(f"[bench] capture of the exchange failed ({type(e).__name__}: {e}); exchanging after the replay",
                       file=sys.stderr)
                 torch.cuda.synchronize()
                 graphed = None
@@ -314,7 +341,9 @@ def run_ours(args):
             return fwd_gather(xyz_d if x is None else x)
         feats = graphed.replay() if x is None else graphed(x)
         if world > 1 and not gather_in_graph:
-            feats = pdist.all_gather_features(feats)
+            if peer_ag is not None:
+                peer_ag.pre()
+            feats = gather(feats)
         return feats
 
     def step_device():
@@ -470,7 +499,7 @@ def run_ours(args):
         "config": {"workload": WORKLOAD,
                    "global_batch": Bg, "n_points": N_POINTS, "parallelism": f"batch-shard x{world}",
                    "bn": "train-mode batch statistics (per shard), as the reference's unregistered SA layers run",
-                   "collective": ("none" if world == 1 else "one NCCL all-gather of the l3 features, " +
+                   "collective": ("none" if world == 1 else "one exchange of the l3 features: " + gather_kind + ", " +
                                   ("captured inside the replayed graph" if gather_in_graph else "launched after the forward")),
                    "timed_region": f"{args.steps} steps, {total_ms:.1f} ms of device time in total (CUDA events)",
                    "launch": "eager calls" if graphed is None else "CUDA-graph replay of the captured forward "

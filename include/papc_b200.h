@@ -346,6 +346,16 @@ int papc_pillar_scatter_f32(const float *voxel_features, const int32_t *coords, 
                             void *workspace, size_t workspace_bytes, papc_stream_t stream);
 
 /* ----------------------------------------------------------------------------------------
+ * 8e  the batch-sharded step's one exchange, over peer memory instead of an NCCL all-gather
+ *     local [n_per_rank] floats of this rank -> every peer's result buffer at offset rank * n_per_rank.
+ *     peer_bufs_host [world] is a HOST array of device pointers to the ranks' result buffers (this rank's own
+ *     included), all peer-accessible -- e.g. torch symmetric memory (papc_b200/dist.py: PeerAllGather, which also
+ *     runs the signal-pad barriers that open and close the exchange).  world <= 16; 16-byte aligned buffers.
+ */
+int papc_p2p_allgather_f32(const float *local, int64_t n_per_rank, void *const *peer_bufs_host, int rank,
+                           int world, papc_stream_t stream);
+
+/* ----------------------------------------------------------------------------------------
  * N3  detector post-processing      pp/libs/ops/non_max_suppression/nms_gpu.py
  *
  *   papc_nms_f32: nms_gpu (:133-164, box_dim 5: x1, y1, x2, y2, score) and rotate_nms_gpu (:453-488, box_dim 6:

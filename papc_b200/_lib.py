@@ -109,6 +109,7 @@ _SIGNATURES = {
     "papc_points_to_bev_workspace_bytes": (_SZ, [_I, C.POINTER(_F), C.POINTER(_F)]),
     "papc_points_to_bev_f32": (_I, [_vp, _I, _I, C.POINTER(_F), C.POINTER(_F), C.POINTER(_F), _I, _I, _vp, _vp,
                                      _SZ, _vp]),
+    "papc_p2p_allgather_f32": (_I, [_vp, _I64, C.POINTER(C.c_void_p), _I, _I, _vp]),
     "papc_nms_workspace_bytes": (_SZ, [_I]),
     "papc_nms_f32": (_I, [_vp, _I, _I, _F, _vp, _vp, _vp, _SZ, _vp]),
     "papc_rotate_iou_f32": (_I, [_vp, _I, _vp, _I, _I, _vp, _vp]),

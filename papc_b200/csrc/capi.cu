@@ -87,3 +87,44 @@ extern "C" int papc_prof_get(int i, char *name, int name_cap, int64_t *M, int32_
     }
     return PAPC_OK;
 }
+
+// ------------------------------------------------------------------ the step's ONE exchange over peer memory
+// the batch-sharded forward ends with an all-gather of the per-shard [B/G, C] features (128 KiB per
+// rank).  NCCL's all-gather costs ~30 us of latency at 8 ranks for these bytes; here every rank stores its rows
+// straight into every peer's (symmetric-memory) result buffer over NVLink / NVSwitch -- plain 16-byte peer stores,
+// one launch -- and a signal-pad barrier (the caller's, torch symmetric memory) closes the exchange.
+namespace papc {
+struct PeerPtrs { float *p[16]; };
+__global__ void __launch_bounds__(256)
+p2p_allgather_kernel(const float *__restrict__ local, long long n, const PeerPtrs peers, int rank, int world) {
+    const int peer = blockIdx.y;
+    float *dst = peers.p[peer] + (long long)rank * n;
+    const long long n4 = n / 4;
+    const float4 *src4 = reinterpret_cast<const float4 *>(local);
+    float4 *dst4 = reinterpret_cast<float4 *>(dst);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) dst4[i] = src4[i];
+    for (long long i = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = local[i];
+}
+}  // namespace papc
+
+extern "C" int papc_p2p_allgather_f32(const float *local, int64_t n_per_rank, void *const *peer_bufs_host, int rank,
+                                      int world, papc_stream_t stream) {
+    using namespace papc;
+    if (!local || !peer_bufs_host || n_per_rank < 0 || world < 1 || world > 16 || rank < 0 || rank >= world) return PAPC_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(local) & 15u) != 0 || (n_per_rank * 4) % 16 != 0) return PAPC_EINVAL;
+    PeerPtrs pp{};
+    for (int i = 0; i < world; ++i) {
+        if (!peer_bufs_host[i] || (reinterpret_cast<uintptr_t>(peer_bufs_host[i]) & 15u) != 0) return PAPC_EINVAL;
+        pp.p[i] = reinterpret_cast<float *>(peer_bufs_host[i]);
+    }
+    if (n_per_rank == 0) return PAPC_OK;
+    cudaStream_t st = as_stream(stream);
+    long long blocks = (n_per_rank / 4 + 255) / 256;
+    if (blocks > 16) blocks = 16;           // 8 peers x 16 blocks: enough stores in flight for 128 KiB per peer
+    if (blocks < 1) blocks = 1;
+    ProfScope prof(st, "p2p_allgather", n_per_rank, world, 0, 0.0, 4.0 * n_per_rank * (world + 1));
+    p2p_allgather_kernel<<<dim3((unsigned)blocks, (unsigned)world), 256, 0, st>>>(local, n_per_rank, pp, rank, world);
+    PAPC_LAUNCH_CHECK();
+    return PAPC_OK;
+}

@@ -40,6 +40,49 @@ def all_gather_features(local, group=None):
     return out
 
 
+class PeerAllGather:
+    """The step's ONE exchange over peer memory instead of NCCL: every rank stores its
+    ``[rows, cols]`` fp32 features straight into every peer's result buffer (torch symmetric memory, NVLink /
+    NVSwitch peer stores from ``papc_p2p_allgather_f32``), closed by a signal-pad barrier.  At 8 ranks x 128 KiB
+    the NCCL all-gather is ~30 us of pure latency; this is one small launch + one barrier.
+
+        ag = PeerAllGather(rows, cols, device)          # collective: all ranks construct it together
+        ag.pre()                                        # any time before gather(): peers are done with the last result
+        full = ag.gather(local)                         # [world*rows, cols], rank-major; valid until the next gather
+
+    ``pre()`` is the barrier that makes reuse of the symmetric buffer safe (every rank has copied the previous
+    result out); it has no data dependency on the forward pass, so callers put it on a side stream / a parallel
+    graph branch.  Raises at construction when symmetric memory is unavailable (callers fall back to
+    ``all_gather_features``)."""
+
+    def __init__(self, rows, cols, device, group=None):
+        import ctypes as C
+
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib as L
+        self._L = L
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.rows, self.cols = int(rows), int(cols)
+        self.buf = symm.empty((self.world * self.rows, self.cols), dtype=torch.float32, device=device)
+        self.hdl = symm.rendezvous(self.buf, self.group)
+        self.ptrs = (C.c_void_p * self.world)(*[int(p) for p in self.hdl.buffer_ptrs])
+        self.out = torch.empty((self.world * self.rows, self.cols), dtype=torch.float32, device=device)
+
+    def pre(self):
+        self.hdl.barrier(channel=0)
+
+    def gather(self, local):
+        L = self._L
+        local = L.f32c(local).reshape(self.rows, self.cols)
+        L.check(L.lib().papc_p2p_allgather_f32(L.ptr(local), self.rows * self.cols, self.ptrs, self.rank, self.world,
+                                               L.stream_ptr(local.device)), "p2p_allgather")
+        self.hdl.barrier(channel=1)          # every rank's rows have landed in this rank's buffer
+        self.out.copy_(self.buf)             # frees the symmetric buffer for the next exchange (see pre())
+        return self.out
+
+
 def all_reduce_sums_(sums, group=None):
     """In-place SUM of the per-layer BatchNorm partial sums over the ranks."""
     if dist.is_initialized() and dist.get_world_size(group) > 1:

@@ -65,12 +65,28 @@ def _worker(rank, world, port, q):
         local = _build(dev)                                   # sharded, per-shard statistics (bench default)
         _, loc = local(xyz[lo:hi].contiguous(), None, start_idx=(st1[lo:hi].contiguous(), st2[lo:hi].contiguous()))
         err_local = float((loc.reshape(hi - lo, 1024) - want[lo:hi]).abs().max())
+        # the same exchange over peer memory (PeerAllGather) == the NCCL all-gather, bit for bit, over reuse
+        p2p = "unavailable"
+        try:
+            ag = pdist.PeerAllGather(hi - lo, 1024, dev)
+        except Exception as e:  # noqa: BLE001  (symmetric memory not supported on this box: reported, not failed)
+            ag, p2p = None, f"unavailable: {type(e).__name__}: {e}"
+        if ag is not None:
+            ok = True
+            for k in range(3):
+                loc_k = (got + float(k)).contiguous()
+                ag.pre()
+                full = ag.gather(loc_k)
+                ok = ok and bool(torch.equal(full, pdist.all_gather_features(loc_k)))
+            p2p = "equal" if ok else "DIFFERENT"
         torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
-        q.put((rank, "ok", err, err_g, err_rm, err_local))
+        q.put((rank, "ok", err, err_g, err_rm, err_local, p2p))
+        q.close()
+        q.join_thread()   # the result is in the pipe before the process leaves
+        os._exit(0)       # symmetric-memory handles + NCCL teardown order is not worth a hang in a test process
     except Exception:  # noqa: BLE001
-        q.put((rank, "error", traceback.format_exc(), 0, 0, 0))
+        q.put((rank, "error", traceback.format_exc(), 0, 0, 0, ""))
 
 
 def test_syncbn_sharded_equals_unsharded_nccl():
@@ -83,13 +99,14 @@ def test_syncbn_sharded_equals_unsharded_nccl():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=600) for _ in procs]
+    res = [q.get(timeout=240) for _ in procs]
     for p in procs:
         p.join(timeout=60)
-    for rank, status, err, err_g, err_rm, err_local in sorted(res):
+    for rank, status, err, err_g, err_rm, err_local, p2p in sorted(res):
         assert status == "ok", err
         print(f"rank {rank}: synced shard vs unsharded {err:.3e}, gathered {err_g:.3e}, running mean {err_rm:.3e}, "
-              f"per-shard statistics differ by {err_local:.3e}")
+              f"per-shard statistics differ by {err_local:.3e}; peer-memory all-gather vs NCCL: {p2p}")
+        assert p2p == "equal" or p2p.startswith("unavailable"), p2p
         # l3 features (|values| up to ~8) after three chained levels computed by two different kernel paths
         # (fused vs step-wise): the chain bound of tests/test_gpu_fullsize.py; measured 1.9e-5 on B200
         assert err <= 3e-5 and err_g <= 3e-5 and err_rm <= 1e-6
