@@ -282,17 +282,16 @@ fps_reg_kernel(const float *__restrict__ xyz, int N, int npoint,
 // All CTAs are co-resident (host: B + B*P <= number of SMs) and the FPS CTAs have the lowest block indices, so
 // the consumers' spin-waits cannot starve a producer.
 constexpr int kSgThreads = 512;   // consumer CTAs: 16 warps hide the scan's shared-memory latency
-constexpr int kSgFpsThreads = 128;  // the FPS role uses the first four warps of its CTA (the rest exit at once)
-
-template <int PPT>
+// the FPS role uses the first FT / 32 warps of its CTA (the rest exit at once)
+template <int FT, int PPT>
 __global__ void __launch_bounds__(kSgThreads)
 sample_group_kernel(const float *__restrict__ xyz, int B, int N, int npoint, const int64_t *__restrict__ start_idx,
                     float init_dist, int64_t *__restrict__ out_idx, float *__restrict__ out_new_xyz,
                     int32_t *__restrict__ pub, int P, float radius2, int K, int32_t *__restrict__ grp_idx,
                     int32_t *__restrict__ empty_count, double *__restrict__ mom_partial, int dbg) {
     if ((int)blockIdx.x < B) {
-        if (threadIdx.x >= kSgFpsThreads) return;
-        fps_reg_body<kSgFpsThreads, PPT, 0, true>(blockIdx.x, xyz, N, npoint, start_idx, init_dist, out_idx, out_new_xyz,
+        if (threadIdx.x >= FT) return;
+        fps_reg_body<FT, PPT, 0, true>(blockIdx.x, xyz, N, npoint, start_idx, init_dist, out_idx, out_new_xyz,
                                                pub + (size_t)blockIdx.x * npoint);
         return;
     }
@@ -514,17 +513,19 @@ extern "C" int papc_sample_group_f32(const float *xyz, int B, int N, int npoint,
 #ifdef PAPC_TRIAGE
     { const char *e = getenv("PAPC_SG_DBG"); dbg = e ? atoi(e) : 0; }
 #endif
-    if (N <= 512) {
-        auto k = sample_group_kernel<4>;
-        if (smem > 48 * 1024) PAPC_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<grid, kSgThreads, smem, st>>>(xyz, B, N, npoint, start_idx, init_dist, out_fps_idx, out_new_xyz, pub, P, radius2,
-                                           nsample, out_group_idx, empty_count, moments_partial, dbg);
-    } else {
-        auto k = sample_group_kernel<8>;
-        if (smem > 48 * 1024) PAPC_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<grid, kSgThreads, smem, st>>>(xyz, B, N, npoint, start_idx, init_dist, out_fps_idx, out_new_xyz, pub, P, radius2,
-                                           nsample, out_group_idx, empty_count, moments_partial, dbg);
-    }
+    // FPS role shape as papc_fps_f32 picks it (PAPC_FPS_WIDE=1: twice the warps, half the points per thread)
+    static const bool wide = [] { const char *e = getenv("PAPC_FPS_WIDE"); return e && atoi(e) == 1; }();
+#define SG_GO(FT, PPT)                                                                                              \
+    do {                                                                                                            \
+        auto k = sample_group_kernel<FT, PPT>;                                                                      \
+        if (smem > 48 * 1024)                                                                                       \
+            PAPC_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+        k<<<grid, kSgThreads, smem, st>>>(xyz, B, N, npoint, start_idx, init_dist, out_fps_idx, out_new_xyz, pub, P, \
+                                           radius2, nsample, out_group_idx, empty_count, moments_partial, dbg);     \
+    } while (0)
+    if (N <= 512) { if (wide) SG_GO(256, 2); else SG_GO(128, 4); }
+    else { if (wide) SG_GO(256, 4); else SG_GO(128, 8); }
+#undef SG_GO
     PAPC_LAUNCH_CHECK();
     return PAPC_OK;
 }

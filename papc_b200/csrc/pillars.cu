@@ -360,25 +360,45 @@ pfn_main_kernel(const float *__restrict__ features, const int32_t *__restrict__ 
         ssq[q] = 0.0;
     }
 
-    for (int p = blockIdx.x * kPfnWarps + warp; p < Pv; p += gridDim.x * kPfnWarps) {
-        int n = num_voxels[p];
-        n = min(max(n, 0), T);
-        const float *src = features + (size_t)p * T * F;
-        for (int i = lane; i < n * F; i += 32) mypts[i] = src[i];
+    // Software pipeline over the warp's pillars: the NEXT pillar's point count, cell and first 32 floats (8 points
+    // at F = 4 -- most pillars hold fewer) are requested before this pillar is computed, so the three dependent
+    // global round trips per pillar (count -> rows -> ...) overlap the arithmetic instead of serialising 48 000
+    // times (the kernel was latency bound at ~5 us per pillar and warp).
+    const int pstride = gridDim.x * kPfnWarps;
+    const int TF = T * F;
+    int n_nx = 0, cx_nx = 0, cy_nx = 0;
+    float v_nx = 0.f;
+    auto prefetch = [&](int pp) {
+        if (pp < Pv) {
+            n_nx = num_voxels[pp];
+            cx_nx = coors[(size_t)pp * 4 + 3];
+            cy_nx = coors[(size_t)pp * 4 + 2];
+            v_nx = lane < TF ? features[(size_t)pp * TF + lane] : 0.f;
+        }
+    };
+    prefetch(blockIdx.x * kPfnWarps + warp);
+    for (int p = blockIdx.x * kPfnWarps + warp; p < Pv; p += pstride) {
+        const int nraw = n_nx, cxi = cx_nx, cyi = cy_nx;
+        const float v0 = v_nx;
+        const int n = min(max(nraw, 0), T);
+        prefetch(p + pstride);
+        const float *src = features + (size_t)p * TF;
+        if (lane < n * F) mypts[lane] = v0;
+        for (int i = 32 + lane; i < n * F; i += 32) mypts[i] = src[i];
         __syncwarp();
         // sequential fp32 sums of x,y,z (lanes 0..2), divided by num_voxels as in pillars.py:82
         float mean = 0.f;
         if (lane < 3) {
             float s = 0.f;
             for (int t = 0; t < n; ++t) s = __fadd_rn(s, mypts[t * F + lane]);
-            mean = __fdiv_rn(s, (float)num_voxels[p]);
+            mean = __fdiv_rn(s, (float)nraw);
         }
         const float mx = __shfl_sync(0xffffffffu, mean, 0);
         const float my = __shfl_sync(0xffffffffu, mean, 1);
         const float mz = __shfl_sync(0xffffffffu, mean, 2);
         // pillar centre: coors[:,3]*vx + x_offset, coors[:,2]*vy + y_offset (pillars.py:87-88)
-        const float ccx = __fadd_rn(__fmul_rn((float)coors[p * 4 + 3], vx), x_off);
-        const float ccy = __fadd_rn(__fmul_rn((float)coors[p * 4 + 2], vy), y_off);
+        const float ccx = __fadd_rn(__fmul_rn((float)cxi, vx), x_off);
+        const float ccy = __fadd_rn(__fmul_rn((float)cyi, vy), y_off);
 
         float vmax[CPL], vmin[CPL], fs[CPL], fq[CPL];
 #pragma unroll

@@ -508,6 +508,30 @@ pool_finish_bsc_kernel(const float *__restrict__ pmax, const float *__restrict__
     }
 }
 
+// the same, four channels per thread (C % 4 == 0, 16-byte aligned buffers): 16-byte loads and stores, a quarter of
+// the instructions -- the scalar form ran at 1.6 TB/s on the 8 MB sa1 output
+__global__ void __launch_bounds__(256)
+pool_finish_bsc_v4_kernel(const float4 *__restrict__ pmax, const float4 *__restrict__ pmin,
+                          const float4 *__restrict__ scale, const float4 *__restrict__ shift, size_t total4,
+                          int C4, float4 *__restrict__ out) {
+    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; e < total4; e += stride) {
+        const int c = (int)(e % C4);
+        const float4 sc = __ldg(scale + c), sh = __ldg(shift + c);
+        const bool pos = sc.x >= 0.f && sc.y >= 0.f && sc.z >= 0.f && sc.w >= 0.f;   // the usual case: gamma > 0
+        const bool neg = sc.x < 0.f && sc.y < 0.f && sc.z < 0.f && sc.w < 0.f;
+        const float4 mx = neg ? make_float4(0.f, 0.f, 0.f, 0.f) : pmax[e];              // only the side that is used
+        const float4 mn = pos ? make_float4(0.f, 0.f, 0.f, 0.f) : pmin[e];
+        float4 o;
+        o.x = fmaxf(fmaf(sc.x >= 0.f ? mx.x : mn.x, sc.x, sh.x), 0.f);
+        o.y = fmaxf(fmaf(sc.y >= 0.f ? mx.y : mn.y, sc.y, sh.y), 0.f);
+        o.z = fmaxf(fmaf(sc.z >= 0.f ? mx.z : mn.z, sc.z, sh.z), 0.f);
+        o.w = fmaxf(fmaf(sc.w >= 0.f ? mx.w : mn.w, sc.w, sh.w), 0.f);
+        out[e] = o;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 pool_finish_bcs_kernel(const float *__restrict__ pmax, const float *__restrict__ pmin,
                        const float *__restrict__ scale, const float *__restrict__ shift, int S, int C,
@@ -857,10 +881,20 @@ extern "C" int papc_sa_pool_finish_f32(const float *pool_max, const float *pool_
     ProfScope prof(st, "pool_finish", (long long)B * S, 0, cout, 0.0, 12.0 * B * S * cout);
     if (out_layout == PAPC_OUT_BSC || S == 1) {  // [B,C,1] and [B,1,C] are the same bytes
         const size_t total = (size_t)B * S * cout;
-        size_t blocks = (total + 255) / 256;
-        if (blocks > (size_t)kNumSMs * 16) blocks = (size_t)kNumSMs * 16;
-        pool_finish_bsc_kernel<<<(unsigned)blocks, 256, 0, st>>>(pool_max, pool_min, scale, shift,
-                                                                 total, cout, out);
+        auto al16 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+        if (cout % 4 == 0 && al16(pool_max) && al16(pool_min) && al16(scale) && al16(shift) && al16(out)) {
+            size_t blocks = (total / 4 + 255) / 256;
+            if (blocks > (size_t)kNumSMs * 8) blocks = (size_t)kNumSMs * 8;
+            pool_finish_bsc_v4_kernel<<<(unsigned)blocks, 256, 0, st>>>(
+                reinterpret_cast<const float4 *>(pool_max), reinterpret_cast<const float4 *>(pool_min),
+                reinterpret_cast<const float4 *>(scale), reinterpret_cast<const float4 *>(shift), total / 4, cout / 4,
+                reinterpret_cast<float4 *>(out));
+        } else {
+            size_t blocks = (total + 255) / 256;
+            if (blocks > (size_t)kNumSMs * 16) blocks = (size_t)kNumSMs * 16;
+            pool_finish_bsc_kernel<<<(unsigned)blocks, 256, 0, st>>>(pool_max, pool_min, scale, shift,
+                                                                     total, cout, out);
+        }
     } else {
         if (B > 65535) return PAPC_EUNSUPPORTED;
         dim3 grid(ceil_div(S, 32), ceil_div(cout, 32), B);
