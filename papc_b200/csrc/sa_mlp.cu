@@ -653,6 +653,8 @@ struct TtOpts {
     bool dry_run;             // only report eligibility
     bool pdl;                 // the previous stream operation is one of this call's kernels: overlap
                               // this launch's prologue with its tail (programmatic dependent launch)
+    void *ximg = nullptr;     // workspace for the activation image of small-M fp16 layers (tt::ximg_bytes), nullable
+    size_t ximg_bytes = 0;
 };
 
 // Tries the transposed tcgen05 kernel.  Returns 1 if launched (or, dry_run, launchable), 0 if the
@@ -697,6 +699,10 @@ static int try_tt(const LayerArgs &a, bool gather, int K, const FusedBn *bn, con
     const size_t wneed = tt::wimg_bytes(t.prec, t.cin, t.cout);
     if (wneed > 0 && (o.wimg == nullptr || o.wimg_bytes < wneed || !aligned16(o.wimg))) return 0;
     t.wimg = o.wimg;
+    {
+        const size_t xneed = tt::ximg_bytes(t.M, t.cin, t.cout);
+        t.ximg = (xneed > 0 && o.ximg != nullptr && o.ximg_bytes >= xneed && aligned16(o.ximg)) ? o.ximg : nullptr;
+    }
     if (o.dry_run) return 1;
     if (bn != nullptr && a.stats_partial != nullptr) {
         t.counter = bn->counter;
@@ -910,6 +916,7 @@ static bool pointmlp_shape_ok(int c0) { return c0 >= 16 && c0 <= 128 && c0 % 16 
 struct WsPlan {
     size_t y[2], pool_max, pool_min, partial, sums, scale, shift, wimg, wimg_bytes;
     size_t counters, fold, mom_partial, colscale, colscale_stride, total;
+    size_t ximg, ximg_bytes;   // activation image of the small-M fp16 layers (tt::ximg_bytes), 0 = none
     size_t counters_bytes;  // 256 bytes of counters + the fixed-point statistic accumulators (see FusedBn)
     // chained path (sa_chain.cu): 0 = off, 1 = points only (folded first layer), 2 = gathered source image
     int chain;
@@ -992,6 +999,17 @@ static int plan_ws(const papc_group_source *src, const papc_mlp *mlp, WsPlan *p)
     }
     p->wimg_bytes = wb;
     p->wimg = take(wb);
+    size_t xb = 0;
+    c_in = mlp->cin;
+    for (int l = 0; l < mlp->num_layers; ++l) {
+        if (l > 0) {
+            const size_t b = tt::ximg_bytes(M, c_in, mlp->layers[l].cout);
+            xb = b > xb ? b : xb;
+        }
+        c_in = mlp->layers[l].cout;
+    }
+    p->ximg_bytes = xb;
+    p->ximg = take(xb);
     p->counters_bytes = 256 + ((size_t)4 * maxc + 8) * sizeof(unsigned long long);
     p->counters = take(p->counters_bytes);
     p->fold = take((size_t)128 * 4 * sizeof(float));
@@ -1293,6 +1311,7 @@ extern "C" int papc_sa_mlp_f32(const papc_group_source *src, const papc_mlp *mlp
         TtOpts o{this_f16 ? tt::PREC_F16 : tt::PREC_TF32,
                  this_f16 ? mlp->layers[l - 1].gamma : nullptr, this_f16 ? mlp->layers[l - 1].beta : nullptr,
                  sqrt_m, nullptr, ws + p.wimg, p.wimg_bytes, false, prev_is_kernel};
+        if (p.ximg_bytes > 0) { o.ximg = ws + p.ximg; o.ximg_bytes = p.ximg_bytes; }
         bool fused_done = false;
         if (folded && l == 1) {
             LayerArgs a{};

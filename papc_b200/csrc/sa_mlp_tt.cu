@@ -273,6 +273,45 @@ prep_wimg_kernel(const float *__restrict__ W, int wld, int wk0, int cin, int cou
     }
 }
 
+// ------------------------------------------------------------------ activation image (SRC_PLAIN, small M)
+// img: [tiles_m][KC][hi | lo][128 rows][128 B], the layout the producers write into an operand stage, holding
+// relu(in_scale[k] * x[row][k] + in_shift[k]) split into fp16 hi / lo.  Rows >= M and columns >= cin are zero.
+__global__ void __launch_bounds__(256)
+prep_ximg_kernel(const float *__restrict__ x, long long M, int cin, const float *__restrict__ in_scale,
+                 const float *__restrict__ in_shift, int KC, uint8_t *__restrict__ img) {
+    using P = Prec<PREC_F16>;
+    const long long tiles_m = ceil_div<long long>(M, kTile);
+    const long long total = tiles_m * KC * kTile * 8;  // one 16-byte unit (8 halves) per thread step
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const int u = (int)(e & 7);
+        const int r = (int)((e >> 3) & (kTile - 1));
+        const int c = (int)((e >> 10) % KC);
+        const long long tm = (e >> 10) / KC;
+        const long long row = tm * kTile + r;
+        const int k0 = c * P::kEPC + u * P::kEPU;
+        float v[P::kEPU];
+#pragma unroll
+        for (int q = 0; q < P::kEPU; ++q) v[q] = 0.f;
+        if (row < M && k0 < cin) {   // cin % 8 == 0: whole units are valid or not
+            const float4 a0 = *reinterpret_cast<const float4 *>(x + row * cin + k0);
+            const float4 a1 = *reinterpret_cast<const float4 *>(x + row * cin + k0 + 4);
+            const float4 s0 = *reinterpret_cast<const float4 *>(in_scale + k0), s1 = *reinterpret_cast<const float4 *>(in_scale + k0 + 4);
+            const float4 h0 = *reinterpret_cast<const float4 *>(in_shift + k0), h1 = *reinterpret_cast<const float4 *>(in_shift + k0 + 4);
+            v[0] = fmaxf(fmaf(a0.x, s0.x, h0.x), 0.f); v[1] = fmaxf(fmaf(a0.y, s0.y, h0.y), 0.f);
+            v[2] = fmaxf(fmaf(a0.z, s0.z, h0.z), 0.f); v[3] = fmaxf(fmaf(a0.w, s0.w, h0.w), 0.f);
+            v[4] = fmaxf(fmaf(a1.x, s1.x, h1.x), 0.f); v[5] = fmaxf(fmaf(a1.y, s1.y, h1.y), 0.f);
+            v[6] = fmaxf(fmaf(a1.z, s1.z, h1.z), 0.f); v[7] = fmaxf(fmaf(a1.w, s1.w, h1.w), 0.f);
+        }
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) split_f16x2(v[2 * q], v[2 * q + 1], hi[q], lo[q]);
+        uint8_t *blk = img + ((size_t)(tm * KC + c) * 2) * kHalfBytes + (size_t)r * 128 + ((u ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4 *>(blk) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4 *>(blk + kHalfBytes) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
 // --------------------------------------------------------------------------------- main kernel
 // WMODE 0: W resident in tensor memory (TS UMMA).  WMODE 1: W chunks streamed through the ring.
 template <int MODE, int PREC, int WMODE, bool POOL>
@@ -1014,6 +1053,30 @@ mlp_layer_tt_kernel(const __grid_constant__ TtArgs a) {
                     ++it;
                     if (cq == KC - 1) ++ptl;
                 }
+        } else if (MODE == SRC_PLAIN && a.ximg_on) {
+            // the activations were converted once by prep_ximg_kernel: every chunk is ONE bulk copy of the
+            // pre-split [hi | lo] block (plus the W chunk when W is streamed); no producer arithmetic at all
+            const uint8_t *ximg = reinterpret_cast<const uint8_t *>(a.ximg);
+            for (long long t = tile0; t < tiles_m; t += gm)
+                for (int cq = 0; cq < KC; ++cq) {
+                    const uint32_t s = it % kStages;
+                    mbar_wait(x_empty + s, ((it / kStages) & 1) ^ 1);
+                    if (ptid == 0) {
+                        uint8_t *stage_p = smem + SmemLayout::ring + s * kStageBytes;
+                        if (WMODE == 1) {
+                            mbar_expect_tx(x_full + s, 2 * kXBytes);   // the issuer's arrival is part of the count
+                            bulk_g2s(stage_p + kXBytes, wimg + ((size_t)tile_n * KC + cq) * kXBytes, kXBytes, x_full + s);
+                        } else {
+                            mbar_expect_tx_only(x_full + s, kXBytes);
+                        }
+                        bulk_g2s(stage_p, ximg + ((size_t)t * KC + cq) * kXBytes, kXBytes, x_full + s);
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(x_full + s);
+                    if (ptid == 0 && it == 0) TT_GCLK(a, 10);
+                    ++it;
+                    if (cq == KC - 1) ++ptl;
+                }
         } else if (MODE == SRC_POINTMLP) {
             if (tile0 < tiles_m && ptid < kTile) {
                 fetch_idx1(tile0);                      // idx of the first tile
@@ -1428,6 +1491,15 @@ void make_fastdiv(uint32_t d, uint32_t *mul, uint32_t *shr) {
     *shr = p - 32u;
 }
 
+size_t ximg_bytes(long long M, int cin, int cout) {
+    // worth it when a row tile feeds several channel tiles and there are few row tiles (small-M layers: today
+    // every channel tile's CTA converts the same activation rows again)
+    const long long tiles_m = ceil_div<long long>(M, kTile);
+    const int nt = ceil_div(cout, kTile);
+    if (M <= 0 || cin < 8 || cin % 8 != 0 || nt < 2 || tiles_m > 128) return 0;
+    return (size_t)tiles_m * ceil_div(cin, Prec<PREC_F16>::kEPC) * kXBytes;
+}
+
 bool eligible(const TtProblem &p) {
     if (p.prec != PREC_TF32 && p.prec != PREC_F16) return false;
     if (p.cout < 1 || p.cout > 8 * kTile) return false;
@@ -1580,6 +1652,23 @@ int launch(const TtArgs &a_in, cudaStream_t st) {
     {
         const char *e = getenv("PAPC_TT_PDL");  // A/B switch: PAPC_TT_PDL=0 disables dependent launch
         if (streamed || (e && e[0] == '0')) a.pdl = 0;  // (the W-image kernel sits in between)
+    }
+    a.ximg_on = 0;
+    {
+        static const bool ximg_off = [] { const char *e = getenv("PAPC_TT_XIMG"); return e && e[0] == '0'; }();  // A/B switch
+        const size_t xb = ximg_bytes(a.M, a.cin, a.cout);
+        if (!ximg_off && a.mode == SRC_PLAIN && a.prec == PREC_F16 && a.in_scale != nullptr && a.in_shift != nullptr &&
+            a.ximg != nullptr && xb > 0 && (reinterpret_cast<uintptr_t>(a.x) & 15u) == 0 &&
+            (reinterpret_cast<uintptr_t>(a.in_scale) & 15u) == 0 && (reinterpret_cast<uintptr_t>(a.in_shift) & 15u) == 0) {
+            const int KCx = ceil_div(a.cin, epc(a.prec));
+            long long blocks = (ceil_div<long long>(a.M, kTile) * KCx * kTile * 8 + 255) / 256;
+            if (blocks > 8LL * kNumSMs) blocks = 8LL * kNumSMs;
+            prep_ximg_kernel<<<(unsigned)blocks, 256, 0, st>>>(a.x, a.M, a.cin, a.in_scale, a.in_shift, KCx,
+                                                               reinterpret_cast<uint8_t *>(a.ximg));
+            PAPC_LAUNCH_CHECK();
+            a.ximg_on = 1;
+            a.pdl = 0;   // the image kernel sits between the previous layer and this launch
+        }
     }
     if (streamed) {
         if (a.wimg == nullptr) return PAPC_EWORKSPACE;

@@ -46,6 +46,11 @@ struct TtArgs {
     // that kernel writes); griddepcontrol.wait precedes every dependent access
     int pdl;
     void *wimg;                  // streamed-W mode: workspace for the pre-split, pre-swizzled image
+    // SRC_PLAIN, fp16 split, small M (few row tiles, several channel tiles): workspace (ximg_bytes(M, cin), nullable)
+    // for a pre-split image of the ACTIVATIONS.  launch() then converts relu(bn(x)) once (prep_ximg_kernel) and
+    // every CTA streams its operand chunks by TMA instead of converting the same rows once per channel tile.
+    void *ximg;
+    int ximg_on;                 // filled in by launch()
     const float *bias;
     float *y;                    // [M,cout] pre-BN output (nullable)
     float *pool_max, *pool_min;  // [M/K,cout] (nullable)
@@ -91,6 +96,8 @@ bool eligible(const TtProblem &p);
 void make_fastdiv(uint32_t d, uint32_t *mul, uint32_t *shr);
 // Bytes of the streamed-W image the launch needs in TtArgs::wimg (0 = W fits in tensor memory).
 size_t wimg_bytes(int prec, int cin, int cout);
+// Bytes of the activation image for an [M, cin] fp16-split layer (0 = the layer does not use one).
+size_t ximg_bytes(long long M, int cin, int cout);
 int launch(const TtArgs &a, cudaStream_t st);
 
 // 2^e (e >= 0) with relu(bn(y)) / 2^e < 2^15 for every possible y: |bn(y)| <= |gamma| sqrt(count) +

@@ -25,6 +25,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
                  "r"(bytes)
                  : "memory");
 }
+// expect-tx WITHOUT an arrival (the arrival count of the barrier is owned by other threads)
+__device__ __forceinline__ void mbar_expect_tx_only(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
 // try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or the
 // hint, in ns, elapses) instead of being woken every ~70 cycles to spin -- in the layer kernels the
 // waiting warps' spin loops were a third of all issued instructions, taken from the warps that work.
