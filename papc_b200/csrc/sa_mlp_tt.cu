@@ -232,6 +232,9 @@ prep_wimg_kernel(const float *__restrict__ W, int wld, int wk0, int cin, int cou
                  const float *__restrict__ cs_beta, float cs_sqrt_count, int KC,
                  uint8_t *__restrict__ img) {
     using P = Prec<PREC>;
+    // the layer kernel that follows is launched as a programmatic dependent of THIS kernel: let its CTAs start
+    // their prologue (barriers, tensor memory, weight staging) now; it reads the image only after griddepcontrol.wait
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int nt = ceil_div(cout, kTile);
     const long long total = (long long)nt * KC * kTile * 8;  // one 16-byte unit per thread step
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
@@ -280,6 +283,7 @@ __global__ void __launch_bounds__(256)
 prep_ximg_kernel(const float *__restrict__ x, long long M, int cin, const float *__restrict__ in_scale,
                  const float *__restrict__ in_shift, int KC, uint8_t *__restrict__ img) {
     using P = Prec<PREC_F16>;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // see prep_wimg_kernel
     const long long tiles_m = ceil_div<long long>(M, kTile);
     const long long total = tiles_m * KC * kTile * 8;  // one 16-byte unit (8 halves) per thread step
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
@@ -1651,7 +1655,11 @@ int launch(const TtArgs &a_in, cudaStream_t st) {
     const int nt = ceil_div(a.cout, kTile);
     {
         const char *e = getenv("PAPC_TT_PDL");  // A/B switch: PAPC_TT_PDL=0 disables dependent launch
-        if (streamed || (e && e[0] == '0')) a.pdl = 0;  // (the W-image kernel sits in between)
+        // a streamed-W / activation-image launch has its image kernel(s) as stream predecessor: still a dependent
+        // launch -- the image kernels release their dependents at once, so this kernel's prologue overlaps them, and
+        // griddepcontrol.wait returns only when they (hence everything before them) are complete
+        if (streamed) a.pdl = 1;
+        if (e && e[0] == '0') a.pdl = 0;
     }
     a.ximg_on = 0;
     {
@@ -1667,7 +1675,7 @@ int launch(const TtArgs &a_in, cudaStream_t st) {
                                                                reinterpret_cast<uint8_t *>(a.ximg));
             PAPC_LAUNCH_CHECK();
             a.ximg_on = 1;
-            a.pdl = 0;   // the image kernel sits between the previous layer and this launch
+            if (a.pdl == 0) { const char *e = getenv("PAPC_TT_PDL"); a.pdl = (e && e[0] == '0') ? 0 : 1; }
         }
     }
     if (streamed) {
