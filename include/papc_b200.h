@@ -184,6 +184,10 @@ typedef struct papc_group_source {
     const double *xyz_moments; /* nullable: [xyz_moment_rows][9] partial sums (x, y, z, xx, xy, xz, yy, yz, zz)  */
     int32_t xyz_moment_rows;   /* of the centred grouped points over all M rows, as papc_sample_group_f32      */
     int32_t reserved;          /* writes them: the folded first layer (D = 0) then skips its own gather pass    */
+    const float *feats_colscale; /* nullable: [D] powers of two c_k with 0 <= feats[.,k] / c_k < 2^15 for every      */
+                                 /* row -- true for post-ReLU outputs of a BatchNorm layer with c_k >= (|gamma_k|  */
+                                 /* sqrt(count) + |beta_k|) / 32000.  Lets the first MLP layer run the fp16 operand  */
+                                 /* split (half the tensor-core products of the 3xTF32 form); NULL = 3xTF32         */
 } papc_group_source;
 
 typedef struct papc_mlp_layer {

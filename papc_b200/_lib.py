@@ -30,7 +30,8 @@ class GroupSource(C.Structure):
     _fields_ = [("grouped", _vp), ("xyz", _vp), ("new_xyz", _vp), ("feats", _vp), ("idx", _vp),
                 ("B", C.c_int32), ("N", C.c_int32), ("S", C.c_int32), ("K", C.c_int32),
                 ("D", C.c_int32), ("order", C.c_int32),
-                ("xyz_moments", _vp), ("xyz_moment_rows", C.c_int32), ("reserved", C.c_int32)]
+                ("xyz_moments", _vp), ("xyz_moment_rows", C.c_int32), ("reserved", C.c_int32),
+                ("feats_colscale", _vp)]
 
 
 class MlpLayer(C.Structure):

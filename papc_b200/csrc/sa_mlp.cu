@@ -655,6 +655,7 @@ struct TtOpts {
                               // this launch's prologue with its tail (programmatic dependent launch)
     void *ximg = nullptr;     // workspace for the activation image of small-M fp16 layers (tt::ximg_bytes), nullable
     size_t ximg_bytes = 0;
+    const float *gather_colscale = nullptr;   // SRC_GATHER + PREC_F16: papc_group_source.feats_colscale
 };
 
 // Tries the transposed tcgen05 kernel.  Returns 1 if launched (or, dry_run, launchable), 0 if the
@@ -680,6 +681,12 @@ static int try_tt(const LayerArgs &a, bool gather, int K, const FusedBn *bn, con
         t.l0_fold = o.l0_fold;
     } else if (gather) {
         if (a.D < 4 || !aligned16(a.feats)) return 0;
+        if (o.prec == tt::PREC_F16) {   // bounded (post-ReLU) features: the caller's column scale on both operands
+            if (o.gather_colscale == nullptr || a.D % 8 != 0 || !aligned16(o.gather_colscale)) return 0;
+            t.x_colscale = o.gather_colscale;
+            t.w_colscale = o.gather_colscale;
+            t.cs_on = 0;
+        }
         t.mode = tt::SRC_GATHER;
         t.cin = a.D;
         t.xyz = a.xyz; t.new_xyz = a.new_xyz; t.feats = a.feats; t.idx = a.idx;
@@ -1312,6 +1319,20 @@ extern "C" int papc_sa_mlp_f32(const papc_group_source *src, const papc_mlp *mlp
                  this_f16 ? mlp->layers[l - 1].gamma : nullptr, this_f16 ? mlp->layers[l - 1].beta : nullptr,
                  sqrt_m, nullptr, ws + p.wimg, p.wimg_bytes, false, prev_is_kernel};
         if (p.ximg_bytes > 0) { o.ximg = ws + p.ximg; o.ximg_bytes = p.ximg_bytes; }
+        if (l == 0 && !src->grouped && src->feats != nullptr && src->feats_colscale != nullptr && src->D % 8 == 0) {
+            // gathered layer 0 on features the caller bounds (post-ReLU outputs of the previous SetAbstraction
+            // layer): fp16 split instead of 3xTF32 -- half the tensor-core products, 64 instead of 32 reduction
+            // elements per operand chunk.  Falls back to 3xTF32 inside layer_forward when the shape does not fit.
+            TtOpts probe = o;
+            probe.prec = tt::PREC_F16; probe.gather_colscale = src->feats_colscale; probe.dry_run = true;
+            bool fd = false;
+            if (layer_forward(src, nullptr, nullptr, nullptr, M, cin, ly.cout, src->K, ly.weight, ly.bias, y,
+                              last ? pmax : nullptr, last ? pmin : nullptr, batch ? partial : nullptr, ws + p.wimg,
+                              p.wimg_bytes, batch ? &bn : nullptr, &probe, &fd, stream) == 1) {
+                o.prec = tt::PREC_F16;
+                o.gather_colscale = src->feats_colscale;
+            }
+        }
         bool fused_done = false;
         if (folded && l == 1) {
             LayerArgs a{};

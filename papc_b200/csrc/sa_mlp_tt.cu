@@ -754,7 +754,7 @@ mlp_layer_tt_kernel(const __grid_constant__ TtArgs a) {
         const int u = ptid & 7;       // 16-byte unit inside the 128-byte chunk row
         const int rb = ptid >> 3;     // rows rb + kRowStride*j, j = 0..kRPT-1
         const uint32_t swz = (uint32_t)((u ^ (rb & 7)) << 4);
-        const bool has_act = (MODE == SRC_PLAIN) && a.in_scale != nullptr;
+        const bool has_act = (MODE == SRC_PLAIN && a.in_scale != nullptr) || (MODE == SRC_GATHER && a.x_colscale != nullptr);
         // the tensor-map descriptor lives in the kernel parameters: have the TMA unit fetch it while
         // this kernel still waits for the previous one (PAPC_TT_DBG=512 switches the prefetch off;
         // measured on the B200: no difference in the step time either way)
@@ -766,6 +766,14 @@ mlp_layer_tt_kernel(const __grid_constant__ TtArgs a) {
         if (MODE == SRC_POINTMLP && ptid < kMaxFold)
             s_fold[ptid] = ptid < a.cin ? reinterpret_cast<const float4 *>(a.l0_fold)[ptid]
                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (MODE == SRC_GATHER && a.x_colscale != nullptr) {
+            // fp16-split gather: features are >= 0 (post-ReLU) and bounded; "activation" = division by the
+            // power-of-two column scale (exact), through the same scale / shift table the PLAIN mode uses
+            for (int k = ptid; k < kMaxAct; k += kProdThreads) {
+                s_scale[k] = k < a.cin ? __frcp_rn(__ldg(a.x_colscale + k)) : 0.f;
+                s_shift[k] = 0.f;
+            }
+        }
         if (MODE != SRC_PLAIN) named_bar_sync(1, kProdThreads);
 
         // ---- per-row geometry pipeline (SRC_GATHER / SRC_POINTMLP)
@@ -1513,7 +1521,7 @@ bool eligible(const TtProblem &p) {
     } else if (p.cin > kMaxAct && !(p.mode == SRC_PLAIN && p.no_act)) {
         return false;  // the scale / shift / column-scale tables hold kMaxAct channels
     }
-    if (p.mode == SRC_GATHER && (p.D != p.cin || p.prec != PREC_TF32)) return false;
+    if (p.mode == SRC_GATHER && p.D != p.cin) return false;
     if (p.pool && !(p.K == 32 || p.K == 64 || p.K == 128)) return false;
     return true;
 }
@@ -1733,7 +1741,8 @@ int launch(const TtArgs &a_in, cudaStream_t st) {
                                     : launch_mp<SRC_PLAIN, PREC_TF32>(a, streamed, pool, grid, st);
             break;
         case SRC_GATHER:
-            rc = launch_mp<SRC_GATHER, PREC_TF32>(a, streamed, pool, grid, st);
+            rc = a.prec == PREC_F16 ? launch_mp<SRC_GATHER, PREC_F16>(a, streamed, pool, grid, st)
+                                    : launch_mp<SRC_GATHER, PREC_TF32>(a, streamed, pool, grid, st);
             break;
         case SRC_POINTMLP:
             rc = a.prec == PREC_F16 ? launch_mp<SRC_POINTMLP, PREC_F16>(a, streamed, pool, grid, st)

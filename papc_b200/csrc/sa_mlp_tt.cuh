@@ -25,6 +25,10 @@ struct TtArgs {
     // SRC_PLAIN
     const float *x, *in_scale, *in_shift;
     // SRC_GATHER / SRC_POINTMLP
+    // SRC_GATHER with the fp16 split (prec == PREC_F16): x_colscale [D] are powers of two with
+    // 0 <= feats[., k] / x_colscale[k] < 2^15 guaranteed by the caller (post-ReLU features of a BatchNorm layer,
+    // bound |gamma| sqrt(count) + |beta|); the producers divide by it, w_colscale (= the same array) multiplies W.
+    const float *x_colscale;
     const float *xyz, *new_xyz, *feats;
     const int32_t *idx;
     int N, S, D;

@@ -519,8 +519,46 @@ class _MlpRunner:
             self._update_running(stats)
 
 
-def _make_src(xyz, new_xyz, feats, idx32, B, N, S, K, order, moments=None):
+# fp16 operand split for the GATHERED first layer of a SetAbstraction module fed by post-ReLU features: built,
+# parity-green, and measured SLOWER on B200 than 3xTF32 (sa2.l1 102 vs 74 us, sa3.l1 37 vs 25 us: the kernel is
+# bound by its producer warps, and the fp16 split + the column-scale division cost more producer instructions per
+# element than the TF32 split saves in tensor-core products) -- off unless PAPC_F16_GATHER=1.
+F16_GATHER = os.environ.get("PAPC_F16_GATHER", "0") == "1"
+
+
+def _feature_colscale(bn, count):
+    """Powers of two c_k with 0 <= relu(bn(y))[., k] / c_k < 2^15 for ANY input of a train-mode BatchNorm over
+    ``count`` rows: a sample is at most sqrt(count - 1) standard deviations from the batch mean, so
+    |bn(y)| <= |gamma| sqrt(count) + |beta| (the same bound the layer kernels use between MLP layers,
+    f16_colscale_sq in sa_mlp_tt.cuh).  Cached on the holder; recomputed when gamma / beta change."""
+    key = (bn.weight.data_ptr(), bn.weight._version, bn.bias.data_ptr(), bn.bias._version, int(count))
+    cache = getattr(bn, "_papc_cs", None)
+    if cache is not None and cache[0] == key:
+        return cache[1]
+    bound = (bn.weight.double().abs() * math.sqrt(float(count)) + bn.bias.double().abs()) * 1.001
+    cs = torch.exp2(torch.ceil(torch.log2(torch.clamp(bound / 32000.0, min=1.0)))).to(torch.float32).contiguous()
+    bn._papc_cs = (key, cs)
+    return cs
+
+
+def _tag_colscale(t, cs):
+    """Attach the bound of a layer's post-ReLU output features (consumed by the next layer's gather kernel)."""
+    t._papc_colscale = (cs, t._version)
+    return t
+
+
+def _colscale_of(t, D):
+    tag = getattr(t, "_papc_colscale", None) if t is not None else None
+    if tag is None or not F16_GATHER:
+        return None
+    cs, version = tag
+    return cs if (t._version == version and cs.numel() == D and cs.device == t.device) else None
+
+
+def _make_src(xyz, new_xyz, feats, idx32, B, N, S, K, order, moments=None, feats_colscale=None):
     src = L.GroupSource()
+    if feats_colscale is not None:   # [D] power-of-two bounds of the (post-ReLU) feature columns: fp16-split layer 0
+        src.feats_colscale = feats_colscale.data_ptr()
     if moments is not None:   # [rows,9] fp64 partial sums from the fused sampling kernel (D = 0 layers)
         src.xyz_moments = moments.data_ptr()
         src.xyz_moment_rows = moments.shape[0]
@@ -606,6 +644,7 @@ class PointNetSetAbstraction(_SAMixin):
         L.require_cuda(xyz, points)
         ready = _ready_event(xyz)
         entry_ev = _entry_event(xyz.device) if not self.group_all else None
+        fcs = _colscale_of(points, points.shape[1]) if points is not None else None
         xyz = L.f32c(xyz.transpose(1, 2))                                  # :203
         feats = L.f32c(points.transpose(1, 2)) if points is not None else None  # :205
         B, N, Cc = xyz.shape
@@ -618,8 +657,8 @@ class PointNetSetAbstraction(_SAMixin):
         if self.group_all:                                                 # :211
             new_xyz = torch.zeros((B, 1, 3), dtype=torch.float32, device=dev)
             S = 1
-            src = _make_src(xyz, None, feats, None, B, N, 1, N, L.XYZ_FIRST)
-            keep = (xyz, feats)
+            src = _make_src(xyz, None, feats, None, B, N, 1, N, L.XYZ_FIRST, feats_colscale=fcs)
+            keep = (xyz, feats, fcs)
         else:                                                              # :213
             S = self.npoint
             if self.nsample > N:
@@ -628,14 +667,19 @@ class PointNetSetAbstraction(_SAMixin):
                                                want_moments=True)
             if feats is not None or self.bn_mode != "batch":
                 mom = None        # only the folded first layer (features = centred xyz, batch statistics) reads them
-            src = _make_src(xyz, new_xyz, feats, idx, B, N, S, self.nsample, L.XYZ_FIRST, moments=mom)
-            keep = (xyz, feats, new_xyz, idx, mom)
+            src = _make_src(xyz, new_xyz, feats, idx, B, N, S, self.nsample, L.XYZ_FIRST, moments=mom, feats_colscale=fcs)
+            keep = (xyz, feats, new_xyz, idx, mom, fcs)
         out = _MlpRunner(self.mlp_convs, self.mlp_bns).run(                # :214-219
             src, keep, 3 + D, B, S, self.bn_mode, dev, self.update_running_stats, self._sync_group())
         out_xyz = new_xyz.transpose(1, 2)
         if not self.group_all:
             _tag_ready(out_xyz, ev, entry_ev)
-        return out_xyz, out.transpose(1, 2)                                # :220-221
+        out_feats = out.transpose(1, 2)
+        if self.bn_mode == "batch" and not self._sync_group()[0]:
+            # post-ReLU outputs of a batch-statistics BatchNorm over B*S*K rows: bounded, and the next layer's
+            # gather kernel can use the fp16 operand split on them
+            _tag_colscale(out_feats, _feature_colscale(self.mlp_bns[-1], B * S * (N if self.group_all else self.nsample)))
+        return out_xyz, out_feats                                          # :220-221
 
 
 class PointNetSetAbstractionMsg(_SAMixin):

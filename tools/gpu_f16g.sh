@@ -1,0 +1,7 @@
+#!/bin/bash
+timeout 600 python -m pytest tests/test_gpu_sa.py tests/test_gpu_models.py tests/test_gpu_chain.py tests/test_gpu_fullsize.py tests/test_gpu_reference_models.py tests/test_gpu_reference_source.py -m gpu -q -x --timeout 400 -p no:cacheprovider 2>&1 | tail -4
+for f in 1 0; do PAPC_F16_GATHER=$f timeout 200 python bench.py --steps 30 --warmup 5 --no-extra 2>/dev/null | python -c "
+import sys, json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print('f16gather=$f', d['value'], d['ms_per_step']); print([(k['name'][:34],k['M'],k['cin'],k['cout'],k['avg_ms']) for k in d['roofline']['kernels'] if 'gather' in k['name']])"; done
