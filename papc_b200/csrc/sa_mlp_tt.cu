@@ -152,6 +152,20 @@ __device__ __forceinline__ void split_f16x2(float a, float b, uint32_t &hi, uint
     lo = *reinterpret_cast<const uint32_t *>(&l);
 }
 
+// The same split with the ReLU folded into the two conversions (every fp16-split operand is a post-ReLU
+// activation): hi = relu(rz_f16(v)) -- rounded TOWARD ZERO so that the residual of a positive v is >= 0 --
+// and lo = relu(rn_f16(v - hi)).  v < 0: hi = 0, residual = v < 0 -> lo = 0.  v >= 0: v - hi is exact and
+// non-negative, the second ReLU does nothing.  |v - (hi + lo)| <= 2^-22 |v|, as for the round-to-nearest
+// pair; saves the FMNMX per element in the producer warps, which bound the layer kernels.
+__device__ __forceinline__ void split_relu_f16x2(float a, float b, uint32_t &hi, uint32_t &lo) {
+    asm("cvt.rz.relu.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));   // first source -> upper half
+    const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&hi));
+    // residual as ONE packed FMA: (a, b) + (-1, -1) * (f.x, f.y), exact
+    float ra, rb;
+    unpack2(fma2(pack2(f.x, f.y), pack2(-1.f, -1.f), pack2(a, b)), ra, rb);
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
+}
+
 // Shared memory: the small fixed tables first, then the operand ring (read by the tensor core) and
 // the raw ring (fp32 activations landed by cp.async, thread-private slots), sized per instantiation.
 struct SmemLayout {
@@ -959,7 +973,11 @@ mlp_layer_tt_kernel(const __grid_constant__ TtArgs a) {
 #pragma unroll
                     for (int j = 0; j < kRPT; ++j) {
                         const float4 w = v[j][h];
-                        if (has_act) {
+                        if (has_act && PREC == PREC_F16) {
+                            // BatchNorm as two packed FMAs; the ReLU happens inside the fp16 conversions below
+                            unpack2(fma2(pack2(w.x, w.y), pack2(sc.x, sc.y), pack2(sh.x, sh.y)), o[j][4 * h + 0], o[j][4 * h + 1]);
+                            unpack2(fma2(pack2(w.z, w.w), pack2(sc.z, sc.w), pack2(sh.z, sh.w)), o[j][4 * h + 2], o[j][4 * h + 3]);
+                        } else if (has_act) {
                             o[j][4 * h + 0] = fmaxf(fmaf(w.x, sc.x, sh.x), 0.f);
                             o[j][4 * h + 1] = fmaxf(fmaf(w.y, sc.y, sh.y), 0.f);
                             o[j][4 * h + 2] = fmaxf(fmaf(w.z, sc.z, sh.z), 0.f);
@@ -996,7 +1014,8 @@ mlp_layer_tt_kernel(const __grid_constant__ TtArgs a) {
 #pragma unroll
                     for (int j = 0; j < kRPT; ++j) {
                         const float4 p = p_cur[j];
-                        o[j][q] = fmaxf(fmaf(f.x, p.x, fmaf(f.y, p.y, fmaf(f.z, p.z, f.w))), 0.f);
+                        const float t = fmaf(f.x, p.x, fmaf(f.y, p.y, fmaf(f.z, p.z, f.w)));
+                        o[j][q] = PREC == PREC_F16 ? t : fmaxf(t, 0.f);   // fp16: ReLU inside the conversions
                     }
                 }
             }
@@ -1025,10 +1044,10 @@ mlp_layer_tt_kernel(const __grid_constant__ TtArgs a) {
                     hi = make_uint4(__float_as_uint(h[0]), __float_as_uint(h[1]), __float_as_uint(h[2]), __float_as_uint(h[3]));
                     lo = make_uint4(__float_as_uint(l[0]), __float_as_uint(l[1]), __float_as_uint(l[2]), __float_as_uint(l[3]));
                 } else {
-                    split_f16x2(o[j][0], o[j][1], hi.x, lo.x);
-                    split_f16x2(o[j][2], o[j][3], hi.y, lo.y);
-                    split_f16x2(o[j][4 % P::kEPU], o[j][5 % P::kEPU], hi.z, lo.z);
-                    split_f16x2(o[j][6 % P::kEPU], o[j][7 % P::kEPU], hi.w, lo.w);
+                    split_relu_f16x2(o[j][0], o[j][1], hi.x, lo.x);
+                    split_relu_f16x2(o[j][2], o[j][3], hi.y, lo.y);
+                    split_relu_f16x2(o[j][4 % P::kEPU], o[j][5 % P::kEPU], hi.z, lo.z);
+                    split_relu_f16x2(o[j][6 % P::kEPU], o[j][7 % P::kEPU], hi.w, lo.w);
                 }
                 const uint32_t off = (uint32_t)(rb + kRowStride * j) * 128u + swz;
                 sts128(stage + off, hi);
