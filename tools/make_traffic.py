@@ -20,7 +20,9 @@ LABELS = [("sample_group", "sample_group", 32768, 512, 32), ("point_moments", "p
           ("pool_finish", "pool_finish", 4096, 0, 256),
           ("prep_wimg", None, 0, 0, 0),
           ("mlp_layer_tt_kernel<1, 0, 1, 0>", "mlp_tt<gather,tf32x3,Wstream>", 4096, 256, 256),
+          ("prep_ximg", None, 0, 0, 0),
           ("mlp_layer_tt_kernel<0, 1, 0, 0>", "mlp_tt<plain,f16x3,Wtmem>", 4096, 256, 512),
+          ("prep_ximg", None, 0, 0, 0),
           ("prep_wimg", None, 0, 0, 0),
           ("mlp_layer_tt_kernel<0, 1, 1, 1>", "mlp_tt<plain,f16x3,Wstream,pool>", 4096, 512, 1024),
           ("pool_finish", "pool_finish", 32, 0, 1024)]
