@@ -332,11 +332,19 @@ prep_ximg_kernel(const float *__restrict__ x, long long M, int cin, const float 
 
 // --------------------------------------------------------------------------------- main kernel
 // WMODE 0: W resident in tensor memory (TS UMMA).  WMODE 1: W chunks streamed through the ring.
-template <int MODE, int PREC, int WMODE, bool POOL>
+// PAIR: one CTA owns TWO 128-channel tiles (cout up to 256 per CTA) of every row tile it visits: the activation
+// chunk is converted ONCE and multiplied by both weight tiles (two passes of the MMA issuer over the same operand
+// stages, accumulator h = channel tile h), instead of two CTAs converting the same rows.  Needs W of both tiles
+// in tensor memory: 2 x (64 + 64) columns, i.e. cin <= kTmemK / 2 (SRC_PLAIN, W resident).
+template <int MODE, int PREC, int WMODE, bool POOL, bool PAIR = false>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_layer_tt_kernel(const __grid_constant__ TtArgs a) {
     using P = Prec<PREC>;
     using CF = Cfg<MODE, PREC, WMODE>;
+    static_assert(!PAIR || (MODE == SRC_PLAIN && WMODE == 0), "paired channel tiles: plain source, resident W");
+    constexpr int kChT = PAIR ? 2 : 1;                        // channel tiles per CTA
+    // tensor-memory columns of channel tile h: W hi / lo (PAIR: 64 columns each)
+    constexpr uint32_t kWHi0 = kColWHi, kWLo0 = PAIR ? kColWHi + 64 : kColWLo, kWStep = PAIR ? 128 : 0;
     constexpr int kStages = CF::kStages;
     constexpr int kStageBytes = CF::kStageBytes;
     constexpr int NV = CF::kNV;
@@ -369,11 +377,11 @@ mlp_layer_tt_kernel(const __grid_constant__ TtArgs a) {
         atomicMin(a.clk + 44, gt0);
     }
 #endif
-    const int nt = ceil_div(a.cout, kTile);
+    const int nt = ceil_div(a.cout, kTile * kChT);
     const int tile_n = blockIdx.x % nt;
     const int mi = blockIdx.x / nt;
     const int gm = gridDim.x / nt;
-    const int n0 = tile_n * kTile;
+    const int n0 = tile_n * kTile * kChT;
     const long long tiles_m = ceil_div<long long>(a.M, kTile);
     const int KC = ceil_div(a.cin, P::kEPC);
     const int kpad = ceil_div(a.cin, P::kMmaK) * P::kMmaK;
@@ -414,9 +422,8 @@ mlp_layer_tt_kernel(const __grid_constant__ TtArgs a) {
         // ================================ epilogue =========================================
         const int quad = warp & 3;        // TMEM lane quadrant this warp may access (warp id % 4)
         const int half = warp >> 2;       // which accumulator column blocks (rows of the tile) it owns
-        const int c = quad * 32 + lane;   // channel inside this CTA's 128-channel tile == TMEM lane
-        const int cg = n0 + c;
-        const bool cvalid = cg < a.cout;
+        const int c = quad * 32 + lane;   // channel inside a 128-channel tile == TMEM lane
+        const int cg_base = n0 + c;       // channel tile h of this CTA: cg_base + h * kTile
         const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
         // ---- stage W into tensor memory (hi / lo split).  Thread = channel reads ITS OWN row
         //      W[cg, kc*kEPC ...] straight into the registers tcgen05.st takes (16-byte loads when the
@@ -440,9 +447,12 @@ mlp_layer_tt_kernel(const __grid_constant__ TtArgs a) {
                 }
                 named_bar_sync(10, kEpiWarps * 32);
             }
-            const float *wrow = a.W + (size_t)(cvalid ? cg : 0) * a.wld + a.wk0;
             const bool vec = ((a.wld | a.wk0) & 3) == 0 && (reinterpret_cast<uintptr_t>(a.W) & 15u) == 0 &&
                              (a.w_colscale == nullptr || (reinterpret_cast<uintptr_t>(a.w_colscale) & 15u) == 0);
+            for (int h = 0; h < kChT; ++h) {
+            const int cg = cg_base + h * kTile;
+            const bool cvalid = cg < a.cout;
+            const float *wrow = a.W + (size_t)(cvalid ? cg : 0) * a.wld + a.wk0;
             for (int kc = half; kc < KC; kc += kEpiHalves) {  // one 32-column TMEM chunk = kEPC elements
                 uint32_t hi[32], lo[32];
 #pragma unroll
@@ -487,8 +497,9 @@ mlp_layer_tt_kernel(const __grid_constant__ TtArgs a) {
                             split_f16x2(v[i], v[i + 1], hi[(pass * 16 + i / 2) & 31], lo[(pass * 16 + i / 2) & 31]);
                     }
                 }
-                tmem_st32(lane_base + kColWHi + kc * 32, hi);
-                tmem_st32(lane_base + kColWLo + kc * 32, lo);
+                tmem_st32(lane_base + kWHi0 + h * kWStep + kc * 32, hi);
+                tmem_st32(lane_base + kWLo0 + h * kWStep + kc * 32, lo);
+            }
             }
             tmem_wait_st();
             tc_fence_before();
@@ -499,29 +510,42 @@ mlp_layer_tt_kernel(const __grid_constant__ TtArgs a) {
         if (tid == 0) TT_GCLK(a, 2);   // W staged
         pdl_wait();
         if (tid == 0) TT_GCLK(a, 3);   // the previous kernel has completed
-        const float bias = (a.bias != nullptr && cvalid) ? a.bias[cg] : 0.f;
+        float bias_h[kChT];
+        double acc_s_h[kChT], acc_q_h[kChT];
+#pragma unroll
+        for (int h = 0; h < kChT; ++h) {
+            const int cgh = cg_base + h * kTile;
+            bias_h[h] = (a.bias != nullptr && cgh < a.cout) ? a.bias[cgh] : 0.f;
+            acc_s_h[h] = 0.0;
+            acc_q_h[h] = 0.0;
+        }
         float wx = 0.f, wy = 0.f, wz = 0.f;
         const bool has_xyz = (MODE == SRC_GATHER) && a.wxyz >= 0;
-        if (has_xyz && cvalid) {
-            const float *wp = a.W + (size_t)cg * a.wld + a.wxyz;
+        if (has_xyz && cg_base < a.cout) {
+            const float *wp = a.W + (size_t)cg_base * a.wld + a.wxyz;
             wx = wp[0]; wy = wp[1]; wz = wp[2];
         }
-        const bool do_y = (!POOL || a.y != nullptr) && cvalid;
-        const bool do_pool = POOL && cvalid;
-        const uint64_t bias2 = pack2(bias, bias);
         const uint64_t wx2 = pack2(wx, wx), wy2 = pack2(wy, wy), wz2 = pack2(wz, wz);
         const int kshift = POOL ? (a.K == 32 ? 5 : a.K == 64 ? 6 : 7) : 0;  // K in {32, 64, 128}
         const size_t ystride = (size_t)a.cout;
         float2 *s_xpool = reinterpret_cast<float2 *>(smem + SmemLayout::xpool);
-        double acc_s = 0.0, acc_q = 0.0;
-        uint32_t tl = 0;
-        for (long long tile = mi; tile < tiles_m; tile += gm, ++tl) {
-            const uint32_t buf = tl & 1;
+        // one accumulator of one row tile: channel tile H (PAIR: accumulator H, filled once per row tile;
+        // otherwise the two accumulators alternate between row tiles)
+        auto tile_body = [&](auto hc, long long tile, uint32_t tl) {
+            constexpr int H = decltype(hc)::value;
+            const int cg = cg_base + H * kTile;
+            const bool cvalid = cg < a.cout;
+            const bool do_y = (!POOL || a.y != nullptr) && cvalid;
+            const bool do_pool = POOL && cvalid;
+            const uint64_t bias2 = pack2(bias_h[H], bias_h[H]);
+            double &acc_s = acc_s_h[H], &acc_q = acc_q_h[H];
+            const uint32_t buf = PAIR ? (uint32_t)H : (tl & 1);
+            const uint32_t par = PAIR ? (tl & 1) : ((tl >> 1) & 1);
             const long long m0 = tile * kTile;
             const int nrows = (int)((a.M - m0) < kTile ? (a.M - m0) : kTile);
             TT_ECLK(a, tl, 0);   // loop top
             if (MODE == SRC_GATHER) mbar_wait(xyz_full + (tl & 3), (tl >> 2) & 1);
-            mbar_wait(acc_full + buf, (tl >> 1) & 1);
+            mbar_wait(acc_full + buf, par);
             TT_ECLK(a, tl, 1);   // accumulator barrier passed
             tc_fence_after();
             TT_ECLK(a, tl, 2);   // tcgen05 fence done
@@ -653,10 +677,21 @@ mlp_layer_tt_kernel(const __grid_constant__ TtArgs a) {
             acc_s += (double)(sa + sb);
             acc_q += (double)(qa + qb);
             TT_ECLK(a, tl, 7);   // tile bookkeeping done
+        };
+        uint32_t tl = 0;
+        for (long long tile = mi; tile < tiles_m; tile += gm, ++tl) {
+            tile_body(std::integral_constant<int, 0>{}, tile, tl);
+            if (PAIR) tile_body(std::integral_constant<int, kChT - 1>{}, tile, tl);
         }
         if (tid == 0) TT_CLK(a, 6);
+#pragma unroll
+        for (int h = 0; h < kChT; ++h) {
+        const int cg = cg_base + h * kTile;
+        const bool cvalid = cg < a.cout;
+        double acc_s = acc_s_h[h], acc_q = acc_q_h[h];
         if (kEpiHalves == 2) {  // fold the two halves' statistics (fixed order -> deterministic)
             double2 *s_xstat = reinterpret_cast<double2 *>(smem + SmemLayout::xstat);
+            if (h > 0) named_bar_sync(6 + quad, 64);   // the lower half has read the previous tile's slot
             if (half == 1) s_xstat[c] = make_double2(acc_s, acc_q);
             named_bar_sync(6 + quad, 64);
             if (half == 0) {
@@ -692,6 +727,7 @@ mlp_layer_tt_kernel(const __grid_constant__ TtArgs a) {
             }
             __threadfence();
         }
+        }
     } else if (warp == kMmaWarp) {
         // ================================ MMA issuer =======================================
         // The whole warp runs the (uniform) control flow; one elected lane issues the tcgen05 ops.
@@ -704,14 +740,20 @@ mlp_layer_tt_kernel(const __grid_constant__ TtArgs a) {
         const uint32_t ring_base = smem_u32(smem + SmemLayout::ring);
         uint32_t it = 0, tl = 0;
         for (long long tile = mi; tile < tiles_m; tile += gm, ++tl) {
-            const uint32_t buf = tl & 1;
-            mbar_wait(acc_empty + buf, ((tl >> 1) & 1) ^ 1);
+          // PAIR: two passes over the row tile's operand stages, pass h -> accumulator h with the weights of
+          // channel tile h; the stages are awaited in pass 0 and handed back to the producers in pass 1
+          const uint32_t it0 = it;
+#pragma unroll
+          for (int h = 0; h < kChT; ++h) {
+            const uint32_t buf = PAIR ? (uint32_t)h : (tl & 1);
+            mbar_wait(acc_empty + buf, (PAIR ? (tl & 1) : ((tl >> 1) & 1)) ^ 1);
             tc_fence_after();
             if (lane == 0) TT_TCLK(a, tl, 2);   // MMA: accumulator buffer free
             const uint32_t d_tmem = tmem_base + kColAcc + buf * kTile;
+            it = it0;
             for (int c = 0; c < KC; ++c, ++it) {
                 const uint32_t s = it % kStages;
-                mbar_wait(x_full + s, (it / kStages) & 1);
+                if (h == 0) mbar_wait(x_full + s, (it / kStages) & 1);
                 tc_fence_after();
                 const int nks = TT_DBG(a, 2) ? 0 : min(P::kEPC, kpad - c * P::kEPC) / P::kMmaK;  // 1..4 K steps
                 const uint32_t x_hi = ring_base + s * kStageBytes;
@@ -719,7 +761,7 @@ mlp_layer_tt_kernel(const __grid_constant__ TtArgs a) {
                 // (address >> 4) field, = 8 tensor-memory columns
                 const uint64_t dxh = make_desc_sw128(x_hi), dxl = make_desc_sw128(x_hi + kHalfBytes);
                 const uint64_t dwh = make_desc_sw128(x_hi + kXBytes), dwl = make_desc_sw128(x_hi + kXBytes + kHalfBytes);
-                const uint32_t w_hi = tmem_base + kColWHi + c * 32, w_lo = tmem_base + kColWLo + c * 32;
+                const uint32_t w_hi = tmem_base + kWHi0 + h * kWStep + c * 32, w_lo = tmem_base + kWLo0 + h * kWStep + c * 32;
                 if (elect_one()) {
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
@@ -749,7 +791,7 @@ mlp_layer_tt_kernel(const __grid_constant__ TtArgs a) {
                             }
                         }
                     }
-                    mma_commit(x_empty + s);                       // chunk reusable once these MMAs have read it
+                    if (h == kChT - 1) mma_commit(x_empty + s);    // chunk reusable once these MMAs have read it
                     if (c == KC - 1) mma_commit(acc_full + buf);   // accumulator complete
                     if (it == 0) TT_CLK(a, 4);
                     if (it == 0) TT_GCLK(a, 11);           // first MMAs issued
@@ -758,9 +800,10 @@ mlp_layer_tt_kernel(const __grid_constant__ TtArgs a) {
                 __syncwarp();
             }
             if (TT_DBG(a, 64)) {  // triage: the issuer itself waits for the tile's MMAs to complete
-                mbar_wait(acc_full + buf, (tl >> 1) & 1);
+                mbar_wait(acc_full + buf, PAIR ? (tl & 1) : ((tl >> 1) & 1));
                 if (lane == 0) TT_TCLK(a, tl, 7);
             }
+          }
         }
     } else {
         // ================================ producers ========================================
@@ -1550,9 +1593,9 @@ size_t wimg_bytes(int prec, int cin, int cout) {
     return (size_t)ceil_div(cout, kTile) * ceil_div(cin, epc(prec)) * kXBytes;
 }
 
-template <int MODE, int PREC, int WMODE, bool POOL>
+template <int MODE, int PREC, int WMODE, bool POOL, bool PAIR = false>
 static int launch_inst(const TtArgs &a, int grid, cudaStream_t st) {
-    auto k = mlp_layer_tt_kernel<MODE, PREC, WMODE, POOL>;
+    auto k = mlp_layer_tt_kernel<MODE, PREC, WMODE, POOL, PAIR>;
     static bool configured = false;
     if (!configured) {
         PAPC_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1560,8 +1603,8 @@ static int launch_inst(const TtArgs &a, int grid, cudaStream_t st) {
         configured = true;
     }
     char name[56];
-    snprintf(name, sizeof(name), "mlp_tt<%s,%s,%s%s>", MODE == SRC_PLAIN ? "plain" : MODE == SRC_GATHER ? "gather" : "pointmlp",
-             PREC == PREC_F16 ? "f16x3" : "tf32x3", WMODE ? "Wstream" : "Wtmem", POOL ? ",pool" : "");
+    snprintf(name, sizeof(name), "mlp_tt<%s,%s,%s%s%s>", MODE == SRC_PLAIN ? "plain" : MODE == SRC_GATHER ? "gather" : "pointmlp",
+             PREC == PREC_F16 ? "f16x3" : "tf32x3", WMODE ? "Wstream" : "Wtmem", POOL ? ",pool" : "", PAIR ? ",pair" : "");
     // algorithmic bytes: the activation rows read (gathered rows count once per row read), the
     // pre-BN output written (if any) and the pooled extrema
     const double in_b = MODE == SRC_POINTMLP ? 16.0 * a.M : 4.0 * (double)a.M * a.cin;
@@ -1679,7 +1722,7 @@ int launch(const TtArgs &a_in, cudaStream_t st) {
     make_fastdiv((uint32_t)(a.S >= 1 ? a.S : 1), &a.smul, &a.sshr);
     a.inv_count = a.count > 0.0 ? 1.0 / a.count : 0.0;
     const bool streamed = a.cin > tmem_k(a.prec);
-    const int nt = ceil_div(a.cout, kTile);
+    int nt = ceil_div(a.cout, kTile);
     {
         const char *e = getenv("PAPC_TT_PDL");  // A/B switch: PAPC_TT_PDL=0 disables dependent launch
         // a streamed-W / activation-image launch has its image kernel(s) as stream predecessor: still a dependent
@@ -1721,6 +1764,15 @@ int launch(const TtArgs &a_in, cudaStream_t st) {
         PAPC_LAUNCH_CHECK();
     }
     const long long tiles_m = ceil_div<long long>(a.M, kTile);
+    // paired channel tiles (one CTA converts a row tile once for 256 output channels): plain fp16-split layers
+    // whose W pair fits in tensor memory, when the row tiles alone fill the GPU
+    bool pair = false;
+    {
+        static const bool pair_off = [] { const char *e = getenv("PAPC_TT_PAIR"); return e && e[0] == '0'; }();  // A/B switch
+        pair = !pair_off && a.mode == SRC_PLAIN && a.prec == PREC_F16 && !streamed && !a.ximg_on && nt >= 2 &&
+               a.cin <= tmem_k(PREC_F16) / 2 && tiles_m * ((nt + 1) / 2) >= kNumSMs;
+        if (pair) nt = (nt + 1) / 2;
+    }
     long long gm = kNumSMs / nt;
     if (gm < 1) gm = 1;
     if (gm > tiles_m) gm = tiles_m;
@@ -1756,8 +1808,12 @@ int launch(const TtArgs &a_in, cudaStream_t st) {
     int rc = PAPC_EINVAL;
     switch (a.mode) {
         case SRC_PLAIN:
-            rc = a.prec == PREC_F16 ? launch_mp<SRC_PLAIN, PREC_F16>(a, streamed, pool, grid, st)
-                                    : launch_mp<SRC_PLAIN, PREC_TF32>(a, streamed, pool, grid, st);
+            if (pair)
+                rc = pool ? launch_inst<SRC_PLAIN, PREC_F16, 0, true, true>(a, grid, st)
+                          : launch_inst<SRC_PLAIN, PREC_F16, 0, false, true>(a, grid, st);
+            else
+                rc = a.prec == PREC_F16 ? launch_mp<SRC_PLAIN, PREC_F16>(a, streamed, pool, grid, st)
+                                        : launch_mp<SRC_PLAIN, PREC_TF32>(a, streamed, pool, grid, st);
             break;
         case SRC_GATHER:
             rc = a.prec == PREC_F16 ? launch_mp<SRC_GATHER, PREC_F16>(a, streamed, pool, grid, st)
