@@ -510,10 +510,15 @@ pool_finish_bsc_kernel(const float *__restrict__ pmax, const float *__restrict__
 
 // the same, four channels per thread (C % 4 == 0, 16-byte aligned buffers): 16-byte loads and stores, a quarter of
 // the instructions -- the scalar form ran at 1.6 TB/s on the 8 MB sa1 output
+// Programmatic dependent launch on both sides: the next kernel of the stream (the first layer kernel of the next
+// SetAbstraction module) may run its prologue while this one works, and this kernel itself is resident before the
+// last layer kernel has finished -- everything it reads is written by that kernel, hence the wait comes first.
 __global__ void __launch_bounds__(256)
 pool_finish_bsc_v4_kernel(const float4 *__restrict__ pmax, const float4 *__restrict__ pmin,
                           const float4 *__restrict__ scale, const float4 *__restrict__ shift, size_t total4,
                           int C4, float4 *__restrict__ out) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (; e < total4; e += stride) {
@@ -561,6 +566,39 @@ pool_finish_bcs_kernel(const float *__restrict__ pmax, const float *__restrict__
 }
 
 static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// The "last CTA" counters and the integer statistic words of one papc_sa_mlp_f32 call start at zero.  A kernel
+// instead of a memset node: it is a programmatic dependent of whatever kernel precedes it on the stream and lets
+// its own dependent (the call's first layer kernel) start its prologue at once, so the chain pool_finish ->
+// zero -> first layer of the next module stays resident instead of paying three launch latencies in a row.
+__global__ void __launch_bounds__(256)
+zero_words_kernel(unsigned int *__restrict__ p, size_t nwords) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // the workspace may have been the previous call's
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (size_t)gridDim.x * blockDim.x)
+        p[i] = 0u;
+}
+
+// Launch with the programmatic-stream-serialization attribute (the kernel must call griddepcontrol.wait before
+// touching anything an earlier kernel of the stream writes).
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+static bool pdl_chain_enabled() {
+    static const bool on = [] { const char *e = getenv("PAPC_TT_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
 
 // Row-tile CTAs per launch: persistent beyond 2 resident CTAs per SM.
 static long long grid_rows(long long M) {
@@ -638,6 +676,19 @@ struct FusedBn {
     float *out_colscale;  // non-null: the NEXT layer runs the fp16 split (see tt::TtArgs)
     // zeroed, self-cleaning [4][cout] 64-bit accumulators + flag (tt::TtArgs::fix_acc); nullable
     unsigned long long *fix_acc = nullptr;
+    // deferred finalisation (tt::TtArgs::in_fix): the kernel only adds its sums into fix_acc, the NEXT layer kernel
+    // derives scale / shift (and writes mean_out / var_out); nothing is written to scale / shift
+    bool defer = false;
+};
+// Consumer side of a deferred finalisation: what the next layer kernel needs to derive its input's scale / shift.
+struct DeferredBn {
+    const unsigned long long *fix = nullptr;
+    const double *partial = nullptr;
+    long long partial_rows = 0;
+    const float *gamma = nullptr, *beta = nullptr;
+    float eps = 0.f;
+    double count = 0.0;
+    float *mean_out = nullptr, *var_out = nullptr;
 };
 
 // Per-launch options of the transposed tcgen05 kernel.
@@ -656,6 +707,7 @@ struct TtOpts {
     void *ximg = nullptr;     // workspace for the activation image of small-M fp16 layers (tt::ximg_bytes), nullable
     size_t ximg_bytes = 0;
     const float *gather_colscale = nullptr;   // SRC_GATHER + PREC_F16: papc_group_source.feats_colscale
+    const DeferredBn *in_bn = nullptr;        // SRC_PLAIN: the input's BatchNorm is finalised by this launch
 };
 
 // Tries the transposed tcgen05 kernel.  Returns 1 if launched (or, dry_run, launchable), 0 if the
@@ -698,9 +750,18 @@ static int try_tt(const LayerArgs &a, bool gather, int K, const FusedBn *bn, con
         t.mode = tt::SRC_PLAIN;
         t.cin = a.cin;
         t.x = a.x; t.in_scale = a.in_scale; t.in_shift = a.in_shift;
+        if (o.in_bn != nullptr && o.in_bn->fix != nullptr) {
+            const DeferredBn &d = *o.in_bn;
+            t.in_scale = nullptr; t.in_shift = nullptr;
+            t.in_fix = d.fix; t.in_partial = d.partial; t.in_partial_rows = d.partial_rows;
+            t.in_gamma = d.gamma; t.in_beta = d.beta; t.in_eps = d.eps;
+            t.in_inv_count = d.count > 0.0 ? 1.0 / d.count : 0.0;
+            t.in_cs = o.prec == tt::PREC_F16 ? 1 : 0;
+            t.in_mean_out = d.mean_out; t.in_var_out = d.var_out;
+        }
     }
     tt::TtProblem prob{t.mode, t.prec, t.cin, t.cout, K, t.D, a.pool_max != nullptr};
-    prob.no_act = t.mode == tt::SRC_PLAIN && t.in_scale == nullptr && t.prec == tt::PREC_TF32;
+    prob.no_act = t.mode == tt::SRC_PLAIN && t.in_scale == nullptr && t.in_fix == nullptr && t.prec == tt::PREC_TF32;
     if (!tt::eligible(prob)) return 0;
     if (!a.pool_max && !a.y) return 0;
     const size_t wneed = tt::wimg_bytes(t.prec, t.cin, t.cout);
@@ -712,7 +773,7 @@ static int try_tt(const LayerArgs &a, bool gather, int K, const FusedBn *bn, con
     }
     if (o.dry_run) return 1;
     if (bn != nullptr && a.stats_partial != nullptr) {
-        t.counter = bn->counter;
+        t.counter = bn->defer ? nullptr : bn->counter;
         t.fix_acc = bn->fix_acc;
         t.gamma = bn->gamma; t.beta = bn->beta; t.eps = bn->eps;
         t.count = bn->count; t.sqrt_count = bn->sqrt_count; t.scale = bn->scale; t.shift = bn->shift;
@@ -898,10 +959,16 @@ extern "C" int papc_sa_pool_finish_f32(const float *pool_max, const float *pool_
         if (cout % 4 == 0 && al16(pool_max) && al16(pool_min) && al16(scale) && al16(shift) && al16(out)) {
             size_t blocks = (total / 4 + 255) / 256;
             if (blocks > (size_t)kNumSMs * 8) blocks = (size_t)kNumSMs * 8;
-            pool_finish_bsc_v4_kernel<<<(unsigned)blocks, 256, 0, st>>>(
-                reinterpret_cast<const float4 *>(pool_max), reinterpret_cast<const float4 *>(pool_min),
-                reinterpret_cast<const float4 *>(scale), reinterpret_cast<const float4 *>(shift), total / 4, cout / 4,
-                reinterpret_cast<float4 *>(out));
+            if (pdl_chain_enabled())
+                PAPC_CUDA_TRY(launch_pdl(pool_finish_bsc_v4_kernel, dim3((unsigned)blocks), dim3(256), st,
+                                         reinterpret_cast<const float4 *>(pool_max), reinterpret_cast<const float4 *>(pool_min),
+                                         reinterpret_cast<const float4 *>(scale), reinterpret_cast<const float4 *>(shift),
+                                         total / 4, cout / 4, reinterpret_cast<float4 *>(out)));
+            else
+                pool_finish_bsc_v4_kernel<<<(unsigned)blocks, 256, 0, st>>>(
+                    reinterpret_cast<const float4 *>(pool_max), reinterpret_cast<const float4 *>(pool_min),
+                    reinterpret_cast<const float4 *>(scale), reinterpret_cast<const float4 *>(shift), total / 4, cout / 4,
+                    reinterpret_cast<float4 *>(out));
         } else {
             size_t blocks = (total + 255) / 256;
             if (blocks > (size_t)kNumSMs * 16) blocks = (size_t)kNumSMs * 16;
@@ -925,6 +992,7 @@ struct WsPlan {
     size_t counters, fold, mom_partial, colscale, colscale_stride, total;
     size_t ximg, ximg_bytes;   // activation image of the small-M fp16 layers (tt::ximg_bytes), 0 = none
     size_t counters_bytes;  // 256 bytes of counters + the fixed-point statistic accumulators (see FusedBn)
+    size_t fix_stride, partial_stride;
     // chained path (sa_chain.cu): 0 = off, 1 = points only (folded first layer), 2 = gathered source image
     int chain;
     size_t ch_scale[3], ch_shift[3], ch_colscale[3];  // per-layer BatchNorm scale / shift / fp16 column scale
@@ -993,7 +1061,8 @@ static int plan_ws(const papc_group_source *src, const papc_mlp *mlp, WsPlan *p)
     p->y[1] = take(ybytes[1]);
     p->pool_max = take((size_t)G * clast * sizeof(float));
     p->pool_min = take((size_t)G * clast * sizeof(float));
-    p->partial = take((size_t)grid_rows(M) * 2 * maxc * sizeof(double));
+    p->partial_stride = align_up((size_t)grid_rows(M) * 2 * maxc * sizeof(double), 256);
+    p->partial = take(2 * p->partial_stride);   // layers alternate (a deferred finalisation reads the previous layer's)
     p->sums = take((size_t)2 * maxc * sizeof(double));
     p->scale = take((size_t)maxc * sizeof(float));
     p->shift = take((size_t)maxc * sizeof(float));
@@ -1017,7 +1086,8 @@ static int plan_ws(const papc_group_source *src, const papc_mlp *mlp, WsPlan *p)
     }
     p->ximg_bytes = xb;
     p->ximg = take(xb);
-    p->counters_bytes = 256 + ((size_t)4 * maxc + 8) * sizeof(unsigned long long);
+    p->fix_stride = ((size_t)4 * maxc + 8) * sizeof(unsigned long long);   // one slot of statistic words per layer
+    p->counters_bytes = 256 + (size_t)mlp->num_layers * p->fix_stride;
     p->counters = take(p->counters_bytes);
     p->fold = take((size_t)128 * 4 * sizeof(float));
     p->mom_partial = take((size_t)2 * kNumSMs * 9 * sizeof(double));
@@ -1238,7 +1308,7 @@ extern "C" int papc_sa_mlp_f32(const papc_group_source *src, const papc_mlp *mlp
     float *ybuf[2] = {reinterpret_cast<float *>(ws + p.y[0]), reinterpret_cast<float *>(ws + p.y[1])};
     float *pmax = reinterpret_cast<float *>(ws + p.pool_max);
     float *pmin = reinterpret_cast<float *>(ws + p.pool_min);
-    double *partial = reinterpret_cast<double *>(ws + p.partial);
+    double *partial0 = reinterpret_cast<double *>(ws + p.partial);
     float *scale = reinterpret_cast<float *>(ws + p.scale);
     float *shift = reinterpret_cast<float *>(ws + p.shift);
     unsigned int *counters = reinterpret_cast<unsigned int *>(ws + p.counters);
@@ -1251,7 +1321,15 @@ extern "C" int papc_sa_mlp_f32(const papc_group_source *src, const papc_mlp *mlp
         if (!batch && (!ly.running_mean || !ly.running_var)) return PAPC_EINVAL;
     }
     // the in-kernel "last CTA" counters start at zero (they clean themselves afterwards)
-    PAPC_CUDA_TRY(cudaMemsetAsync(counters, 0, p.counters_bytes, st));
+    const bool zero_by_kernel = pdl_chain_enabled() && p.chain == 0 && p.counters_bytes % 4 == 0;
+    if (zero_by_kernel) {
+        const size_t nw = p.counters_bytes / 4;
+        PAPC_CUDA_TRY(launch_pdl(zero_words_kernel, dim3((unsigned)((nw + 255) / 256 < 64 ? (nw + 255) / 256 : 64)),
+                                 dim3(256), st, counters, nw));
+        ++g_launch_count;
+    } else {
+        PAPC_CUDA_TRY(cudaMemsetAsync(counters, 0, p.counters_bytes, st));
+    }
     if (p.chain != 0) return run_chain(src, mlp, p, ws, out, out_layout, stream);
 
     int cin = mlp->cin;
@@ -1272,7 +1350,7 @@ extern "C" int papc_sa_mlp_f32(const papc_group_source *src, const papc_mlp *mlp
         const bool last = l == L - 1;
         a.y = last ? nullptr : ybuf[l & 1];
         a.pool_max = last ? pmax : nullptr; a.pool_min = last ? pmin : nullptr;
-        a.stats_partial = partial;
+        a.stats_partial = partial0;
         if (last && M % src->K != 0) return false;
         const TtOpts o{tt::PREC_F16, nullptr, nullptr, 0.f, nullptr, ws + p.wimg, p.wimg_bytes, true, false};
         return try_tt(a, false, src->K, nullptr, o, st) == 1;
@@ -1280,7 +1358,13 @@ extern "C" int papc_sa_mlp_f32(const papc_group_source *src, const papc_mlp *mlp
     bool this_f16 = false;  // precision of the layer about to run
     // (float)sqrt(M) rounded up: the one value every f16_colscale_sq() user of this call receives
     const float sqrt_m = nextafterf((float)sqrt((double)M), INFINITY);
-    bool prev_is_kernel = false;  // the last stream operation of this call is a kernel of ours (PDL)
+    bool prev_is_kernel = zero_by_kernel;  // the last stream operation of this call is a kernel of ours (PDL)
+    // Deferred finalisation (tt::TtArgs::in_fix): a hidden layer whose consumer is a plain fp16-split tcgen05 launch
+    // without an activation image leaves its BatchNorm to that launch.  PAPC_TT_DEFER=0: A/B switch.
+    static const bool defer_on = [] { const char *e = getenv("PAPC_TT_DEFER"); return !(e && e[0] == '0'); }();
+    DeferredBn in_bn;           // filled when the PREVIOUS layer deferred
+    bool prev_deferred = false;
+    auto partial_of = [&](int l) { return reinterpret_cast<double *>(ws + p.partial + (size_t)(l & 1) * p.partial_stride); };
     if (pointmlp_ok(src, mlp)) {
         // Layer 0 (3 -> c0) is never materialised: its BatchNorm statistics follow analytically
         // from the moments of the centred points, and layer 1's producer recomputes it per row.
@@ -1312,13 +1396,16 @@ extern "C" int papc_sa_mlp_f32(const papc_group_source *src, const papc_mlp *mlp
         const bool last = (l == L - 1);
         float *y = last ? nullptr : ybuf[l & 1];
         const bool next_f16 = f16_ok(l + 1, ly.cout);
+        double *partial = partial_of(l);
         FusedBn bn{counters + l, ly.gamma, ly.beta, mlp->eps, (double)M, sqrt_m,
                    scale, shift, ly.batch_mean, ly.batch_var, next_f16 ? colscale[l & 1] : nullptr};
-        bn.fix_acc = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(counters) + 256);
+        bn.fix_acc = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(counters) + 256 + (size_t)l * p.fix_stride);
+        bn.defer = defer_on && batch && !last && next_f16 && tt::ximg_bytes(M, ly.cout, mlp->layers[l + 1].cout) == 0;
         TtOpts o{this_f16 ? tt::PREC_F16 : tt::PREC_TF32,
                  this_f16 ? mlp->layers[l - 1].gamma : nullptr, this_f16 ? mlp->layers[l - 1].beta : nullptr,
                  sqrt_m, nullptr, ws + p.wimg, p.wimg_bytes, false, prev_is_kernel};
         if (p.ximg_bytes > 0) { o.ximg = ws + p.ximg; o.ximg_bytes = p.ximg_bytes; }
+        if (prev_deferred) o.in_bn = &in_bn;
         if (l == 0 && !src->grouped && src->feats != nullptr && src->feats_colscale != nullptr && src->D % 8 == 0) {
             // gathered layer 0 on features the caller bounds (post-ReLU outputs of the previous SetAbstraction
             // layer): fp16 split instead of 3xTF32 -- half the tensor-core products, 64 instead of 32 reduction
@@ -1374,6 +1461,12 @@ extern "C" int papc_sa_mlp_f32(const papc_group_source *src, const papc_mlp *mlp
             rc = papc_bn_running_scale_shift_f32(ly.running_mean, ly.running_var, ly.gamma, ly.beta,
                                                  mlp->eps, ly.cout, scale, shift, stream);
             if (rc != PAPC_OK) return rc;
+        }
+        prev_deferred = batch && fused_done && bn.defer;
+        if (prev_deferred) {
+            in_bn.fix = bn.fix_acc; in_bn.partial = partial; in_bn.partial_rows = papc_mlp_stats_partial_rows(M);
+            in_bn.gamma = ly.gamma; in_bn.beta = ly.beta; in_bn.eps = mlp->eps; in_bn.count = (double)M;
+            in_bn.mean_out = ly.batch_mean; in_bn.var_out = ly.batch_var;
         }
         xprev = y;
         cin = ly.cout;

@@ -166,6 +166,28 @@ __device__ __forceinline__ void split_relu_f16x2(float a, float b, uint32_t &hi,
     asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
 }
 
+// BatchNorm scale / shift of one channel from its batch sums -- the one place this arithmetic lives (last-CTA
+// finalisation and the consumer-side derivation must agree bit for bit).  fp64 division and square root are long
+// software sequences on a slow pipe: reciprocal of the count from the host, 1/sqrt by two Newton steps from the
+// fp32 estimate (full double accuracy).  cs: power-of-two column scale the results are divided by (1 = none).
+__device__ __forceinline__ void bn_from_sums(double sum, double sumsq, double inv_count, float gamma, float beta,
+                                             float eps, float cs, float &scale, float &shift, float &mean_f,
+                                             float &var_f) {
+    const double mean = sum * inv_count;
+    double var = sumsq * inv_count - mean * mean;  // biased, as Paddle's training BN
+    var = var > 0.0 ? var : 0.0;
+    const double g = (double)gamma, b = (double)beta;
+    const double ve = var + (double)eps;
+    double rs = (double)rsqrtf((float)ve);
+    rs = rs * (1.5 - 0.5 * ve * rs * rs);
+    rs = rs * (1.5 - 0.5 * ve * rs * rs);
+    const double sc = g * rs;
+    scale = (float)sc / cs;
+    shift = (float)(b - mean * sc) / cs;
+    mean_f = (float)mean;
+    var_f = (float)var;
+}
+
 // Shared memory: the small fixed tables first, then the operand ring (read by the tensor core) and
 // the raw ring (fp32 activations landed by cp.async, thread-private slots), sized per instantiation.
 struct SmemLayout {
@@ -709,8 +731,9 @@ mlp_layer_tt_kernel(const __grid_constant__ TtArgs a) {
                 a.stats_partial[(rr * 2 + 0) * a.cout + cg] = 0.0;
                 a.stats_partial[(rr * 2 + 1) * a.cout + cg] = 0.0;
             }
-            if (a.fix_acc != nullptr && a.counter != nullptr) {
-                // the same sums once more, for the last CTA's fast path (TtArgs::fix_acc)
+            if (a.fix_acc != nullptr) {
+                // the same sums once more, for the last CTA's fast path (TtArgs::fix_acc) -- or, deferred
+                // finalisation (no counter), for the next layer's CTAs
                 const double v2[2] = {acc_s, acc_q};
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
@@ -811,7 +834,8 @@ mlp_layer_tt_kernel(const __grid_constant__ TtArgs a) {
         const int u = ptid & 7;       // 16-byte unit inside the 128-byte chunk row
         const int rb = ptid >> 3;     // rows rb + kRowStride*j, j = 0..kRPT-1
         const uint32_t swz = (uint32_t)((u ^ (rb & 7)) << 4);
-        const bool has_act = (MODE == SRC_PLAIN && a.in_scale != nullptr) || (MODE == SRC_GATHER && a.x_colscale != nullptr);
+        const bool has_act = (MODE == SRC_PLAIN && (a.in_scale != nullptr || a.in_fix != nullptr)) ||
+                             (MODE == SRC_GATHER && a.x_colscale != nullptr);
         // the tensor-map descriptor lives in the kernel parameters: have the TMA unit fetch it while
         // this kernel still waits for the previous one (PAPC_TT_DBG=512 switches the prefetch off;
         // measured on the B200: no difference in the step time either way)
@@ -1168,7 +1192,41 @@ mlp_layer_tt_kernel(const __grid_constant__ TtArgs a) {
                 if (ti < tiles_m) { issue(ti, ci, n); advance(ti, ci); }
                 cp_async_commit();
             }
-            if (MODE == SRC_PLAIN) {
+            if (MODE == SRC_PLAIN && a.in_fix != nullptr) {
+                // deferred finalisation of the producing layer (TtArgs::in_fix): words -> scale / shift table
+                const unsigned long long *fx = a.in_fix;
+                const bool fixed = __ldcg(fx + (size_t)4 * a.cin) == 0ull;
+                for (int k = ptid; k < kMaxAct; k += kProdThreads) {
+                    float sc = 0.f, sh = 0.f;
+                    if (k < a.cin) {
+                        double sum, sq;
+                        if (fixed) {
+                            const long long si = (long long)__ldcg(fx + k), sf = (long long)__ldcg(fx + (size_t)a.cin + k);
+                            const long long qi = (long long)__ldcg(fx + (size_t)2 * a.cin + k);
+                            const long long qf = (long long)__ldcg(fx + (size_t)3 * a.cin + k);
+                            sum = (double)si + (double)sf * 0x1p-54;
+                            sq = (double)qi + (double)qf * 0x1p-54;
+                        } else {   // a sum left the fixed-point range (or is not finite): the partial rows, in order
+                            sum = 0.0; sq = 0.0;
+                            for (long long r = 0; r < a.in_partial_rows; ++r) {
+                                sum += __ldcg(a.in_partial + (r * 2 + 0) * a.cin + k);
+                                sq += __ldcg(a.in_partial + (r * 2 + 1) * a.cin + k);
+                            }
+                        }
+                        const float g = a.in_gamma ? __ldg(a.in_gamma + k) : 1.f, b = a.in_beta ? __ldg(a.in_beta + k) : 0.f;
+                        const float cs = a.in_cs ? f16_colscale_sq(g, b, a.cs_sqrt_count) : 1.f;
+                        float mean, var;
+                        bn_from_sums(sum, sq, a.in_inv_count, g, b, a.in_eps, cs, sc, sh, mean, var);
+                        if (blockIdx.x == 0) {
+                            if (a.in_mean_out) a.in_mean_out[k] = mean;
+                            if (a.in_var_out) a.in_var_out[k] = var;
+                        }
+                    }
+                    s_scale[k] = sc;
+                    s_shift[k] = sh;
+                }
+                named_bar_sync(1, kProdThreads);
+            } else if (MODE == SRC_PLAIN) {
                 for (int k = ptid; k < kMaxAct; k += kProdThreads) {
                     s_scale[k] = (has_act && k < a.cin) ? a.in_scale[k] : 0.f;
                     s_shift[k] = (has_act && k < a.cin) ? a.in_shift[k] : 0.f;
@@ -1302,25 +1360,18 @@ mlp_layer_tt_kernel(const __grid_constant__ TtArgs a) {
             // from the fp32 estimate (full double accuracy)
             const double inv_count = a.inv_count;
             for (int ch = tid; ch < a.cout; ch += kThreads) {
-                const double mean = all[ch] * inv_count;
-                double var = all[a.cout + ch] * inv_count - mean * mean;  // biased, as Paddle's training BN
-                var = var > 0.0 ? var : 0.0;
-                const double g = a.gamma ? (double)a.gamma[ch] : 1.0;
-                const double b = a.beta ? (double)a.beta[ch] : 0.0;
-                const double ve = var + (double)a.eps;
-                double rs = (double)rsqrtf((float)ve);
-                rs = rs * (1.5 - 0.5 * ve * rs * rs);
-                rs = rs * (1.5 - 0.5 * ve * rs * rs);
-                const double sc = g * rs;
+                const float g = a.gamma ? a.gamma[ch] : 1.f, b = a.beta ? a.beta[ch] : 0.f;
                 float cs = 1.f;
                 if (a.out_colscale != nullptr) {
-                    cs = f16_colscale_sq(a.gamma ? a.gamma[ch] : 1.f, a.beta ? a.beta[ch] : 0.f, a.sqrt_count);
+                    cs = f16_colscale_sq(g, b, a.sqrt_count);
                     a.out_colscale[ch] = cs;
                 }
-                a.scale[ch] = (float)sc / cs;
-                a.shift[ch] = (float)(b - mean * sc) / cs;
-                if (a.mean_out) a.mean_out[ch] = (float)mean;
-                if (a.var_out) a.var_out[ch] = (float)var;
+                float sc, sh, mean, var;
+                bn_from_sums(all[ch], all[a.cout + ch], inv_count, g, b, a.eps, cs, sc, sh, mean, var);
+                a.scale[ch] = sc;
+                a.shift[ch] = sh;
+                if (a.mean_out) a.mean_out[ch] = mean;
+                if (a.var_out) a.var_out[ch] = var;
             }
             if (tid == 0) *a.counter = 0u;  // self-cleaning for the next launch
             if (tid == 0) TT_GCLK(a, 9);   // last CTA: scale / shift written (this thread's share)

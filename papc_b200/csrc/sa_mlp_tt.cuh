@@ -70,6 +70,20 @@ struct TtArgs {
     // of reducing gridDim partial rows.  The flag is raised by a sum outside +-2^53 (or NaN): the last
     // CTA then falls back to the partial rows.
     unsigned long long *fix_acc;
+    // Deferred finalisation.  PRODUCING side: counter == nullptr with fix_acc != nullptr -- the CTAs add their sums
+    // into fix_acc (zeroed by the caller, NOT cleaned here) and nobody finalises: the kernel ends with its last
+    // tile.  CONSUMING side (SRC_PLAIN, no activation image): in_fix != nullptr -- every CTA derives the scale /
+    // shift table of its input from the producer's words (one L2 round trip that overlaps its first tile copy)
+    // with the arithmetic of the last-CTA finalisation, bit for bit; CTA 0 also writes the batch mean / variance.
+    // Removes ticket, reduction and scale / shift round trips (~5 us) from the layer-to-layer boundary.
+    const unsigned long long *in_fix;  // [4][cin] + flag word at [4*cin]
+    const double *in_partial;          // the producer's partial rows (used when the flag is raised)
+    long long in_partial_rows;
+    const float *in_gamma, *in_beta;   // BatchNorm parameters of the producing layer (nullable = 1 / 0)
+    float in_eps;
+    double in_inv_count;
+    int in_cs;                         // scale / shift divided by f16_colscale_sq(in_gamma, in_beta, cs_sqrt_count)
+    float *in_mean_out, *in_var_out;   // nullable
     const float *gamma, *beta;
     float eps;
     double count;
