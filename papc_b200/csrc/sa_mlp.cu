@@ -537,6 +537,44 @@ pool_finish_bsc_v4_kernel(const float4 *__restrict__ pmax, const float4 *__restr
     }
 }
 
+// The same with the last layer's BatchNorm finalised HERE (tt::DeferredIn): every block derives the scale / shift
+// table of the C <= 1024 channels from the layer kernel's exact sums into shared memory, block 0 also writes them
+// (and the batch mean / variance) out.  The layer kernel then ends with its last tile: no ticket, no last-CTA tail.
+constexpr int kPoolFinishMaxC = 1024;
+__global__ void __launch_bounds__(256)
+pool_finish_bsc_v4_deferred_kernel(const float4 *__restrict__ pmax, const float4 *__restrict__ pmin, size_t total4,
+                                   int C, float4 *__restrict__ out, const tt::DeferredIn d,
+                                   float *__restrict__ scale_out, float *__restrict__ shift_out) {
+    __shared__ __align__(16) float s_sc[kPoolFinishMaxC], s_sh[kPoolFinishMaxC];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    for (int k = threadIdx.x; k < C; k += blockDim.x) {
+        float sc, sh;
+        tt::deferred_scale_shift(d, C, k, blockIdx.x == 0, sc, sh);
+        s_sc[k] = sc;
+        s_sh[k] = sh;
+        if (blockIdx.x == 0) { scale_out[k] = sc; shift_out[k] = sh; }
+    }
+    __syncthreads();
+    const int C4 = C >> 2;
+    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; e < total4; e += stride) {
+        const int c = (int)(e % C4);
+        const float4 sc = reinterpret_cast<const float4 *>(s_sc)[c], sh = reinterpret_cast<const float4 *>(s_sh)[c];
+        const bool pos = sc.x >= 0.f && sc.y >= 0.f && sc.z >= 0.f && sc.w >= 0.f;   // the usual case: gamma > 0
+        const bool neg = sc.x < 0.f && sc.y < 0.f && sc.z < 0.f && sc.w < 0.f;
+        const float4 mx = neg ? make_float4(0.f, 0.f, 0.f, 0.f) : pmax[e];              // only the side that is used
+        const float4 mn = pos ? make_float4(0.f, 0.f, 0.f, 0.f) : pmin[e];
+        float4 o;
+        o.x = fmaxf(fmaf(sc.x >= 0.f ? mx.x : mn.x, sc.x, sh.x), 0.f);
+        o.y = fmaxf(fmaf(sc.y >= 0.f ? mx.y : mn.y, sc.y, sh.y), 0.f);
+        o.z = fmaxf(fmaf(sc.z >= 0.f ? mx.z : mn.z, sc.z, sh.z), 0.f);
+        o.w = fmaxf(fmaf(sc.w >= 0.f ? mx.w : mn.w, sc.w, sh.w), 0.f);
+        out[e] = o;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 pool_finish_bcs_kernel(const float *__restrict__ pmax, const float *__restrict__ pmin,
                        const float *__restrict__ scale, const float *__restrict__ shift, int S, int C,
@@ -1400,7 +1438,11 @@ extern "C" int papc_sa_mlp_f32(const papc_group_source *src, const papc_mlp *mlp
         FusedBn bn{counters + l, ly.gamma, ly.beta, mlp->eps, (double)M, sqrt_m,
                    scale, shift, ly.batch_mean, ly.batch_var, next_f16 ? colscale[l & 1] : nullptr};
         bn.fix_acc = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(counters) + 256 + (size_t)l * p.fix_stride);
-        bn.defer = defer_on && batch && !last && next_f16 && tt::ximg_bytes(M, ly.cout, mlp->layers[l + 1].cout) == 0;
+        // hidden layer: the consumer is a plain fp16-split tcgen05 launch (or its activation-image kernel);
+        // last layer: the consumer is pool_finish (channels-last output, 16-byte rows)
+        const bool pf_deferred_ok = pdl_chain_enabled() && (out_layout == PAPC_OUT_BSC || src->S == 1) && ly.cout % 4 == 0 &&
+                                    ly.cout <= kPoolFinishMaxC && aligned16(out) && aligned16(pmax) && aligned16(pmin);
+        bn.defer = defer_on && batch && (last ? pf_deferred_ok : next_f16);
         TtOpts o{this_f16 ? tt::PREC_F16 : tt::PREC_TF32,
                  this_f16 ? mlp->layers[l - 1].gamma : nullptr, this_f16 ? mlp->layers[l - 1].beta : nullptr,
                  sqrt_m, nullptr, ws + p.wimg, p.wimg_bytes, false, prev_is_kernel};
@@ -1471,6 +1513,20 @@ extern "C" int papc_sa_mlp_f32(const papc_group_source *src, const papc_mlp *mlp
         xprev = y;
         cin = ly.cout;
         prev_is_kernel = true;  // a layer kernel (or the scale / shift kernel after it)
+    }
+    if (prev_deferred) {   // the last layer left its BatchNorm to pool_finish
+        const int cl = mlp->layers[L - 1].cout;
+        const size_t total4 = (size_t)src->B * src->S * cl / 4;
+        size_t blocks = (total4 + 255) / 256;
+        if (blocks > (size_t)kNumSMs * 8) blocks = (size_t)kNumSMs * 8;
+        ProfScope prof(st, "pool_finish", (long long)src->B * src->S, 0, cl, 0.0, 12.0 * src->B * src->S * cl);
+        tt::DeferredIn d{in_bn.fix, in_bn.partial, in_bn.partial_rows, in_bn.gamma, in_bn.beta, in_bn.eps,
+                         in_bn.count > 0.0 ? 1.0 / in_bn.count : 0.0, 0, sqrt_m, in_bn.mean_out, in_bn.var_out};
+        PAPC_CUDA_TRY(launch_pdl(pool_finish_bsc_v4_deferred_kernel, dim3((unsigned)blocks), dim3(256), st,
+                                 reinterpret_cast<const float4 *>(pmax), reinterpret_cast<const float4 *>(pmin), total4, cl,
+                                 reinterpret_cast<float4 *>(out), d, scale, shift));
+        PAPC_LAUNCH_CHECK();
+        return PAPC_OK;
     }
     return papc_sa_pool_finish_f32(pmax, pmin, scale, shift, src->B, src->S,
                                    mlp->layers[L - 1].cout, out, out_layout, stream);

@@ -166,28 +166,6 @@ __device__ __forceinline__ void split_relu_f16x2(float a, float b, uint32_t &hi,
     asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
 }
 
-// BatchNorm scale / shift of one channel from its batch sums -- the one place this arithmetic lives (last-CTA
-// finalisation and the consumer-side derivation must agree bit for bit).  fp64 division and square root are long
-// software sequences on a slow pipe: reciprocal of the count from the host, 1/sqrt by two Newton steps from the
-// fp32 estimate (full double accuracy).  cs: power-of-two column scale the results are divided by (1 = none).
-__device__ __forceinline__ void bn_from_sums(double sum, double sumsq, double inv_count, float gamma, float beta,
-                                             float eps, float cs, float &scale, float &shift, float &mean_f,
-                                             float &var_f) {
-    const double mean = sum * inv_count;
-    double var = sumsq * inv_count - mean * mean;  // biased, as Paddle's training BN
-    var = var > 0.0 ? var : 0.0;
-    const double g = (double)gamma, b = (double)beta;
-    const double ve = var + (double)eps;
-    double rs = (double)rsqrtf((float)ve);
-    rs = rs * (1.5 - 0.5 * ve * rs * rs);
-    rs = rs * (1.5 - 0.5 * ve * rs * rs);
-    const double sc = g * rs;
-    scale = (float)sc / cs;
-    shift = (float)(b - mean * sc) / cs;
-    mean_f = (float)mean;
-    var_f = (float)var;
-}
-
 // Shared memory: the small fixed tables first, then the operand ring (read by the tensor core) and
 // the raw ring (fp32 activations landed by cp.async, thread-private slots), sized per instantiation.
 struct SmemLayout {
@@ -315,11 +293,25 @@ prep_wimg_kernel(const float *__restrict__ W, int wld, int wk0, int cin, int cou
 // ------------------------------------------------------------------ activation image (SRC_PLAIN, small M)
 // img: [tiles_m][KC][hi | lo][128 rows][128 B], the layout the producers write into an operand stage, holding
 // relu(in_scale[k] * x[row][k] + in_shift[k]) split into fp16 hi / lo.  Rows >= M and columns >= cin are zero.
+// d.fix != nullptr: the BatchNorm of x was deferred to this kernel (TtArgs::in_fix) -- every block derives the
+// scale / shift table into shared memory first (cin <= kMaxAct), block 0 records the batch mean / variance.
 __global__ void __launch_bounds__(256)
 prep_ximg_kernel(const float *__restrict__ x, long long M, int cin, const float *__restrict__ in_scale,
-                 const float *__restrict__ in_shift, int KC, uint8_t *__restrict__ img) {
+                 const float *__restrict__ in_shift, int KC, uint8_t *__restrict__ img, const DeferredIn d) {
     using P = Prec<PREC_F16>;
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // see prep_wimg_kernel
+    __shared__ __align__(16) float s_sc[kMaxAct], s_sh[kMaxAct];
+    if (d.fix != nullptr) {
+        for (int k = threadIdx.x; k < cin; k += blockDim.x) {
+            float sc, sh;
+            deferred_scale_shift(d, cin, k, blockIdx.x == 0, sc, sh);
+            s_sc[k] = sc;
+            s_sh[k] = sh;
+        }
+        __syncthreads();
+        in_scale = s_sc;
+        in_shift = s_sh;
+    }
     const long long tiles_m = ceil_div<long long>(M, kTile);
     const long long total = tiles_m * KC * kTile * 8;  // one 16-byte unit (8 halves) per thread step
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
@@ -1786,14 +1778,19 @@ int launch(const TtArgs &a_in, cudaStream_t st) {
     {
         static const bool ximg_off = [] { const char *e = getenv("PAPC_TT_XIMG"); return e && e[0] == '0'; }();  // A/B switch
         const size_t xb = ximg_bytes(a.M, a.cin, a.cout);
-        if (!ximg_off && a.mode == SRC_PLAIN && a.prec == PREC_F16 && a.in_scale != nullptr && a.in_shift != nullptr &&
-            a.ximg != nullptr && xb > 0 && (reinterpret_cast<uintptr_t>(a.x) & 15u) == 0 &&
-            (reinterpret_cast<uintptr_t>(a.in_scale) & 15u) == 0 && (reinterpret_cast<uintptr_t>(a.in_shift) & 15u) == 0) {
+        const bool act_tab = a.in_scale != nullptr && a.in_shift != nullptr &&
+                             (reinterpret_cast<uintptr_t>(a.in_scale) & 15u) == 0 && (reinterpret_cast<uintptr_t>(a.in_shift) & 15u) == 0;
+        if (!ximg_off && a.mode == SRC_PLAIN && a.prec == PREC_F16 && (act_tab || a.in_fix != nullptr) &&
+            a.ximg != nullptr && xb > 0 && (reinterpret_cast<uintptr_t>(a.x) & 15u) == 0) {
             const int KCx = ceil_div(a.cin, epc(a.prec));
             long long blocks = (ceil_div<long long>(a.M, kTile) * KCx * kTile * 8 + 255) / 256;
             if (blocks > 8LL * kNumSMs) blocks = 8LL * kNumSMs;
+            DeferredIn d{};
+            if (a.in_fix != nullptr)
+                d = DeferredIn{a.in_fix, a.in_partial, a.in_partial_rows, a.in_gamma, a.in_beta, a.in_eps, a.in_inv_count,
+                               a.in_cs, a.cs_sqrt_count, a.in_mean_out, a.in_var_out};
             prep_ximg_kernel<<<(unsigned)blocks, 256, 0, st>>>(a.x, a.M, a.cin, a.in_scale, a.in_shift, KCx,
-                                                               reinterpret_cast<uint8_t *>(a.ximg));
+                                                               reinterpret_cast<uint8_t *>(a.ximg), d);
             PAPC_LAUNCH_CHECK();
             a.ximg_on = 1;
             if (a.pdl == 0) { const char *e = getenv("PAPC_TT_PDL"); a.pdl = (e && e[0] == '0') ? 0 : 1; }

@@ -131,6 +131,67 @@ __host__ __device__ inline float f16_colscale_sq(float gamma, float beta, float 
     return s;
 }
 
+// Consumer side of a deferred finalisation (TtArgs::in_fix) for kernels other than the layer kernel itself
+// (pool_finish, the activation-image kernel): what they need to derive scale / shift of C channels.
+struct DeferredIn {
+    const unsigned long long *fix;   // [4][C] + flag word at [4*C]; nullptr = not deferred
+    const double *partial;           // the producer's partial rows (flag raised)
+    long long partial_rows;
+    const float *gamma, *beta;       // nullable = 1 / 0
+    float eps;
+    double inv_count;
+    int cs_on;                       // divide by f16_colscale_sq(gamma, beta, sqrt_count)
+    float sqrt_count;
+    float *mean_out, *var_out;       // nullable; written by block 0
+};
+
+#ifdef __CUDACC__
+// BatchNorm scale / shift of one channel from its batch sums -- the one place this arithmetic lives (last-CTA
+// finalisation and every consumer-side derivation must agree bit for bit).  fp64 division and square root are long
+// software sequences on a slow pipe: reciprocal of the count from the host, 1/sqrt by two Newton steps from the
+// fp32 estimate (full double accuracy).  cs: power-of-two column scale the results are divided by (1 = none).
+__device__ __forceinline__ void bn_from_sums(double sum, double sumsq, double inv_count, float gamma, float beta,
+                                             float eps, float cs, float &scale, float &shift, float &mean_f,
+                                             float &var_f) {
+    const double mean = sum * inv_count;
+    double var = sumsq * inv_count - mean * mean;  // biased, as Paddle's training BN
+    var = var > 0.0 ? var : 0.0;
+    const double g = (double)gamma, b = (double)beta;
+    const double ve = var + (double)eps;
+    double rs = (double)rsqrtf((float)ve);
+    rs = rs * (1.5 - 0.5 * ve * rs * rs);
+    rs = rs * (1.5 - 0.5 * ve * rs * rs);
+    const double sc = g * rs;
+    scale = (float)sc / cs;
+    shift = (float)(b - mean * sc) / cs;
+    mean_f = (float)mean;
+    var_f = (float)var;
+}
+// scale / shift of channel k (< C) from the producer's words; block 0 (write_stats) also records mean / variance
+__device__ __forceinline__ void deferred_scale_shift(const DeferredIn &d, int C, int k, bool write_stats, float &sc,
+                                                     float &sh) {
+    double sum, sq;
+    if (__ldcg(d.fix + (size_t)4 * C) == 0ull) {
+        sum = (double)(long long)__ldcg(d.fix + k) + (double)(long long)__ldcg(d.fix + (size_t)C + k) * 0x1p-54;
+        sq = (double)(long long)__ldcg(d.fix + (size_t)2 * C + k) + (double)(long long)__ldcg(d.fix + (size_t)3 * C + k) * 0x1p-54;
+    } else {   // a sum left the fixed-point range (or is not finite): the partial rows, in order
+        sum = 0.0; sq = 0.0;
+        for (long long r = 0; r < d.partial_rows; ++r) {
+            sum += __ldcg(d.partial + (r * 2 + 0) * C + k);
+            sq += __ldcg(d.partial + (r * 2 + 1) * C + k);
+        }
+    }
+    const float g = d.gamma ? __ldg(d.gamma + k) : 1.f, b = d.beta ? __ldg(d.beta + k) : 0.f;
+    const float cs = d.cs_on ? f16_colscale_sq(g, b, d.sqrt_count) : 1.f;
+    float mean, var;
+    bn_from_sums(sum, sq, d.inv_count, g, b, d.eps, cs, sc, sh, mean, var);
+    if (write_stats) {
+        if (d.mean_out) d.mean_out[k] = mean;
+        if (d.var_out) d.var_out[k] = var;
+    }
+}
+#endif
+
 // Moments of the centred grouped points p = xyz[b, idx] - new_xyz over all M rows, then -- in the
 // last block -- BatchNorm statistics of y0 = W0 p + b0 derived analytically in fp64
 // (mean = W0 mu + b0, var = W0 Cov W0^T), the resulting scale / shift and the folded first layer.
