@@ -749,6 +749,10 @@ def nms_block(torch, dev, timeit):
                 mine = keep[:k].cpu().numpy().tolist()
                 blk["reference"] = {"ms": 1e3 * float(np.median(t)), "kind": "reference",
                                     "same_keep_list": bool(list(map(int, r)) == mine),
+                                    # boxes with EQUAL scores: the reference orders them by numpy's default (unstable)
+                                    # argsort, this library by the stable order -- the kept SET is what is comparable
+                                    "same_keep_set": bool(sorted(map(int, r)) == sorted(mine)),
+                                    "duplicated_scores": int(d.shape[0] - len(np.unique(d[:, -1]))),
                                     "sample": "the reference's own numba.cuda kernels + host suppress loop (nms_gpu.py, "
                                               "unmodified, oracle/_ref), NumPy in -> list out, median of 3 calls"}
             except Exception as e:  # noqa: BLE001

@@ -12,7 +12,8 @@
 //                     (the reference recomputes cos / sin for every pair);
 //   nms_scan_kernel   the suppress scan on the device: one CTA walks the 64-box blocks, a single thread resolves
 //                     the in-block dependencies on the diagonal mask words, all threads OR the kept rows into
-//                     the removal bitmap; the kept ORIGINAL indices and their count stay on the device.
+//                     the removal bitmap (16 independent row loads per thread); the kept ORIGINAL indices and
+//                     their count stay on the device.
 // Arithmetic: IEEE fp32, every operation separately rounded (this file is compiled with -fmad=false), in the
 // reference's order; cos / sin in double, rounded to float -- identical to oracle/nms_oracle.c, so keep lists
 // and IoU values are compared bit for bit.
@@ -167,26 +168,34 @@ nms_rank_kernel(const float *__restrict__ dets, int n, int stride, int32_t *__re
 }
 
 // ------------------------------------------------------------------ suppression mask (upper triangle)
+// 256 threads per 64 x 64 tile: thread = (row, quarter of the columns), the four 16-bit parts of a row's mask word
+// meet in shared memory -- four times the warps per tile of the one-thread-per-row form (the rotated IoU is a long
+// serial polygon clip per pair; a 1000-box call has only 136 tiles for 148 SMs).
+constexpr int kMaskThreads = 4 * kNmsTile;
 template <bool ROT>
-__global__ void __launch_bounds__(kNmsTile)
+__global__ void __launch_bounds__(kMaskThreads)
 nms_mask_kernel(const float *__restrict__ dets, const int32_t *__restrict__ order, int n, float thresh,
                 unsigned long long *__restrict__ mask) {
     const int col_start = blockIdx.x, row_start = blockIdx.y;
     if (col_start < row_start) return;     // never read by the scan
-    const int tx = threadIdx.x;
+    const int tx = threadIdx.x & (kNmsTile - 1), part = threadIdx.x >> 6;
     const int row_size = min(n - row_start * kNmsTile, kNmsTile);
     const int col_size = min(n - col_start * kNmsTile, kNmsTile);
     const int col_blocks = ceil_div(n, kNmsTile);
     constexpr int W = ROT ? 9 : 4;   // rotated: 8 corner floats + area; plain: the 4 box coordinates
     __shared__ float s_box[kNmsTile * W];
-    if (tx < col_size) {
-        const float *b = dets + (size_t)order[col_start * kNmsTile + tx] * (ROT ? 6 : 5);
-        if (ROT) {
-            rbbox_to_corners(s_box + tx * W, b);
-            s_box[tx * W + 8] = b[2] * b[3];
-        } else {
+    __shared__ unsigned long long s_word[kNmsTile];
+    if (part == 0) {
+        s_word[tx] = 0ull;
+        if (tx < col_size) {
+            const float *b = dets + (size_t)order[col_start * kNmsTile + tx] * (ROT ? 6 : 5);
+            if (ROT) {
+                rbbox_to_corners(s_box + tx * W, b);
+                s_box[tx * W + 8] = b[2] * b[3];
+            } else {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) s_box[tx * W + q] = b[q];
+                for (int q = 0; q < 4; ++q) s_box[tx * W + q] = b[q];
+            }
         }
     }
     __syncthreads();
@@ -203,14 +212,17 @@ nms_mask_kernel(const float *__restrict__ dets, const int32_t *__restrict__ orde
             for (int q = 0; q < 4; ++q) mine[q] = b[q];
         }
         unsigned long long t = 0ull;
-        const int start = (row_start == col_start) ? tx + 1 : 0;
-        for (int i = start; i < col_size; ++i) {
+        const int start = max((row_start == col_start) ? tx + 1 : 0, part * 16);
+        const int stop = min(col_size, part * 16 + 16);
+        for (int i = start; i < stop; ++i) {
             const float v = ROT ? rotate_iou_corners(mine, my_area, s_box + i * W, s_box[i * W + 8], -1)
                                 : iou_device(mine, s_box + i * W);
             if (v > thresh) t |= 1ull << i;
         }
-        mask[(size_t)cur * col_blocks + col_start] = t;
+        if (t != 0ull) atomicOr(s_word + tx, t);
     }
+    __syncthreads();
+    if (part == 0 && tx < row_size) mask[(size_t)(row_start * kNmsTile + tx) * col_blocks + col_start] = s_word[tx];
 }
 
 // ------------------------------------------------------------------ suppress scan (nms_postprocess :111-130)
@@ -243,15 +255,23 @@ nms_scan_kernel(const unsigned long long *__restrict__ mask, const int32_t *__re
         const unsigned long long kept = s_kept;
         if (tid < rows && ((kept >> tid) & 1ull))
             keep[base + __popcll(kept & ((1ull << tid) - 1ull))] = order[b * kNmsTile + tid];
-        for (int j = b + 1 + tid; j < col_blocks; j += kScanThreads) {
-            unsigned long long acc = s_remv[j];
-            unsigned long long k = kept;
-            while (k) {
-                const int t = __ffsll((long long)k) - 1;
-                k &= k - 1;
-                acc |= mask[(size_t)(b * kNmsTile + t) * col_blocks + j];
+        // OR the mask rows of the kept boxes into the removal bitmap.  Thread = (word j, slice of 16 rows): the
+        // rows of a slice are independent predicated loads, all in flight together (one L2 round trip per block
+        // of 64 boxes instead of a chain of up to 64), the four slices meet in shared memory.
+        for (int j0 = b + 1; j0 < col_blocks; j0 += kNmsTile) {
+            const int j = j0 + (tid & (kNmsTile - 1));
+            const int sl = tid >> 6;                       // kScanThreads / kNmsTile = 4 slices
+            unsigned long long acc = 0ull;
+            if (j < col_blocks) {
+                const unsigned long long *mrow = mask + (size_t)(b * kNmsTile + sl * 16) * col_blocks + j;
+                unsigned long long v[16];
+#pragma unroll
+                for (int t = 0; t < 16; ++t)
+                    v[t] = ((kept >> (sl * 16 + t)) & 1ull) ? mrow[(size_t)t * col_blocks] : 0ull;
+#pragma unroll
+                for (int t = 0; t < 16; ++t) acc |= v[t];
+                if (acc != 0ull) atomicOr(s_remv + j, acc);
             }
-            s_remv[j] = acc;
         }
         base += __popcll(kept);
     }
@@ -316,8 +336,8 @@ extern "C" int papc_nms_f32(const float *dets, int n, int box_dim, float thresh,
     nms_rank_kernel<<<ceil_div(n, 256), 256, 0, st>>>(dets, n, box_dim, order);
     PAPC_LAUNCH_CHECK();
     dim3 grid(cb, cb);
-    if (box_dim == 6) nms_mask_kernel<true><<<grid, kNmsTile, 0, st>>>(dets, order, n, thresh, mask);
-    else nms_mask_kernel<false><<<grid, kNmsTile, 0, st>>>(dets, order, n, thresh, mask);
+    if (box_dim == 6) nms_mask_kernel<true><<<grid, kMaskThreads, 0, st>>>(dets, order, n, thresh, mask);
+    else nms_mask_kernel<false><<<grid, kMaskThreads, 0, st>>>(dets, order, n, thresh, mask);
     PAPC_LAUNCH_CHECK();
     nms_scan_kernel<<<1, kScanThreads, (size_t)cb * sizeof(unsigned long long), st>>>(mask, order, n, keep_out, num_out);
     PAPC_LAUNCH_CHECK();
