@@ -231,6 +231,37 @@ def test_fp16_split_column_scale_large_gamma():
     np.testing.assert_allclose(gp.cpu().numpy(), rp, **TOL)
 
 
+@pytest.mark.parametrize("cfg", ["ssg_sa1", "ssg_sa2"])
+def test_statistics_outside_the_fixed_point_range(cfg):
+    """A convolution bias large enough that the per-channel sums of squares exceed 2^53 (32 768 rows x (6e5)^2):
+    the layer kernels raise the flag of their exact fixed-point statistic words and every consumer of a deferred
+    BatchNorm finalisation (the next layer kernel, pool_finish) must fall back to the fp64 partial rows.  The
+    pre-BN values sit at 6e5 +- 1e4, where fp32 resolves 0.06: both sides (the oracle computes the layer in fp32 as
+    the reference does) lose digits in y - mean over three layers.  This is a test of the fallback PATH, bound
+    2e-3 (measured 5e-4); the 1e-5 parity bound is tested everywhere else."""
+    rng = np.random.default_rng(21)
+    B, N = 8, 512
+    xyz = synth.clouds(B, N, seed=13)
+    start = synth.fps_start(B, N, seed=14)
+    if cfg == "ssg_sa1":
+        D, args = 0, (128, 0.2, 32, 3, [64, 64, 128], False)
+    else:
+        D, args = 128, (64, 0.4, 64, 131, [128, 128, 256], False)
+    feats = rng.standard_normal((B, D, N)).astype(np.float32) if D else None
+    gpu, ref = layers.PointNetSetAbstraction(*args), layers_np.PointNetSetAbstraction(*args)
+    params = synth.mlp_params(args[3], args[4], seed=15)
+    for p in params:
+        p["weight"] = (p["weight"] * np.float32(1e4)).astype(np.float32)
+        p["bias"] = np.full_like(p["bias"], 6e5)
+    _set_params(gpu.mlp_convs, gpu.mlp_bns, ref.mlp_convs, ref.mlp_bns, params, rng)
+    gpu.to(DEV)
+    gx, gp = gpu(_cu(xyz), _cu(feats) if D else None, start_idx=_cu(start))
+    rx, rp = ref(xyz, feats, start_idx=start)
+    assert np.isfinite(gp.cpu().numpy()).all()
+    np.testing.assert_array_equal(gx.cpu().numpy(), rx)
+    np.testing.assert_allclose(gp.cpu().numpy(), rp, rtol=2e-3, atol=2e-3)
+
+
 def test_ssg_stack_c2_full_size_vs_oracle():
     """BASELINE config 2 at full size (B=32, N=1024, the three SSG SetAbstraction layers of
     PointNet2_SSG_Clas, classify/pointnet2/pointnet2.py:11-16) against the oracle."""
