@@ -548,13 +548,7 @@ pool_finish_bsc_v4_deferred_kernel(const float4 *__restrict__ pmax, const float4
     __shared__ __align__(16) float s_sc[kPoolFinishMaxC], s_sh[kPoolFinishMaxC];
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    for (int k = threadIdx.x; k < C; k += blockDim.x) {
-        float sc, sh;
-        tt::deferred_scale_shift(d, C, k, blockIdx.x == 0, sc, sh);
-        s_sc[k] = sc;
-        s_sh[k] = sh;
-        if (blockIdx.x == 0) { scale_out[k] = sc; shift_out[k] = sh; }
-    }
+    tt::deferred_table<kPoolFinishMaxC / 256>(d, C, threadIdx.x, 256, blockIdx.x == 0, s_sc, s_sh, scale_out, shift_out);
     __syncthreads();
     const int C4 = C >> 2;
     size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -302,12 +302,7 @@ prep_ximg_kernel(const float *__restrict__ x, long long M, int cin, const float 
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // see prep_wimg_kernel
     __shared__ __align__(16) float s_sc[kMaxAct], s_sh[kMaxAct];
     if (d.fix != nullptr) {
-        for (int k = threadIdx.x; k < cin; k += blockDim.x) {
-            float sc, sh;
-            deferred_scale_shift(d, cin, k, blockIdx.x == 0, sc, sh);
-            s_sc[k] = sc;
-            s_sh[k] = sh;
-        }
+        deferred_table<kMaxAct / 256>(d, cin, threadIdx.x, 256, blockIdx.x == 0, s_sc, s_sh, nullptr, nullptr);
         __syncthreads();
         in_scale = s_sc;
         in_shift = s_sh;

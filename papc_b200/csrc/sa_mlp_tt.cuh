@@ -167,27 +167,54 @@ __device__ __forceinline__ void bn_from_sums(double sum, double sumsq, double in
     mean_f = (float)mean;
     var_f = (float)var;
 }
-// scale / shift of channel k (< C) from the producer's words; block 0 (write_stats) also records mean / variance
-__device__ __forceinline__ void deferred_scale_shift(const DeferredIn &d, int C, int k, bool write_stats, float &sc,
-                                                     float &sh) {
-    double sum, sq;
-    if (__ldcg(d.fix + (size_t)4 * C) == 0ull) {
-        sum = (double)(long long)__ldcg(d.fix + k) + (double)(long long)__ldcg(d.fix + (size_t)C + k) * 0x1p-54;
-        sq = (double)(long long)__ldcg(d.fix + (size_t)2 * C + k) + (double)(long long)__ldcg(d.fix + (size_t)3 * C + k) * 0x1p-54;
-    } else {   // a sum left the fixed-point range (or is not finite): the partial rows, in order
-        sum = 0.0; sq = 0.0;
-        for (long long r = 0; r < d.partial_rows; ++r) {
-            sum += __ldcg(d.partial + (r * 2 + 0) * C + k);
-            sq += __ldcg(d.partial + (r * 2 + 1) * C + k);
+// The scale / shift table of C <= NPT * nthreads channels into shared memory, one block: every global load of a
+// thread's channels (statistic words, flag, gamma, beta) is issued before the first is used -- ONE L2 round trip
+// for the whole table instead of one per channel and stage (this sits on the step's critical path: the kernel's
+// input only exists once the previous kernel has ended).  scale_out / shift_out / mean / var: written when
+// write_stats (block 0).
+template <int NPT>
+__device__ __forceinline__ void deferred_table(const DeferredIn &d, int C, int tid, int nthreads, bool write_stats,
+                                               float *s_sc, float *s_sh, float *scale_out, float *shift_out) {
+    unsigned long long w[NPT][4];
+    float g[NPT], b[NPT];
+#pragma unroll
+    for (int j = 0; j < NPT; ++j) {
+        const int k = tid + j * nthreads;
+        g[j] = 1.f; b[j] = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) w[j][q] = k < C ? __ldcg(d.fix + (size_t)q * C + k) : 0ull;
+        if (k < C) {
+            if (d.gamma) g[j] = __ldg(d.gamma + k);
+            if (d.beta) b[j] = __ldg(d.beta + k);
         }
     }
-    const float g = d.gamma ? __ldg(d.gamma + k) : 1.f, b = d.beta ? __ldg(d.beta + k) : 0.f;
-    const float cs = d.cs_on ? f16_colscale_sq(g, b, d.sqrt_count) : 1.f;
-    float mean, var;
-    bn_from_sums(sum, sq, d.inv_count, g, b, d.eps, cs, sc, sh, mean, var);
-    if (write_stats) {
-        if (d.mean_out) d.mean_out[k] = mean;
-        if (d.var_out) d.var_out[k] = var;
+    const bool fixed = __ldcg(d.fix + (size_t)4 * C) == 0ull;
+#pragma unroll
+    for (int j = 0; j < NPT; ++j) {
+        const int k = tid + j * nthreads;
+        if (k >= C) continue;
+        double sum, sq;
+        if (fixed) {
+            sum = (double)(long long)w[j][0] + (double)(long long)w[j][1] * 0x1p-54;
+            sq = (double)(long long)w[j][2] + (double)(long long)w[j][3] * 0x1p-54;
+        } else {   // a sum left the fixed-point range (or is not finite): the partial rows, in order
+            sum = 0.0; sq = 0.0;
+            for (long long r = 0; r < d.partial_rows; ++r) {
+                sum += __ldcg(d.partial + (r * 2 + 0) * C + k);
+                sq += __ldcg(d.partial + (r * 2 + 1) * C + k);
+            }
+        }
+        const float cs = d.cs_on ? f16_colscale_sq(g[j], b[j], d.sqrt_count) : 1.f;
+        float sc, sh, mean, var;
+        bn_from_sums(sum, sq, d.inv_count, g[j], b[j], d.eps, cs, sc, sh, mean, var);
+        s_sc[k] = sc;
+        s_sh[k] = sh;
+        if (write_stats) {
+            if (scale_out) scale_out[k] = sc;
+            if (shift_out) shift_out[k] = sh;
+            if (d.mean_out) d.mean_out[k] = mean;
+            if (d.var_out) d.var_out[k] = var;
+        }
     }
 }
 #endif
