@@ -21,7 +21,8 @@
  *     before anything is launched.  papc_status_string() names a code.
  *   - Re-entrant: no global mutable state; concurrent calls on distinct streams/workspaces
  *     are safe.  A few environment variables are read as kernel-selection A/B switches
- *     (PAPC_MLP_TC, PAPC_CHAIN, PAPC_TT_PDL, PAPC_TT_TMA2D, PAPC_FPS_WIDE): every setting gives
+ *     (PAPC_MLP_TC, PAPC_CHAIN, PAPC_TT_PDL, PAPC_TT_TMA2D, PAPC_TT_XIMG, PAPC_TT_PAIR, PAPC_TT_DEFER,
+ *     PAPC_FPS_WIDE): every setting gives
  *     the same results within the stated tolerances.  Switches that change results exist in
  *     triage builds only (-DPAPC_TRIAGE / -DPAPC_TT_TRIAGE).
  */

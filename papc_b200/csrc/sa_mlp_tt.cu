@@ -182,16 +182,22 @@ struct SmemLayout {
     static constexpr uint32_t misc = bars + nbars * 8;               // tmem slot, last-CTA flag
     static constexpr uint32_t ring = (misc + 16 + 1023) / 1024 * 1024;  // operand ring (1024-aligned)
 };
-template <int MODE, int PREC, int WMODE>
+#ifndef PAPC_TT_PAIR_STAGES
+#define PAPC_TT_PAIR_STAGES 3
+#define PAPC_TT_PAIR_RAW 3
+#endif
+template <int MODE, int PREC, int WMODE, bool PAIR = false>
 struct Cfg {
     static constexpr int kNV = Prec<PREC>::kEPU / 4;                 // 16-byte loads per row per chunk
     static constexpr int kStageBytes = WMODE ? 2 * kXBytes : kXBytes;  // [X hi][X lo]([W hi][W lo])
     static constexpr int kRawStageBytes =
         MODE == SRC_POINTMLP ? 0 : kProdThreads * 16 * (kRPT * kNV) + (MODE == SRC_GATHER ? kTile * 4 * 6 : 0);
     // operand stages / raw stages (cp.async groups in flight per thread = kRawStages - 1)
-    static constexpr int kStages = MODE == SRC_POINTMLP ? 6 : WMODE ? 2 : (PREC == PREC_F16 || MODE == SRC_GATHER) ? 3 : 4;
+    static constexpr int kStages = PAIR ? PAPC_TT_PAIR_STAGES
+                                   : MODE == SRC_POINTMLP ? 6 : WMODE ? 2 : (PREC == PREC_F16 || MODE == SRC_GATHER) ? 3 : 4;
     static constexpr int kRawStages =
-        MODE == SRC_POINTMLP ? 0 : (PREC == PREC_F16 ? (WMODE ? 2 : 3) : (MODE == SRC_GATHER && WMODE) ? 3 : 4);
+        PAIR ? PAPC_TT_PAIR_RAW
+             : MODE == SRC_POINTMLP ? 0 : (PREC == PREC_F16 ? (WMODE ? 2 : 3) : (MODE == SRC_GATHER && WMODE) ? 3 : 4);
     static constexpr uint32_t raw = SmemLayout::ring + kStages * kStageBytes;
     static constexpr uint32_t total = raw + kRawStages * kRawStageBytes;
     static constexpr uint32_t bytes = total + 1024;  // + alignment slack
@@ -349,7 +355,7 @@ template <int MODE, int PREC, int WMODE, bool POOL, bool PAIR = false>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_layer_tt_kernel(const __grid_constant__ TtArgs a) {
     using P = Prec<PREC>;
-    using CF = Cfg<MODE, PREC, WMODE>;
+    using CF = Cfg<MODE, PREC, WMODE, PAIR>;
     static_assert(!PAIR || (MODE == SRC_PLAIN && WMODE == 0), "paired channel tiles: plain source, resident W");
     constexpr int kChT = PAIR ? 2 : 1;                        // channel tiles per CTA
     // tensor-memory columns of channel tile h: W hi / lo (PAIR: 64 columns each)
@@ -1637,7 +1643,7 @@ static int launch_inst(const TtArgs &a, int grid, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
         PAPC_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)Cfg<MODE, PREC, WMODE>::bytes));
+                                           (int)Cfg<MODE, PREC, WMODE, PAIR>::bytes));
         configured = true;
     }
     char name[56];
@@ -1653,7 +1659,7 @@ static int launch_inst(const TtArgs &a, int grid, cudaStream_t st) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)grid);
         cfg.blockDim = dim3(kThreads);
-        cfg.dynamicSmemBytes = Cfg<MODE, PREC, WMODE>::bytes;
+        cfg.dynamicSmemBytes = Cfg<MODE, PREC, WMODE, PAIR>::bytes;
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -1664,7 +1670,7 @@ static int launch_inst(const TtArgs &a, int grid, cudaStream_t st) {
         PAPC_CUDA_TRY(cudaLaunchKernelEx(&cfg, k, a));
         return PAPC_OK;
     }
-    k<<<grid, kThreads, Cfg<MODE, PREC, WMODE>::bytes, st>>>(a);
+    k<<<grid, kThreads, Cfg<MODE, PREC, WMODE, PAIR>::bytes, st>>>(a);
     PAPC_LAUNCH_CHECK();
     return PAPC_OK;
 }

@@ -144,6 +144,8 @@ def _set_params(gpu_convs, gpu_bns, ref_convs, ref_bns, params, rng):
 
 
 @pytest.mark.parametrize("B,S,K,cin,mlp", [(2, 16, 32, 3, [64, 64, 128]), (2, 8, 64, 131, [128, 128, 256]),
+                                           # 20 480 rows: paired channel tiles with a ragged second tile (cout = 192)
+                                           (4, 80, 64, 20, [64, 192]), (4, 80, 64, 20, [128, 256, 64]),
                                            (3, 1, 128, 259, [256, 512, 1024]), (2, 5, 12, 10, [20, 36]),
                                            (1, 3, 7, 6, [9]), (2, 4, 256, 19, [32, 48])])
 def test_grouped_mlp_explicit_input(B, S, K, cin, mlp):
