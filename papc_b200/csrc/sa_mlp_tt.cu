@@ -182,6 +182,9 @@ struct SmemLayout {
     static constexpr uint32_t misc = bars + nbars * 8;               // tmem slot, last-CTA flag
     static constexpr uint32_t ring = (misc + 16 + 1023) / 1024 * 1024;  // operand ring (1024-aligned)
 };
+#ifndef PAPC_TT_PM_STAGES
+#define PAPC_TT_PM_STAGES 6
+#endif
 #ifndef PAPC_TT_PAIR_STAGES
 #define PAPC_TT_PAIR_STAGES 3
 #define PAPC_TT_PAIR_RAW 3
@@ -194,7 +197,7 @@ struct Cfg {
         MODE == SRC_POINTMLP ? 0 : kProdThreads * 16 * (kRPT * kNV) + (MODE == SRC_GATHER ? kTile * 4 * 6 : 0);
     // operand stages / raw stages (cp.async groups in flight per thread = kRawStages - 1)
     static constexpr int kStages = PAIR ? PAPC_TT_PAIR_STAGES
-                                   : MODE == SRC_POINTMLP ? 6 : WMODE ? 2 : (PREC == PREC_F16 || MODE == SRC_GATHER) ? 3 : 4;
+                                   : MODE == SRC_POINTMLP ? PAPC_TT_PM_STAGES : WMODE ? 2 : (PREC == PREC_F16 || MODE == SRC_GATHER) ? 3 : 4;
     static constexpr int kRawStages =
         PAIR ? PAPC_TT_PAIR_RAW
              : MODE == SRC_POINTMLP ? 0 : (PREC == PREC_F16 ? (WMODE ? 2 : 3) : (MODE == SRC_GATHER && WMODE) ? 3 : 4);
