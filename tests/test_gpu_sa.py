@@ -265,6 +265,36 @@ def test_statistics_outside_the_fixed_point_range(cfg):
     np.testing.assert_allclose(gp.cpu().numpy(), rp, rtol=3e-2, atol=3e-2)
 
 
+@pytest.mark.parametrize("cfg", ["ssg_sa1", "ssg_sa2", "group_all"])
+def test_running_statistics_of_every_layer(cfg):
+    """update_running_stats: the batch mean / variance of every MLP layer.  With the deferred BatchNorm
+    finalisation they are written by whoever finalises the layer -- the next layer kernel's CTA 0, block 0 of the
+    activation-image kernel (group_all: small M), block 0 of pool_finish (last layer), the moments kernel (folded
+    first layer) -- so each writer is checked against the oracle's running buffers."""
+    rng = np.random.default_rng(31)
+    B, N = 4, 512
+    xyz = synth.clouds(B, N, seed=23)
+    start = synth.fps_start(B, N, seed=24)
+    if cfg == "ssg_sa1":
+        D, args = 0, (128, 0.2, 32, 3, [64, 64, 128], False)
+    elif cfg == "ssg_sa2":
+        D, args = 128, (64, 0.4, 64, 131, [128, 128, 256], False)
+    else:
+        D, args = 256, (None, None, None, 259, [256, 512, 1024], True)
+    feats = rng.standard_normal((B, D, N)).astype(np.float32) if D else None
+    gpu, ref = layers.PointNetSetAbstraction(*args), layers_np.PointNetSetAbstraction(*args)
+    _set_params(gpu.mlp_convs, gpu.mlp_bns, ref.mlp_convs, ref.mlp_bns, synth.mlp_params(args[3], args[4], seed=25), rng)
+    gpu.update_running_stats = True
+    gpu.to(DEV)
+    gx, gp = gpu(_cu(xyz), _cu(feats) if D else None, start_idx=_cu(start))
+    rx, rp = ref(xyz, feats, start_idx=start)
+    np.testing.assert_allclose(gp.cpu().numpy(), rp, **TOL)
+    for l, (g, r) in enumerate(zip(gpu.mlp_bns, ref.mlp_bns)):
+        np.testing.assert_allclose(g._mean.cpu().numpy(), r._mean, rtol=1e-5, atol=1e-6, err_msg=f"running mean, layer {l}")
+        np.testing.assert_allclose(g._variance.cpu().numpy(), r._variance, rtol=1e-5, atol=1e-6,
+                                   err_msg=f"running variance, layer {l}")
+
+
 def test_ssg_stack_c2_full_size_vs_oracle():
     """BASELINE config 2 at full size (B=32, N=1024, the three SSG SetAbstraction layers of
     PointNet2_SSG_Clas, classify/pointnet2/pointnet2.py:11-16) against the oracle."""
