@@ -60,6 +60,38 @@ def test_pure_host_queries(built):
     assert lib.papc_voxelize_f32(None, 5, 2, vs, cr, 5, 1, 10, None, None, None, None, None, 0, None) == -1
 
 
+def test_sa_mlp_workspace_plan_on_the_host(built):
+    """papc_sa_mlp_workspace_bytes is pure host arithmetic: it covers the two activation buffers, the pooled
+    extrema, TWO partial-row buffers (layers alternate, a deferred BatchNorm finalisation reads the previous
+    layer's) and ONE statistic slot per layer, and rejects a malformed MLP."""
+    from papc_b200 import _lib
+    lib = _lib.lib()
+
+    def ws_bytes(B, S, K, D, couts, chain_free=True):
+        src = _lib.GroupSource()
+        src.B, src.N, src.S, src.K, src.D, src.order = B, 1024, S, K, D, _lib.XYZ_FIRST
+        src.xyz = 256   # non-null placeholders: the size query never dereferences them
+        src.idx = 256
+        if D:
+            src.feats = 256
+        mlp = _lib.Mlp()
+        mlp.num_layers, mlp.cin, mlp.bn_mode, mlp.eps = len(couts), 3 + D, _lib.BN_BATCH, 1e-5
+        for l, c in enumerate(couts):
+            mlp.layers[l].cout = c
+            mlp.layers[l].weight = 256
+        return lib.papc_sa_mlp_workspace_bytes(ctypes.byref(src), ctypes.byref(mlp))
+
+    M = 32 * 128 * 64
+    b3 = ws_bytes(32, 128, 64, 128, [128, 128, 256])
+    rows = lib.papc_mlp_stats_partial_rows(M)
+    lower = 2 * M * 128 * 4 + 2 * (32 * 128) * 256 * 4 + 2 * rows * 2 * 256 * 8 + 3 * (4 * 256 + 8) * 8
+    assert lower <= b3 < lower + (8 << 20)
+    # one more hidden layer of the same width: exactly one more statistic slot (nothing else grows)
+    b4 = ws_bytes(32, 128, 64, 128, [128, 128, 128, 256])
+    assert abs((b4 - b3) - (4 * 256 + 8) * 8) < 256   # (regions are 256-byte aligned)
+    assert ws_bytes(32, 128, 64, 128, []) == 0 and ws_bytes(32, 128, 64, 128, [128, 0]) == 0
+
+
 def test_no_cpu_fallback():
     import torch
     from papc_b200 import _lib, layers
